@@ -1,0 +1,183 @@
+/*
+ * radnet_b200.h - C ABI of libradnet_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (Swedish-Rock-Art-Research-Archives/rock-art-radnet) has no FFI:
+ * its proposal / RoI hot path is plain Python + NumPy (+ one Keras layer).  This
+ * header is therefore the boundary the *replacement* binds: the Python package
+ * `rock_art_radnet_b200` keeps the reference's function names and array layouts
+ * and calls these entry points through ctypes.  Each entry
+ * point names the reference interface (file:line under the reference tree) whose
+ * arithmetic it takes over.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no C++ or torch types.
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with
+ *     `h_` (host).  Buffers are caller-allocated; sizes of scratch areas come
+ *     from the matching `*_workspace_bytes` function.
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous with
+ *     respect to the host.  The library keeps no global device state.
+ *   - return value: 0 = RADNET_OK, negative = RADNET_E_*.  Nothing throws.
+ *     `radnet_last_error_string()` returns a thread-local description.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with RADNET_E_CUDA.
+ */
+#ifndef RADNET_B200_H
+#define RADNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RADNET_ABI_VERSION 1
+
+enum {
+    RADNET_OK = 0,
+    RADNET_E_INVALID = -1,   /* bad argument (null pointer, size out of range)   */
+    RADNET_E_CUDA = -2,      /* CUDA runtime error, see radnet_last_error_string */
+    RADNET_E_WORKSPACE = -3, /* workspace too small                              */
+    RADNET_E_UNSUPPORTED = -4
+};
+
+/* Per-panel detection record written by radnet_sort_nms_i32 and exchanged between
+ * ranks (one NCCL gather per batch).  A record is
+ *   int32 header[4] = {count, n_candidates, n_score_ties, reserved}
+ *   int32 boxes [max_boxes][4]   x1,y1,x2,y2 in feature cells, score-descending
+ *   float scores[max_boxes]
+ *   int32 index [max_boxes]      flat anchor index a*H*W + r*W + c of each kept box
+ * padded to a multiple of 16 bytes; radnet_det_record_bytes gives the stride.
+ * Rows >= count are zero. */
+size_t radnet_det_record_bytes(int max_boxes);
+
+int radnet_version(void);
+const char *radnet_last_error_string(void);
+const char *radnet_error_name(int code);
+/* Device facts used by the host to size launches: out[0]=SM count, out[1]=max opt-in
+ * shared memory per block, out[2]=compute capability major*10+minor. */
+int radnet_device_info(int *h_out3);
+
+/* ---------------------------------------------------------------- K1: decode + clip
+ * Replaces the anchor loop of rpn_to_roi (reference faster_rcnn/rpn.py:91-166) and
+ * apply_regr_np (rpn.py:299-344) for a batch of B panels.
+ *   cls   [B][H][W][A]    float32 objectness           (rpn.py:75-77)
+ *   regr  [B][H][W][4A]   float32 (tx,ty,tw,th) per anchor (rpn.py:78-80)
+ *   h_anchor_wh [A][2]    float64 anchor (w,h) in feature cells, i.e.
+ *                         scale*ratio/rpn_stride evaluated by the caller (rpn.py:112-113)
+ *   std_scaling           divisor applied in float32 (rpn.py:91)
+ *   use_regr              0 = anchors only (rpn.py:133)
+ * Outputs, anchor-major flat order i = a*H*W + r*W + c (rpn.py:154-155):
+ *   boxes_i32 [B][N][4]   x1,y1,x2,y2 after round/min-size/clip, as int32 (use_regr=1:
+ *                         always integer valued; use_regr=0: only valid when every
+ *                         anchor half-size is an integer, else use the f64 variant)
+ *   keys      [B][N]      order-preserving uint32 image of the score; 0 marks a box the
+ *                         reference deletes as degenerate (rpn.py:163-166)
+ *   stats     [B][4]      int32 {n_valid, n_nonfinite, n_round_near_ties, n_noninteger}
+ */
+int radnet_decode_clip_i32(const float *cls, const float *regr, int B, int H, int W, int A,
+                           const double *h_anchor_wh, float std_scaling, int use_regr,
+                           int32_t *boxes_i32, uint32_t *keys, int32_t *stats, void *stream);
+
+/* Same arithmetic, float64 boxes + float32 scores + validity bytes (general path and the
+ * parity surface for decoded boxes).  boxes_f64 [B][N][4], scores [B][N], valid [B][N]. */
+int radnet_decode_clip_f64(const float *cls, const float *regr, int B, int H, int W, int A,
+                           const double *h_anchor_wh, float std_scaling, int use_regr,
+                           double *boxes_f64, float *scores, uint8_t *valid, int32_t *stats,
+                           void *stream);
+
+/* apply_regr_np(X, T) (rpn.py:299-344): X [4][n] float64 (x,y,w,h planes), T [4][n]
+ * float64 (tx,ty,tw,th planes; the float32 regression map widened exactly by the caller)
+ * -> out [4][n] float64 (x1,y1,w1,h1 rounded half-even). */
+int radnet_apply_regr(const double *X, const double *T, long long n, double *out, void *stream);
+
+/* ------------------------------------------------- K2: segmented score sort + greedy NMS
+ * Replaces non_max_suppression_fast on the rpn_to_roi path (rpn.py:380-456, called at
+ * rpn.py:170) for B independent panels (segments) of N candidates each.  One CTA per
+ * panel: radix sort of the keys (ties: higher flat index first), then exact greedy
+ * suppression `inter/(union+1e-6) > thr` (rpn.py:443-447) with a stop at max_boxes
+ * (rpn.py:449-450).  Integer boxes make inter/union exact; the float64 predicate is
+ * tabulated per union value at kernel start, so the decision is bit-exact.
+ *   boxes_i32 [B][N][4], keys [B][N] as produced by radnet_decode_clip_i32
+ *   map_h,map_w  feature-map size (bounds the union table: 2*(H-1)*(W-1) entries)
+ *   det        B records (layout above), record stride radnet_det_record_bytes(max_boxes)
+ *   ws         scratch of radnet_sort_nms_i32_workspace_bytes(B,N,map_h,map_w,max_boxes)
+ */
+size_t radnet_sort_nms_i32_workspace_bytes(int B, int N, int map_h, int map_w, int max_boxes);
+int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *keys, int B, int N,
+                        int map_h, int map_w, double thr, int max_boxes, void *det,
+                        void *ws, size_t ws_bytes, void *stream);
+
+/* General non_max_suppression_fast(boxes, probs, overlap_thresh, max_boxes)
+ * (rpn.py:380-456; other call sites RADNet.py:574,639,698): float64 boxes of any
+ * magnitude, float64 scores, float64 IoU arithmetic in the reference's association
+ * order.  One segment of M boxes.
+ *   boxes [M][4] float64, probs [M] float64
+ *   valid [M] uint8 or NULL: rows with valid==0 are skipped (the rows rpn_to_roi deletes
+ *         as degenerate, rpn.py:163-166); NULL = all rows are candidates
+ *   pick  [min(max_boxes,M)] int32 picked row indices, score-descending
+ *   count [2] int32 {n_picked, n_score_ties}
+ */
+size_t radnet_nms_f64_workspace_bytes(int M, int max_boxes);
+int radnet_nms_f64(const double *boxes, const double *probs, const uint8_t *valid, int M, double thr,
+                   int max_boxes, int32_t *pick, int32_t *count, void *ws, size_t ws_bytes, void *stream);
+
+/* ----------------------------------------------------------------- K4: RoI pooling
+ * Replaces RoiPoolingConv.call (reference faster_rcnn/RoiPoolingConv.py:48-88): crop
+ * + TF-1 legacy bilinear resize (tf.image.resize_images, align_corners=False) of every
+ * RoI to pool x pool, float32, no fused multiply-add.
+ *   feat   [B][H][W][C]  float32 NHWC feature maps
+ *   rois   xywh int32, feature cells.  Two addressing modes:
+ *          det != NULL : RoIs are the kept boxes of the B detection records (xyxy ->
+ *                        x,y,w=x2-x1,h=y2-y1, RADNet.py:564-565), rois_per_panel slots each;
+ *          det == NULL : rois [B][rois_per_panel][4] int32 (x,y,w,h), roi_count [B] (may be NULL
+ *                        = all slots used).
+ *   out    [B][rois_per_panel][pool][pool][C] float32; slots >= count are zero-filled.
+ * RoIs must lie inside the map after TF's slice clamping (x,y >= 0); the host shim checks.
+ */
+int radnet_roi_pool(const float *feat, int B, int H, int W, int C, const void *det,
+                    int det_max_boxes, const int32_t *rois, const int32_t *roi_count,
+                    int rois_per_panel, int pool, float *out, void *stream);
+
+/* --------------------------------------------------- K3: RPN anchor target assignment
+ * Replaces the deterministic part of calc_region_props (reference faster_rcnn/utils.py:
+ * 585-775 and 815-816; upstream name calc_rpn) for B panels.  The RNG-driven 256-region
+ * subsampling (utils.py:777-813) stays on the host in the Python shim.
+ *   gt        [B][Gmax][4] float64 x1,x2,y1,y2 in resized-image pixels (utils.py:608-613)
+ *   gt_is_bg  [B][Gmax]    uint8, 1 = class 'bg' (utils.py:690)
+ *   gt_count  [B]          int32
+ *   h_anchor_px [A][2]     float64 anchor (w,h) in pixels, a = ratio_idx + n_ratios*size_idx
+ *   img_wh    [B][2]       float64 resized width,height (utils.py:629,638)
+ *   n_ratios               len(anchor_box_ratios), to split a into (ratio_idx,size_idx)
+ * Outputs (channel-first, as returned by the reference):
+ *   y_rpn_cls  [B][2A][H][W] float64 = [valid | overlap]              (utils.py:815)
+ *   y_rpn_regr [B][8A][H][W] float64 = [repeat(overlap,4) | regr]     (utils.py:816)
+ *   best_anchor [B][Gmax][4] int32 {jy, ix, ratio_idx, size_idx} or -1 (utils.py:697)
+ *   n_hits      [B][Gmax]    int32 positives per GT before forcing    (utils.py:707)
+ */
+size_t radnet_rpn_targets_workspace_bytes(int B, int Gmax);
+int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, const int32_t *gt_count,
+                       int B, int Gmax, int H, int W, int A, int n_ratios,
+                       const double *h_anchor_px, double rpn_stride, const double *img_wh,
+                       double max_overlap, double *y_rpn_cls, double *y_rpn_regr,
+                       int32_t *best_anchor, int32_t *n_hits, void *ws, size_t ws_bytes,
+                       void *stream);
+
+/* ----------------------------------------------------------- a4: RoI target assignment
+ * Replaces the per-RoI loop of calc_iou (reference faster_rcnn/rpn.py:209-282).
+ *   rois   [R][4] int32 x1,y1,x2,y2;  gt [G][4] float64 x1,x2,y1,y2 in feature cells
+ *   (already rounded by the host, rpn.py:197-200);  gt_class [G] int32 class index.
+ *   bg_class  index of 'bg';  n_cls = len(class_mapping);  regr_std [4].
+ * Outputs compacted in RoI order: x_roi [R][4] int32 (x,y,w,h), y_class [R][n_cls] int32,
+ * y_regr [R][8*(n_cls-1)] float64 = [labels | coords], ious [R] float64,
+ * count [1] int32 = number of rows written.
+ */
+int radnet_roi_targets(const int32_t *rois, int R, const double *gt, const int32_t *gt_class,
+                       int G, int n_cls, int bg_class, double min_overlap, double max_overlap,
+                       const double *h_regr_std4, int32_t *x_roi, int32_t *y_class,
+                       double *y_regr, double *ious, int32_t *count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADNET_B200_H */

@@ -1,0 +1,124 @@
+// common.cuh - shared helpers for the sm_100a kernels of libradnet_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/radnet_b200.h"
+
+namespace radnet {
+
+constexpr int kMaxAnchors = 64;
+constexpr int kSmCountB200 = 148;
+
+// thread-local error text, set by every failing entry point
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define RADNET_CHECK_ARG(cond, ...)                  \
+    do {                                             \
+        if (!(cond)) {                               \
+            ::radnet::set_error(__VA_ARGS__);        \
+            return RADNET_E_INVALID;                 \
+        }                                            \
+    } while (0)
+
+#define RADNET_CUDA(call)                                                    \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return ::radnet::cuda_fail(e__, #call);      \
+    } while (0)
+
+// launch-error check that does not synchronise
+static inline int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return RADNET_OK;
+}
+
+struct AnchorTable {
+    double wh[kMaxAnchors][2];
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+// Order-preserving uint32 image of a float32 score.  0 is reserved for "deleted".
+// -0.0 is folded onto +0.0 (NumPy compares them equal) and every NaN sorts last
+// (= largest), like np.argsort.
+__device__ __forceinline__ uint32_t score_to_key(float s) {
+    uint32_t b = __float_as_uint(s);
+    if (s != s) return 0xFFFFFFFFu;
+    if (b == 0x80000000u) b = 0u;
+    uint32_t k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return k == 0u ? 1u : k;
+}
+__device__ __forceinline__ float key_to_score(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t score_to_key64(double s) {
+    uint64_t b = (uint64_t)__double_as_longlong(s);
+    if (s != s) return ~0ull;
+    if (b == 0x8000000000000000ull) b = 0ull;
+    uint64_t k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    return k == 0ull ? 1ull : k;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) -----------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                             uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// streaming 16-byte store: written once, never re-read by this kernel
+__device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace radnet

@@ -1,0 +1,240 @@
+// decode.cu - K1: anchor decode + clip (reference faster_rcnn/rpn.py:91-166, 299-344).
+//
+// One thread per (cell, anchor) pair in the INPUT order, so the float4 regression
+// loads and the score loads are fully coalesced; results are transposed through
+// shared memory and leave in the reference's anchor-major flat order
+// i = a*H*W + r*W + c with 16-byte coalesced stores per anchor row.
+//
+// Arithmetic contract (bit-exact against the NumPy reference, except exp() ulps):
+//   t = regr / std_scaling           float32 IEEE divide            (rpn.py:91)
+//   all box math in float64, one rounding per NumPy operation, no FMA contraction
+//   (the library is compiled with -fmad=false and the products below use __dmul_rn)
+//   np.round == rint() (half to even)                                (rpn.py:335-338)
+#include "common.cuh"
+
+namespace radnet {
+
+constexpr int kDecodeCells = 64;      // cells per CTA
+constexpr int kDecodeThreads = 256;
+
+struct DecodedBox {
+    double x1, y1, x2, y2;
+    int flags;   // bit0 valid, bit1 nonfinite, bit2 round near-tie, bit3 non-integer coordinate
+};
+
+__device__ __forceinline__ int near_half(double v) {
+    // |frac(v) - 0.5| tiny: an exp() ulp difference against NumPy could flip np.round
+    double f = v - floor(v);
+    return fabs(f - 0.5) < 1e-9 ? 4 : 0;
+}
+
+__device__ __forceinline__ DecodedBox decode_one(int c, int r, double aw, double ah, float4 t,
+                                                 int use_regr, int rows, int cols) {
+    DecodedBox o;
+    double x = __dsub_rn((double)c, __ddiv_rn(aw, 2.0));     // X - anchor_x/2   (rpn.py:127)
+    double y = __dsub_rn((double)r, __ddiv_rn(ah, 2.0));     // Y - anchor_y/2   (rpn.py:128)
+    double w = aw, h = ah;
+    int flags = 0;
+    if (use_regr) {                                          // apply_regr_np     (rpn.py:325-338)
+        double cx = __dadd_rn(x, __ddiv_rn(w, 2.0));
+        double cy = __dadd_rn(y, __ddiv_rn(h, 2.0));
+        double cx1 = __dadd_rn(__dmul_rn((double)t.x, w), cx);
+        double cy1 = __dadd_rn(__dmul_rn((double)t.y, h), cy);
+        double w1 = __dmul_rn(exp((double)t.z), w);
+        double h1 = __dmul_rn(exp((double)t.w), h);
+        double x1 = __dsub_rn(cx1, __ddiv_rn(w1, 2.0));
+        double y1 = __dsub_rn(cy1, __ddiv_rn(h1, 2.0));
+        flags |= near_half(x1) | near_half(y1) | near_half(w1) | near_half(h1);
+        x = rint(x1);
+        y = rint(y1);
+        w = rint(w1);
+        h = rint(h1);
+    }
+    // np.maximum / np.minimum propagate NaN; fmax/fmin do not, so test explicitly
+    w = (w != w) ? w : fmax(1.0, w);                         // rpn.py:137
+    h = (h != h) ? h : fmax(1.0, h);                         // rpn.py:138
+    double x2 = __dadd_rn(w, x);                             // rpn.py:143
+    double y2 = __dadd_rn(h, y);                             // rpn.py:144
+    x = (x != x) ? x : fmax(0.0, x);                         // rpn.py:147
+    y = (y != y) ? y : fmax(0.0, y);                         // rpn.py:148
+    x2 = (x2 != x2) ? x2 : fmin((double)(cols - 1), x2);     // rpn.py:149
+    y2 = (y2 != y2) ? y2 : fmin((double)(rows - 1), y2);     // rpn.py:150
+    bool nan_any = (x != x) || (y != y) || (x2 != x2) || (y2 != y2);
+    // rows the reference deletes: (x1 - x2 >= 0) | (y1 - y2 >= 0)         (rpn.py:163)
+    bool drop = (__dsub_rn(x, x2) >= 0.0) || (__dsub_rn(y, y2) >= 0.0);
+    if (!drop) flags |= 1;
+    if (nan_any) flags |= 2;   // survives the delete and trips the NMS assert (rpn.py:400-401)
+    if (!drop && !nan_any &&
+        (x != rint(x) || y != rint(y) || x2 != rint(x2) || y2 != rint(y2)))
+        flags |= 8;
+    o.x1 = x; o.y1 = y; o.x2 = x2; o.y2 = y2; o.flags = flags;
+    return o;
+}
+
+template <bool kF64>
+__global__ void __launch_bounds__(kDecodeThreads)
+decode_clip_kernel(const float *__restrict__ cls, const float *__restrict__ regr, int H, int W,
+                   int A, AnchorTable anchors, float std_scaling, int use_regr,
+                   int32_t *__restrict__ boxes_i32, uint32_t *__restrict__ keys,
+                   double *__restrict__ boxes_f64, float *__restrict__ scores,
+                   uint8_t *__restrict__ valid, int32_t *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // staging: per anchor row kDecodeCells(+1 pad) entries
+    constexpr int kPad = kDecodeCells + 1;
+    int4 *s_box = reinterpret_cast<int4 *>(smem_raw);                       // [A][kPad] (i32 path)
+    double4 *s_boxd = reinterpret_cast<double4 *>(smem_raw);                // [A][kPad] (f64 path)
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(
+        smem_raw + (size_t)A * kPad * (kF64 ? sizeof(double4) : sizeof(int4)));  // [A][kPad]
+    __shared__ int s_stats[4];
+
+    const int HW = H * W;
+    const int b = blockIdx.y;
+    const int cell0 = blockIdx.x * kDecodeCells;
+    const int ncell = min(kDecodeCells, HW - cell0);
+    const size_t N = (size_t)HW * A;
+    if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+
+    const float *cls_b = cls + (size_t)b * N + (size_t)cell0 * A;
+    const float4 *regr_b = reinterpret_cast<const float4 *>(regr + ((size_t)b * N + (size_t)cell0 * A) * 4);
+    int n_valid = 0, n_nonfinite = 0, n_tie = 0, n_nonint = 0;
+    for (int p = threadIdx.x; p < ncell * A; p += kDecodeThreads) {
+        int cl = p / A;
+        int a = p - cl * A;
+        int cell = cell0 + cl;
+        int r = cell / W, c = cell - r * W;
+        float4 t = __ldg(regr_b + p);
+        float s = __ldg(cls_b + p);
+        t.x = __fdiv_rn(t.x, std_scaling);
+        t.y = __fdiv_rn(t.y, std_scaling);
+        t.z = __fdiv_rn(t.z, std_scaling);
+        t.w = __fdiv_rn(t.w, std_scaling);
+        DecodedBox d = decode_one(c, r, anchors.wh[a][0], anchors.wh[a][1], t, use_regr, H, W);
+        n_valid += d.flags & 1;
+        n_nonfinite += (d.flags >> 1) & 1;
+        n_tie += (d.flags >> 2) & 1;
+        n_nonint += (d.flags >> 3) & 1;
+        if (kF64) {
+            s_boxd[a * kPad + cl] = make_double4(d.x1, d.y1, d.x2, d.y2);
+            // key slot carries the raw score bits and validity in the f64 path
+            s_key[a * kPad + cl] = __float_as_uint(s);
+            reinterpret_cast<uint8_t *>(s_key + (size_t)A * kPad)[a * kPad + cl] = (uint8_t)(d.flags & 1);
+        } else {
+            // saturating conversions; deleted / non-finite boxes never reach the NMS
+            int4 bi = make_int4(__double2int_rn(d.x1), __double2int_rn(d.y1), __double2int_rn(d.x2),
+                                __double2int_rn(d.y2));
+            s_box[a * kPad + cl] = bi;
+            s_key[a * kPad + cl] = ((d.flags & 3) == 1) ? score_to_key(s) : 0u;
+        }
+    }
+    // block-level stats
+    n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+    n_nonfinite = __reduce_add_sync(0xffffffffu, n_nonfinite);
+    n_tie = __reduce_add_sync(0xffffffffu, n_tie);
+    n_nonint = __reduce_add_sync(0xffffffffu, n_nonint);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_valid) atomicAdd(&s_stats[0], n_valid);
+        if (n_nonfinite) atomicAdd(&s_stats[1], n_nonfinite);
+        if (n_tie) atomicAdd(&s_stats[2], n_tie);
+        if (n_nonint) atomicAdd(&s_stats[3], n_nonint);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_stats[threadIdx.x]) atomicAdd(&stats[b * 4 + threadIdx.x], s_stats[threadIdx.x]);
+
+    // transposed, coalesced write-out: anchor-major rows of ncell entries
+    for (int p = threadIdx.x; p < ncell * A; p += kDecodeThreads) {
+        int a = p / ncell;
+        int cl = p - a * ncell;
+        size_t o = (size_t)b * N + (size_t)a * HW + cell0 + cl;
+        if (kF64) {
+            double4 v = s_boxd[a * kPad + cl];
+            reinterpret_cast<double4 *>(boxes_f64)[o] = v;
+            scores[o] = __uint_as_float(s_key[a * kPad + cl]);
+            valid[o] = reinterpret_cast<uint8_t *>(s_key + (size_t)A * kPad)[a * kPad + cl];
+        } else {
+            reinterpret_cast<int4 *>(boxes_i32)[o] = s_box[a * kPad + cl];
+            keys[o] = s_key[a * kPad + cl];
+        }
+    }
+}
+
+// apply_regr_np as a flat elementwise kernel (API parity; not on the batched hot path)
+__global__ void apply_regr_kernel(const double *__restrict__ X, const double *__restrict__ T,
+                                  long long n, double *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = X[i], y = X[n + i], w = X[2 * n + i], h = X[3 * n + i];
+    double tx = T[i], ty = T[n + i], tw = T[2 * n + i], th = T[3 * n + i];
+    double cx = __dadd_rn(x, __ddiv_rn(w, 2.0));
+    double cy = __dadd_rn(y, __ddiv_rn(h, 2.0));
+    double cx1 = __dadd_rn(__dmul_rn(tx, w), cx);
+    double cy1 = __dadd_rn(__dmul_rn(ty, h), cy);
+    double w1 = __dmul_rn(exp(tw), w);
+    double h1 = __dmul_rn(exp(th), h);
+    out[i] = rint(__dsub_rn(cx1, __ddiv_rn(w1, 2.0)));
+    out[n + i] = rint(__dsub_rn(cy1, __ddiv_rn(h1, 2.0)));
+    out[2 * n + i] = rint(w1);
+    out[3 * n + i] = rint(h1);
+}
+
+static int decode_common(bool f64, const float *cls, const float *regr, int B, int H, int W, int A,
+                         const double *h_anchor_wh, float std_scaling, int use_regr,
+                         int32_t *boxes_i32, uint32_t *keys, double *boxes_f64, float *scores,
+                         uint8_t *valid, int32_t *stats, void *stream) {
+    RADNET_CHECK_ARG(cls && regr && h_anchor_wh && stats, "decode_clip: null pointer");
+    RADNET_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && A >= 1 && A <= kMaxAnchors,
+                     "decode_clip: bad shape B=%d H=%d W=%d A=%d (A<=%d)", B, H, W, A, kMaxAnchors);
+    RADNET_CHECK_ARG(B <= 65535, "decode_clip: B=%d exceeds grid.y", B);
+    RADNET_CHECK_ARG(std_scaling != 0.f, "decode_clip: std_scaling == 0");
+    if (f64) RADNET_CHECK_ARG(boxes_f64 && scores && valid, "decode_clip_f64: null output");
+    else RADNET_CHECK_ARG(boxes_i32 && keys, "decode_clip_i32: null output");
+    AnchorTable tab;
+    for (int a = 0; a < A; ++a) {
+        tab.wh[a][0] = h_anchor_wh[2 * a];
+        tab.wh[a][1] = h_anchor_wh[2 * a + 1];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    RADNET_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4 * B, st));
+    const int HW = H * W;
+    dim3 grid((HW + kDecodeCells - 1) / kDecodeCells, B);
+    size_t per = f64 ? (sizeof(double4) + sizeof(uint32_t) + 1) : (sizeof(int4) + sizeof(uint32_t));
+    size_t smem = (size_t)A * (kDecodeCells + 1) * per + 16;
+    if (f64) {
+        RADNET_CUDA(cudaFuncSetAttribute(decode_clip_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        decode_clip_kernel<true><<<grid, kDecodeThreads, smem, st>>>(
+            cls, regr, H, W, A, tab, std_scaling, use_regr, nullptr, nullptr, boxes_f64, scores, valid, stats);
+    } else {
+        RADNET_CUDA(cudaFuncSetAttribute(decode_clip_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        decode_clip_kernel<false><<<grid, kDecodeThreads, smem, st>>>(
+            cls, regr, H, W, A, tab, std_scaling, use_regr, boxes_i32, keys, nullptr, nullptr, nullptr, stats);
+    }
+    return check_launch("decode_clip_kernel");
+}
+
+}  // namespace radnet
+
+extern "C" int radnet_decode_clip_i32(const float *cls, const float *regr, int B, int H, int W, int A,
+                                      const double *h_anchor_wh, float std_scaling, int use_regr,
+                                      int32_t *boxes_i32, uint32_t *keys, int32_t *stats, void *stream) {
+    return radnet::decode_common(false, cls, regr, B, H, W, A, h_anchor_wh, std_scaling, use_regr,
+                                 boxes_i32, keys, nullptr, nullptr, nullptr, stats, stream);
+}
+
+extern "C" int radnet_decode_clip_f64(const float *cls, const float *regr, int B, int H, int W, int A,
+                                      const double *h_anchor_wh, float std_scaling, int use_regr,
+                                      double *boxes_f64, float *scores, uint8_t *valid, int32_t *stats,
+                                      void *stream) {
+    return radnet::decode_common(true, cls, regr, B, H, W, A, h_anchor_wh, std_scaling, use_regr,
+                                 nullptr, nullptr, boxes_f64, scores, valid, stats, stream);
+}
+
+extern "C" int radnet_apply_regr(const double *X, const double *T, long long n, double *out, void *stream) {
+    RADNET_CHECK_ARG(X && T && out && n >= 0, "apply_regr: bad arguments");
+    if (n == 0) return RADNET_OK;
+    long long blocks = (n + 255) / 256;
+    RADNET_CHECK_ARG(blocks <= 0x7fffffffLL, "apply_regr: n too large");
+    radnet::apply_regr_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(X, T, n, out);
+    return radnet::check_launch("apply_regr_kernel");
+}

@@ -1,0 +1,640 @@
+// sort_nms.cu - K2: segmented score sort + exact greedy NMS, one CTA per panel.
+//
+// Replaces non_max_suppression_fast (reference faster_rcnn/rpn.py:380-456).
+//
+// Stage 1  stable LSD radix sort of the candidate keys (8-bit digits).  Each warp owns a
+//          contiguous slice of the array; the rank of an element inside a 32-wide row
+//          comes from __match_any_sync + popc (no atomics), per-warp digit counters live
+//          in shared memory.  Stable + ascending => reading from the end visits equal
+//          scores "higher flat index first", the documented tie rule.  On the hot path
+//          (N*12 B fits) keys are staged into shared memory with one TMA bulk copy
+//          (cp.async.bulk + mbarrier) and all passes run out of shared memory.
+// Stage 2  greedy suppression over tiles of 1024 sorted candidates, one candidate per
+//          thread.  (a) every candidate is tested against the boxes kept by earlier tiles;
+//          (b) each warp builds the 32x32 "lower lane overlaps me" bit matrix of its row
+//          from a shared-memory box tile; (c) warps retire in rank order (a systolic
+//          hand-off through two shared words): a warp tests its row against the boxes
+//          kept since it last looked, resolves its own row with a ballot fixed point and
+//          appends its keeps.  The loop stops as soon as max_boxes are kept
+//          (rpn.py:449-450), so only the top few hundred candidates are ever touched.
+//
+// Exactness: the i32 path evaluates `inter/(union+1e-6) > thr` (rpn.py:443-447) through a
+// per-union table of the smallest suppressing intersection, built at kernel start with
+// the float64 division itself; the f64 path performs the float64 arithmetic directly in
+// the reference's association order.  Both are bit-exact decisions.
+#include "common.cuh"
+
+namespace radnet {
+
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr int kCntStride = 257;                 // padded digit row: conflict-free scan
+constexpr int kTile = kNmsThreads;              // candidates per NMS tile
+constexpr int kMaxTableEntries = 65535;
+constexpr int kKeptSmemMax = 1024;              // kept boxes held in shared memory
+
+// ----------------------------------------------------------------------------------
+// box traits
+// ----------------------------------------------------------------------------------
+struct BoxI32 {
+    using Box = int4;          // x1,y1,x2,y2
+    using Area = int;
+    struct Ctx { const uint16_t *tab; };
+    static __device__ __forceinline__ Box load(const void *boxes, size_t i) {
+        return __ldg(reinterpret_cast<const int4 *>(boxes) + i);
+    }
+    static __device__ __forceinline__ Area area(const Box &b) { return (b.z - b.x) * (b.w - b.y); }
+    // true when a kept box `k` suppresses candidate `c`
+    static __device__ __forceinline__ bool suppress(const Box &k, Area ka, const Box &c, Area ca,
+                                                    const Ctx &ctx) {
+        int iw = max(min(k.z, c.z) - max(k.x, c.x), 0);
+        int ih = max(min(k.w, c.w) - max(k.y, c.y), 0);
+        int inter = iw * ih;
+        int uni = ka + ca - inter;
+        return inter >= (int)ctx.tab[uni];
+    }
+};
+
+struct BoxF64 {
+    using Box = double4;
+    using Area = double;
+    struct Ctx { double thr; };
+    static __device__ __forceinline__ Box load(const void *boxes, size_t i) {
+        return reinterpret_cast<const double4 *>(boxes)[i];
+    }
+    static __device__ __forceinline__ Area area(const Box &b) {
+        return __dmul_rn(__dsub_rn(b.z, b.x), __dsub_rn(b.w, b.y));                 // rpn.py:412
+    }
+    static __device__ __forceinline__ bool suppress(const Box &k, Area ka, const Box &c, Area ca,
+                                                    const Ctx &ctx) {
+        double xx1 = fmax(k.x, c.x), yy1 = fmax(k.y, c.y);                           // rpn.py:429-430
+        double xx2 = fmin(k.z, c.z), yy2 = fmin(k.w, c.w);                           // rpn.py:431-432
+        double ww = fmax(0.0, __dsub_rn(xx2, xx1));                                  // rpn.py:434
+        double hh = fmax(0.0, __dsub_rn(yy2, yy1));                                  // rpn.py:435
+        double inter = __dmul_rn(ww, hh);                                            // rpn.py:437
+        double uni = __dsub_rn(__dadd_rn(ka, ca), inter);                            // rpn.py:440
+        return __ddiv_rn(inter, __dadd_rn(uni, 1e-6)) > ctx.thr;                     // rpn.py:443,447
+    }
+};
+
+template <typename KeyT> struct KeyBits;
+template <> struct KeyBits<uint32_t> { static constexpr int passes = 4; };
+template <> struct KeyBits<uint64_t> { static constexpr int passes = 8; };
+
+struct SortNmsParams {
+    const void *boxes;        // [B][N] Box
+    const void *keys;         // [B][N] KeyT, 0 = deleted
+    int N;
+    int max_boxes;            // effective K = min(max_boxes, N)
+    double thr;
+    int table_entries;        // i32 only: umax + 1
+    // outputs
+    unsigned char *det;       // i32: detection records
+    size_t det_stride;
+    int det_max_boxes;
+    int32_t *pick;            // f64: picked indices
+    int32_t *count;           // f64: {n, ties}
+    // global scratch per panel (generic-path sort buffers, big kept lists)
+    unsigned char *ws;
+    size_t ws_stride;
+    size_t ws_off_kA, ws_off_kB, ws_off_iA, ws_off_iB, ws_off_kept;
+    // dynamic shared memory carve-up (bytes from the base)
+    int sm_off_cnt, sm_off_sort, sm_off_table, sm_off_kept;
+    int sort_cap;             // elements per smem sort buffer
+};
+
+// block-wide exclusive scan of one int per thread (1024 threads); returns exclusive prefix,
+// total via *total (same value in every thread)
+__device__ __forceinline__ int block_exscan(int v, int *s_warp, int *total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int t = s_warp[lane];
+        int ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, ti, d);
+            if (lane >= d) ti += n;
+        }
+        s_warp[lane] = ti - t;            // exclusive warp base
+        if (lane == 31) s_warp[32] = ti;  // grand total
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[w] + inc - v;
+}
+
+// One stable radix pass over n_in elements.  first=true: input is the raw key array
+// (index = position, key 0 skipped).  Returns number of elements written (block-uniform),
+// or -1 when the pass was skipped because every element shares the digit.
+template <typename KeyT, typename IdxT>
+__device__ int radix_pass(const KeyT *in_k, const IdxT *in_i, KeyT *out_k, IdxT *out_i, int n_in,
+                          int shift, bool first, uint32_t *s_cnt, int *s_scan, int *s_flag) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kNmsWarps * kCntStride; i += kNmsThreads) s_cnt[i] = 0;
+    if (threadIdx.x == 0) *s_flag = 0;
+    __syncthreads();
+    int chunk = ((n_in + kNmsWarps - 1) / kNmsWarps + 31) & ~31;
+    int wbeg = min(w * chunk, n_in), wend = min(wbeg + chunk, n_in);
+    uint32_t *cnt = s_cnt + w * kCntStride;
+    for (int base = wbeg; base < wend; base += 32) {
+        int i = base + lane;
+        bool act = i < wend;
+        KeyT key = act ? in_k[i] : (KeyT)0;
+        if (first) act = act && key != (KeyT)0;
+        uint32_t am = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            uint32_t d = (uint32_t)(key >> shift) & 0xFFu;
+            uint32_t m = __match_any_sync(am, d);
+            if ((m & lanemask_lt()) == 0) cnt[d] += __popc(m);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // scan in (digit major, warp minor) order; thread t owns digit t>>2, warps (t&3)*8..+7
+    {
+        const int d = threadIdx.x >> 2, wq = (threadIdx.x & 3) * 8;
+        uint32_t c[8];
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = s_cnt[(wq + j) * kCntStride + d];
+            sum += (int)c[j];
+        }
+        int dsum = sum;
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+        int total;
+        int ex = block_exscan(sum, s_scan, &total);
+        if (!first && dsum == total && total > 0 && (threadIdx.x & 3) == 0) *s_flag = 1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s_cnt[(wq + j) * kCntStride + d] = (uint32_t)ex;
+            ex += (int)c[j];
+        }
+        __syncthreads();
+        if (*s_flag) return -1;
+        n_in = first ? total : n_in;
+        if (first && threadIdx.x == 0) s_scan[33] = total;
+    }
+    for (int base = wbeg; base < wend; base += 32) {
+        int i = base + lane;
+        bool act = i < wend;
+        KeyT key = act ? in_k[i] : (KeyT)0;
+        if (first) act = act && key != (KeyT)0;
+        uint32_t am = __ballot_sync(0xffffffffu, act);
+        uint32_t d = 0, m = 0, off = 0;
+        if (act) {
+            IdxT idx = first ? (IdxT)i : in_i[i];
+            d = (uint32_t)(key >> shift) & 0xFFu;
+            m = __match_any_sync(am, d);
+            off = cnt[d];
+            uint32_t pos = off + __popc(m & lanemask_lt());
+            out_k[pos] = key;
+            out_i[pos] = idx;
+        }
+        __syncwarp();
+        if (act && (m & lanemask_lt()) == 0) cnt[d] = off + __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    return n_in;
+}
+
+template <typename Traits, typename KeyT, typename IdxT, bool kSmemSort, bool kKeptSmem>
+__global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams p) {
+    using Box = typename Traits::Box;
+    using Area = typename Traits::Area;
+    constexpr bool kI32 = sizeof(Box) == sizeof(int4);
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);                 // 8 B
+    int *s_misc = reinterpret_cast<int *>(smem + 16);                     // 16 ints
+    int *s_scan = reinterpret_cast<int *>(smem + 96);                     // 34 ints
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + p.sm_off_cnt);  // [32][257]
+    volatile int *s_kcount = s_misc + 0;
+    volatile int *s_wdone = s_misc + 1;
+    int *s_flag = s_misc + 2;
+    int *s_ties = s_misc + 3;
+
+    const int seg = blockIdx.x;
+    const int N = p.N;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const KeyT *g_keys = reinterpret_cast<const KeyT *>(p.keys) + (size_t)seg * N;
+    const unsigned char *g_boxes = reinterpret_cast<const unsigned char *>(p.boxes) + (size_t)seg * N * sizeof(Box);
+    unsigned char *ws = p.ws + (size_t)seg * p.ws_stride;
+
+    KeyT *kA, *kB;
+    IdxT *iA, *iB;
+    if (kSmemSort) {
+        unsigned char *sb = smem + p.sm_off_sort;
+        kA = reinterpret_cast<KeyT *>(sb);
+        kB = kA + p.sort_cap;
+        iA = reinterpret_cast<IdxT *>(kB + p.sort_cap);
+        iB = iA + p.sort_cap;
+    } else {
+        kA = reinterpret_cast<KeyT *>(ws + p.ws_off_kA);
+        kB = reinterpret_cast<KeyT *>(ws + p.ws_off_kB);
+        iA = reinterpret_cast<IdxT *>(ws + p.ws_off_iA);
+        iB = reinterpret_cast<IdxT *>(ws + p.ws_off_iB);
+    }
+
+    if (threadIdx.x == 0) {
+        *s_kcount = 0;
+        *s_wdone = 0;
+        *s_ties = 0;
+    }
+
+    // ---- stage keys (TMA bulk copy into shared memory on the hot path) -------------
+    const KeyT *in_k;
+    const IdxT *in_i = nullptr;
+    KeyT *out_k;
+    IdxT *out_i;
+    if (kSmemSort) {
+        size_t bytes = (size_t)N * sizeof(KeyT);
+        uint32_t bulk = ((reinterpret_cast<uintptr_t>(g_keys) & 15) == 0) ? (uint32_t)(bytes & ~(size_t)15) : 0u;
+        if (threadIdx.x == 0) {
+            mbar_init(s_bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && bulk) {
+            mbar_expect_tx(s_bar, bulk);
+            tma_bulk_g2s(kA, g_keys, bulk, s_bar);
+        }
+        // tail (and the whole array when the source is not 16-byte aligned)
+        for (int i = (int)(bulk / sizeof(KeyT)) + threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
+        if (bulk) mbar_wait(s_bar, 0);
+        __syncthreads();
+        in_k = kA; out_k = kB; out_i = iB;
+    } else {
+        __syncthreads();
+        in_k = g_keys; out_k = kA; out_i = iA;
+    }
+
+    // ---- build the suppression table while the keys land (i32 path) ----------------
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem + p.sm_off_table);
+    if (kI32) {
+        const double thr = p.thr;
+        for (int u = threadIdx.x; u < p.table_entries; u += kNmsThreads) {
+            double d = __dadd_rn((double)u, 1e-6);
+            double g = floor(__dmul_rn(thr, d)) - 1.0;
+            int c = (g > 0.0) ? ((g < 65534.0) ? (int)g : 65535) : 0;
+            int lim = c + 4;
+            // smallest inter with inter/(u+1e-6) > thr, found with the float64 divide itself
+            while (c < lim && c <= u && !(__ddiv_rn((double)c, d) > thr)) ++c;
+            bool ok = (c <= u) && (c < lim) && (__ddiv_rn((double)c, d) > thr);
+            s_tab[u] = ok ? (uint16_t)c : (uint16_t)0xFFFF;
+        }
+    }
+
+    // ---- stage 1: radix sort --------------------------------------------------------
+    int M = 0;
+    {
+        int n_in = N;
+        bool first = true;
+#pragma unroll 1
+        for (int pass = 0; pass < KeyBits<KeyT>::passes; ++pass) {
+            int r = radix_pass<KeyT, IdxT>(in_k, in_i, out_k, out_i, n_in, pass * 8, first, s_cnt, s_scan, s_flag);
+            if (r >= 0) {
+                n_in = r;
+                const KeyT *nk = out_k;
+                const IdxT *ni = out_i;
+                // next output buffer is "the other one"
+                if (out_k == kA) { out_k = kB; out_i = iB; } else { out_k = kA; out_i = iA; }
+                in_k = nk; in_i = ni;
+            }
+            first = false;
+            if (n_in == 0) break;
+        }
+        M = n_in;
+    }
+    // in_k / in_i now hold M entries ascending by (score, flat index)
+
+    // ---- score ties among the candidates (reported) -----------------
+    {
+        int t = 0;
+        for (int i = threadIdx.x; i < M; i += kNmsThreads) {
+            KeyT k = in_k[i];
+            bool tie = (i > 0 && in_k[i - 1] == k) || (i + 1 < M && in_k[i + 1] == k);
+            t += tie ? 1 : 0;
+        }
+        t = __reduce_add_sync(0xffffffffu, t);
+        if (lane == 0 && t) atomicAdd(s_ties, t);
+    }
+
+    // ---- stage 2: greedy suppression ------------------------------------------------
+    const int K = min(p.max_boxes, M);
+    Box *kbox;
+    Area *karea;
+    int *kidx;
+    if (kKeptSmem) {
+        unsigned char *kb = smem + p.sm_off_kept;
+        kbox = reinterpret_cast<Box *>(kb);
+        karea = reinterpret_cast<Area *>(kbox + kKeptSmemMax);
+        kidx = reinterpret_cast<int *>(karea + kKeptSmemMax);
+    } else {
+        unsigned char *kb = ws + p.ws_off_kept;
+        int cap = min(p.max_boxes, N);
+        kbox = reinterpret_cast<Box *>(kb);
+        karea = reinterpret_cast<Area *>(kbox + cap);
+        kidx = reinterpret_cast<int *>(karea + cap);
+    }
+    Box *s_tile = reinterpret_cast<Box *>(s_cnt);   // counters are dead; [kTile] boxes fit
+    typename Traits::Ctx ctx;
+    if constexpr (kI32) ctx.tab = s_tab; else ctx.thr = p.thr;
+    __syncthreads();
+
+    int k0 = 0;
+#pragma unroll 1
+    for (int base = 0; base < M && k0 < K; base += kTile) {
+        const int r = base + threadIdx.x;
+        const bool active = r < M;
+        Box box;
+        Area ar = 0;
+        int flat = 0;
+        if (active) {
+            flat = (int)in_i[M - 1 - r];
+            box = Traits::load(g_boxes, (size_t)flat);
+            ar = Traits::area(box);
+        } else {
+            if constexpr (kI32) box = make_int4(0, 0, 0, 0); else box = make_double4(0, 0, 0, 0);
+        }
+        s_tile[threadIdx.x] = box;
+        __syncwarp();
+
+        // (a) against boxes kept by earlier tiles
+        bool alive = active;
+        for (int j = 0; j < k0; ++j) {
+            Box kb = kbox[j];
+            Area ka = karea[j];
+            if (Traits::suppress(kb, ka, box, ar, ctx)) alive = false;
+        }
+        // (b) intra-row matrix: which lower lanes of my row overlap me
+        uint32_t row_alive = __ballot_sync(0xffffffffu, alive);
+        uint32_t lower = 0;
+        {
+            uint32_t todo = row_alive;
+            while (todo) {
+                int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                Box ob = s_tile[(w << 5) + j];
+                Area oa = Traits::area(ob);
+                if (j < lane && Traits::suppress(ob, oa, box, ar, ctx)) lower |= 1u << j;
+            }
+        }
+        // (c) systolic hand-off: wait for my turn, testing new keeps as they appear
+        int seen = k0;
+        int kc = k0;
+        unsigned spins = 0;
+        while (true) {
+            if (++spins > (1u << 24)) { *s_flag = 2; break; }   // watchdog: never hang the device
+            int wd = *s_wdone;
+            __threadfence_block();
+            kc = *s_kcount;
+            for (int j = seen; j < kc; ++j) {
+                Box kb = kbox[j];
+                Area ka = karea[j];
+                if (Traits::suppress(kb, ka, box, ar, ctx)) alive = false;
+            }
+            seen = kc;
+            if (kc >= K || wd == w) break;
+        }
+        if (kc < K) {
+            uint32_t und = __ballot_sync(0xffffffffu, alive);
+            uint32_t kept = 0;
+            const bool me0 = alive;
+            while (und) {
+                bool me = me0 && ((und >> lane) & 1u);
+                uint32_t know = __ballot_sync(0xffffffffu, me && !(lower & kept) && !(lower & und));
+                kept |= know;
+                uint32_t dnow = __ballot_sync(0xffffffffu, me && (lower & kept));
+                und &= ~(know | dnow);
+            }
+            int room = K - kc;
+            int nk = __popc(kept);
+            if (nk > room) {                       // keep only the first `room` of this row
+                kept &= (1u << __fns(kept, 0, room + 1)) - 1u;
+                nk = room;
+            }
+            if ((kept >> lane) & 1u) {
+                int pos = kc + __popc(kept & lanemask_lt());
+                kbox[pos] = box;
+                karea[pos] = ar;
+                kidx[pos] = flat;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                *s_kcount = kc + nk;
+                __threadfence_block();
+                *s_wdone = w + 1;
+            }
+        } else if (lane == 0) {
+            // list is full: just pass the baton so later warps can leave too
+            __threadfence_block();
+            if (*s_wdone == w) *s_wdone = w + 1;
+        }
+        __syncthreads();
+        k0 = *s_kcount;
+        __syncthreads();
+        if (threadIdx.x == 0) *s_wdone = 0;
+        __syncthreads();
+    }
+    const int kept_n = *s_kcount;
+
+    // ---- epilogue -------------------------------------------------------------------
+    if constexpr (kI32) {
+        unsigned char *rec = p.det + (size_t)seg * p.det_stride;
+        int32_t *hdr = reinterpret_cast<int32_t *>(rec);
+        int4 *rb = reinterpret_cast<int4 *>(rec + 16);
+        float *rs = reinterpret_cast<float *>(rec + 16 + (size_t)p.det_max_boxes * 16);
+        int32_t *ri = reinterpret_cast<int32_t *>(rec + 16 + (size_t)p.det_max_boxes * 20);
+        if (threadIdx.x == 0) {
+            hdr[0] = kept_n;
+            hdr[1] = M;
+            hdr[2] = *s_ties;
+            hdr[3] = (*s_flag == 2) ? 1 : 0;   // hand-off watchdog fired: results invalid
+        }
+        for (int j = threadIdx.x; j < p.det_max_boxes; j += kNmsThreads) {
+            if (j < kept_n) {
+                int flat = kidx[j];
+                rb[j] = kbox[j];
+                rs[j] = key_to_score((uint32_t)g_keys[flat]);
+                ri[j] = flat;
+            } else {
+                rb[j] = make_int4(0, 0, 0, 0);
+                rs[j] = 0.f;
+                ri[j] = 0;
+            }
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            p.count[0] = (*s_flag == 2) ? -1 : kept_n;
+            p.count[1] = *s_ties;
+        }
+        for (int j = threadIdx.x; j < kept_n; j += kNmsThreads) p.pick[j] = kidx[j];
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// host side: shared-memory plan + launch
+// ----------------------------------------------------------------------------------
+struct NmsPlan {
+    bool smem_sort;
+    bool kept_smem;
+    size_t smem_bytes;
+    size_t ws_stride;
+    SortNmsParams p;
+};
+
+static int max_optin_smem() {
+    static int v = -1;
+    if (v < 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 232448;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) v = 232448;
+    }
+    return v;
+}
+
+template <typename Box, typename Area, typename KeyT>
+static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_smem_sort, int smem_limit) {
+    NmsPlan pl{};
+    SortNmsParams &p = pl.p;
+    const int K = max_boxes < N ? max_boxes : N;
+    size_t off = 256;                                   // barrier + misc + scan scratch
+    p.sm_off_cnt = (int)off;
+    size_t cnt_bytes = (size_t)kNmsWarps * kCntStride * 4;
+    size_t tile_bytes = (size_t)kTile * sizeof(Box);
+    off += align_up(cnt_bytes > tile_bytes ? cnt_bytes : tile_bytes, 128);
+    p.sm_off_table = (int)off;
+    off += align_up((size_t)table_entries * 2, 128);
+    pl.kept_smem = K <= kKeptSmemMax;
+    p.sm_off_kept = (int)off;
+    if (pl.kept_smem) off += align_up((size_t)kKeptSmemMax * (sizeof(Box) + sizeof(Area) + 4), 128);
+    // shared-memory sort: keys ping-pong + uint16 index ping-pong
+    size_t cap = align_up((size_t)N, 64);
+    size_t sort_bytes = 2 * cap * sizeof(KeyT) + 2 * cap * sizeof(uint16_t);
+    pl.smem_sort = allow_smem_sort && N <= 65535 && off + sort_bytes <= (size_t)smem_limit;
+    p.sm_off_sort = (int)off;
+    p.sort_cap = (int)cap;
+    if (pl.smem_sort) off += sort_bytes;
+    pl.smem_bytes = off;
+    // global scratch (always sized so that either variant can run)
+    size_t w = 0;
+    p.ws_off_kA = w; w += align_up(cap * sizeof(KeyT), 256);
+    p.ws_off_kB = w; w += align_up(cap * sizeof(KeyT), 256);
+    p.ws_off_iA = w; w += align_up(cap * 4, 256);
+    p.ws_off_iB = w; w += align_up(cap * 4, 256);
+    p.ws_off_kept = w; w += align_up((size_t)K * (sizeof(Box) + sizeof(Area) + 4) + 64, 256);
+    pl.ws_stride = w;
+    p.ws_stride = w;
+    return pl;
+}
+
+template <typename K>
+static int launch(K kernel, const NmsPlan &pl, int B, cudaStream_t st) {
+    RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    kernel<<<B, kNmsThreads, pl.smem_bytes, st>>>(pl.p);
+    return check_launch("sort_nms_kernel");
+}
+
+}  // namespace radnet
+
+using namespace radnet;
+
+extern "C" size_t radnet_det_record_bytes(int max_boxes) {
+    if (max_boxes < 0) return 0;
+    return align_up(16 + (size_t)max_boxes * 24, 16);
+}
+
+extern "C" size_t radnet_sort_nms_i32_workspace_bytes(int B, int N, int map_h, int map_w, int max_boxes) {
+    if (B < 1 || N < 1 || max_boxes < 1) return 0;
+    (void)map_h; (void)map_w;
+    NmsPlan pl = make_plan<int4, int, uint32_t>(N, max_boxes, 1, false, 0);
+    return pl.ws_stride * (size_t)B;
+}
+
+extern "C" int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *keys, int B, int N, int map_h,
+                                   int map_w, double thr, int max_boxes, void *det, void *ws,
+                                   size_t ws_bytes, void *stream) {
+    RADNET_CHECK_ARG(boxes_i32 && keys && det && ws, "sort_nms_i32: null pointer");
+    RADNET_CHECK_ARG(B >= 1 && N >= 1 && max_boxes >= 1 && map_h >= 1 && map_w >= 1,
+                     "sort_nms_i32: bad sizes B=%d N=%d max_boxes=%d", B, N, max_boxes);
+    long long umax = 2LL * (map_h - 1) * (map_w - 1);
+    if (umax + 1 > kMaxTableEntries) {
+        set_error("sort_nms_i32: map %dx%d exceeds the exact-table range; use the f64 path", map_h, map_w);
+        return RADNET_E_UNSUPPORTED;
+    }
+    NmsPlan pl = make_plan<int4, int, uint32_t>(N, max_boxes, (int)umax + 1, true, max_optin_smem());
+    if (pl.smem_bytes > (size_t)max_optin_smem()) {
+        set_error("sort_nms_i32: shared memory plan %zu B exceeds the device limit", pl.smem_bytes);
+        return RADNET_E_UNSUPPORTED;
+    }
+    if (ws_bytes < pl.ws_stride * (size_t)B) {
+        set_error("sort_nms_i32: workspace %zu < %zu", ws_bytes, pl.ws_stride * (size_t)B);
+        return RADNET_E_WORKSPACE;
+    }
+    SortNmsParams &p = pl.p;
+    p.boxes = boxes_i32; p.keys = keys; p.N = N; p.max_boxes = max_boxes; p.thr = thr;
+    p.table_entries = (int)umax + 1;
+    p.det = reinterpret_cast<unsigned char *>(det);
+    p.det_stride = radnet_det_record_bytes(max_boxes);
+    p.det_max_boxes = max_boxes;
+    p.pick = nullptr; p.count = nullptr;
+    p.ws = reinterpret_cast<unsigned char *>(ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl.smem_sort) {
+        if (pl.kept_smem) return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true>, pl, B, st);
+        return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, false>, pl, B, st);
+    }
+    if (pl.kept_smem) return launch(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true>, pl, B, st);
+    return launch(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, false>, pl, B, st);
+}
+
+extern "C" size_t radnet_nms_f64_workspace_bytes(int M, int max_boxes) {
+    if (M < 1 || max_boxes < 1) return 0;
+    // +M*8 for the uint64 key image built by the entry point
+    NmsPlan pl = make_plan<double4, double, uint64_t>(M, max_boxes, 1, false, 0);
+    return pl.ws_stride + align_up((size_t)M * 8, 256);
+}
+
+namespace radnet {
+__global__ void make_keys64_kernel(const double *probs, const uint8_t *valid, int M, uint64_t *keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) keys[i] = (valid && !valid[i]) ? 0ull : score_to_key64(probs[i]);
+}
+}  // namespace radnet
+
+extern "C" int radnet_nms_f64(const double *boxes, const double *probs, const uint8_t *valid, int M, double thr, int max_boxes,
+                              int32_t *pick, int32_t *count, void *ws, size_t ws_bytes, void *stream) {
+    RADNET_CHECK_ARG(boxes && probs && pick && count && ws, "nms_f64: null pointer");
+    RADNET_CHECK_ARG(M >= 1 && max_boxes >= 1, "nms_f64: bad sizes M=%d max_boxes=%d", M, max_boxes);
+    NmsPlan pl = make_plan<double4, double, uint64_t>(M, max_boxes, 1, false, max_optin_smem());
+    size_t key_bytes = align_up((size_t)M * 8, 256);
+    if (ws_bytes < pl.ws_stride + key_bytes) {
+        set_error("nms_f64: workspace %zu < %zu", ws_bytes, pl.ws_stride + key_bytes);
+        return RADNET_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(ws);
+    make_keys64_kernel<<<(M + 255) / 256, 256, 0, st>>>(probs, valid, M, keys);
+    int rc = check_launch("make_keys64_kernel");
+    if (rc) return rc;
+    SortNmsParams &p = pl.p;
+    p.boxes = boxes; p.keys = keys; p.N = M; p.max_boxes = max_boxes; p.thr = thr;
+    p.table_entries = 0;
+    p.det = nullptr; p.det_stride = 0; p.det_max_boxes = 0;
+    p.pick = pick; p.count = count;
+    p.ws = reinterpret_cast<unsigned char *>(ws) + key_bytes;
+    if (pl.kept_smem) return launch(sort_nms_kernel<BoxF64, uint64_t, uint32_t, false, true>, pl, 1, st);
+    return launch(sort_nms_kernel<BoxF64, uint64_t, uint32_t, false, false>, pl, 1, st);
+}

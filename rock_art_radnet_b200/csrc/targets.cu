@@ -1,0 +1,353 @@
+// targets.cu - K3: RPN anchor target assignment (reference faster_rcnn/utils.py:554-775,
+// 815-816; upstream name calc_rpn) and a4: RoI target assignment (reference
+// faster_rcnn/rpn.py:209-282).
+//
+// K3 layout: one thread per anchor (a, jy, ix) with ix fastest, so each of the 10 float64
+// output planes an anchor touches is written with coalesced 8-byte stores.  The GT boxes
+// of the panel sit in shared memory.  The kernel is bound by the float64 output stream
+// (10*A*H*W*8 B per panel); IoU work is skipped for non-intersecting pairs (IoU == 0.0
+// exactly) so the float64 divide only runs where boxes meet.
+//
+// Order-dependent reference semantics and how they are kept without a serial loop:
+//   * best anchor per GT = first anchor, in the reference's loop order
+//     size -> ratio -> ix -> jy (utils.py:616-632), whose float32-rounded IoU is the
+//     maximum (float32 accumulator utils.py:603; NumPy>=2 compares in float32, see
+//     SURVEY.md row a3').  Realised as a 64-bit atomicMax on
+//     (float32 bits of IoU) << 32 | (0xFFFFFFFF - loop_order).
+//   * per-anchor best GT: strict '>' from 0.0, first GT wins ties (utils.py:710-713) - a
+//     serial loop over the GT inside the thread.
+//   * forced positives (utils.py:741-766) are applied by a second tiny kernel in GT order,
+//     with the float32-rounded targets (utils.py:605,766).
+#include "common.cuh"
+
+namespace radnet {
+
+constexpr int kTgtThreads = 256;
+
+struct RpnTargetParams {
+    const double *gt;          // [B][Gmax][4] x1,x2,y1,y2
+    const uint8_t *gt_is_bg;   // [B][Gmax]
+    const int32_t *gt_count;   // [B]
+    int Gmax, H, W, A, n_ratios;
+    AnchorTable anchors;       // pixels
+    double stride;
+    const double *img_wh;      // [B][2]
+    double max_overlap;
+    double *y_cls;             // [B][2A][H][W]
+    double *y_regr;            // [B][8A][H][W]
+    int32_t *best_anchor;      // [B][Gmax][4]
+    int32_t *n_hits;           // [B][Gmax]
+    unsigned long long *best_key;  // [B][Gmax] workspace
+};
+
+// reference utils.py:77-109 with a = GT (x1,y1,x2,y2), b = anchor
+__device__ __forceinline__ double ref_iou(double ax1, double ay1, double ax2, double ay2, double bx1,
+                                          double by1, double bx2, double by2) {
+    if (ax1 >= ax2 || ay1 >= ay2 || bx1 >= bx2 || by1 >= by2) return 0.0;
+    double x = fmax(ax1, bx1), y = fmax(ay1, by1);
+    double w = __dsub_rn(fmin(ax2, bx2), x), h = __dsub_rn(fmin(ay2, by2), y);
+    if (w < 0.0 || h < 0.0) return 0.0;
+    double inter = __dmul_rn(w, h);
+    if (inter == 0.0) return 0.0;
+    double area_a = __dmul_rn(__dsub_rn(ax2, ax1), __dsub_rn(ay2, ay1));
+    double area_b = __dmul_rn(__dsub_rn(bx2, bx1), __dsub_rn(by2, by1));
+    double uni = __dsub_rn(__dadd_rn(area_a, area_b), inter);
+    return __ddiv_rn(inter, __dadd_rn(uni, 1e-6));
+}
+
+struct AnchorPx { double x1, x2, y1, y2; };
+
+__device__ __forceinline__ AnchorPx anchor_px(double stride, int ix, int jy, double aw, double ah) {
+    AnchorPx a;
+    double cx = __dmul_rn(stride, (double)ix + 0.5), cy = __dmul_rn(stride, (double)jy + 0.5);
+    a.x1 = __dsub_rn(cx, __ddiv_rn(aw, 2.0));      // utils.py:625
+    a.x2 = __dadd_rn(cx, __ddiv_rn(aw, 2.0));      // utils.py:626
+    a.y1 = __dsub_rn(cy, __ddiv_rn(ah, 2.0));      // utils.py:635
+    a.y2 = __dadd_rn(cy, __ddiv_rn(ah, 2.0));      // utils.py:636
+    return a;
+}
+
+// (tx,ty,tw,th) of utils.py:669-687
+__device__ __forceinline__ void regr_targets(const AnchorPx &a, double gx1, double gx2, double gy1,
+                                             double gy2, double t[4]) {
+    double cx = __ddiv_rn(__dadd_rn(gx1, gx2), 2.0), cy = __ddiv_rn(__dadd_rn(gy1, gy2), 2.0);
+    double cxa = __ddiv_rn(__dadd_rn(a.x1, a.x2), 2.0), cya = __ddiv_rn(__dadd_rn(a.y1, a.y2), 2.0);
+    double wa = __dsub_rn(a.x2, a.x1), ha = __dsub_rn(a.y2, a.y1);
+    t[0] = __ddiv_rn(__dsub_rn(cx, cxa), wa);
+    t[1] = __ddiv_rn(__dsub_rn(cy, cya), ha);
+    t[2] = log(__ddiv_rn(__dsub_rn(gx2, gx1), wa));
+    t[3] = log(__ddiv_rn(__dsub_rn(gy2, gy1), ha));
+}
+
+__global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *s_gt = reinterpret_cast<double *>(smem);                                   // [G][4]
+    unsigned long long *s_best = reinterpret_cast<unsigned long long *>(s_gt + 4 * p.Gmax);
+    int *s_hits = reinterpret_cast<int *>(s_best + p.Gmax);
+    uint8_t *s_bg = reinterpret_cast<uint8_t *>(s_hits + p.Gmax);
+
+    const int b = blockIdx.z, a = blockIdx.y;
+    const int HW = p.H * p.W;
+    const int G = p.gt_count[b];
+    for (int i = threadIdx.x; i < G * 4; i += kTgtThreads) s_gt[i] = p.gt[(size_t)b * p.Gmax * 4 + i];
+    for (int i = threadIdx.x; i < G; i += kTgtThreads) {
+        s_best[i] = 0ull;
+        s_hits[i] = 0;
+        s_bg[i] = p.gt_is_bg[(size_t)b * p.Gmax + i];
+    }
+    __syncthreads();
+
+    const int cell = blockIdx.x * kTgtThreads + threadIdx.x;
+    const bool in_map = cell < HW;
+    const int jy = in_map ? cell / p.W : 0, ix = in_map ? cell - jy * p.W : 0;
+    const double aw = p.anchors.wh[a][0], ah = p.anchors.wh[a][1];
+    const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
+    const double img_w = p.img_wh[2 * b], img_h = p.img_wh[2 * b + 1];
+    // anchors crossing the image are skipped entirely (utils.py:629,638)
+    const bool inside = in_map && !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h);
+    const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);     // size->ratio->ix->jy
+    const int lane = threadIdx.x & 31;
+
+    bool pos = false;
+    double loc_best = 0.0;
+    int loc_g = -1;
+    for (int g = 0; g < G; ++g) {
+        double iou = 0.0;
+        if (inside)
+            iou = ref_iou(s_gt[4 * g + 0], s_gt[4 * g + 2], s_gt[4 * g + 1], s_gt[4 * g + 3], an.x1, an.y1,
+                          an.x2, an.y2);
+        const bool fg = !s_bg[g];
+        const float iou32 = (float)iou;
+        unsigned long long key = 0ull;
+        if (fg && iou32 > 0.f) key = ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order);
+        const bool hit = fg && iou > p.max_overlap;                   // utils.py:704
+        if (hit) {
+            pos = true;
+            if (iou > loc_best) { loc_best = iou; loc_g = g; }        // utils.py:710-713
+        }
+        // warp-aggregate, then one shared atomic per warp
+        if (__any_sync(0xffffffffu, key != 0ull)) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
+                key = o > key ? o : key;
+            }
+            if (lane == 0) atomicMax(&s_best[g], key);
+        }
+        unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm && lane == 0) atomicAdd(&s_hits[g], __popc(hm));
+    }
+
+    if (in_map) {
+        // labels are written inside the GT loop of the reference: no GT, no labels (utils.py:722-738)
+        const double valid = (inside && G > 0) ? 1.0 : 0.0;
+        const double ov = pos ? 1.0 : 0.0;
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        if (pos) regr_targets(an, s_gt[4 * loc_g + 0], s_gt[4 * loc_g + 1], s_gt[4 * loc_g + 2], s_gt[4 * loc_g + 3], t);
+        double *cls_b = p.y_cls + (size_t)b * 2 * p.A * HW;
+        double *regr_b = p.y_regr + (size_t)b * 8 * p.A * HW;
+        cls_b[(size_t)a * HW + cell] = valid;
+        cls_b[(size_t)(p.A + a) * HW + cell] = ov;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            regr_b[(size_t)(4 * a + k) * HW + cell] = ov;                       // np.repeat(overlap,4)
+            regr_b[(size_t)(4 * p.A + 4 * a + k) * HW + cell] = t[k];
+        }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += kTgtThreads) {
+        if (s_best[g]) atomicMax(&p.best_key[(size_t)b * p.Gmax + g], s_best[g]);
+        if (s_hits[g]) atomicAdd(&p.n_hits[(size_t)b * p.Gmax + g], s_hits[g]);
+    }
+}
+
+// forced positives + best_anchor table, one thread per panel, GT in order (utils.py:741-766)
+__global__ void rpn_targets_finalize_kernel(RpnTargetParams p, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int HW = p.H * p.W;
+    const int G = p.gt_count[b];
+    double *cls_b = p.y_cls + (size_t)b * 2 * p.A * HW;
+    double *regr_b = p.y_regr + (size_t)b * 8 * p.A * HW;
+    for (int g = 0; g < p.Gmax; ++g) {
+        int32_t *ba = p.best_anchor + ((size_t)b * p.Gmax + g) * 4;
+        unsigned long long key = (g < G) ? p.best_key[(size_t)b * p.Gmax + g] : 0ull;
+        if (!key) {
+            ba[0] = ba[1] = ba[2] = ba[3] = -1;
+            continue;
+        }
+        unsigned order = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+        int jy = (int)(order % (unsigned)p.H);
+        unsigned rest = order / (unsigned)p.H;
+        int ix = (int)(rest % (unsigned)p.W);
+        int a = (int)(rest / (unsigned)p.W);
+        ba[0] = jy; ba[1] = ix; ba[2] = a % p.n_ratios; ba[3] = a / p.n_ratios;     // utils.py:697
+        if (p.n_hits[(size_t)b * p.Gmax + g] != 0) continue;
+        const double *gt = p.gt + ((size_t)b * p.Gmax + g) * 4;
+        AnchorPx an = anchor_px(p.stride, ix, jy, p.anchors.wh[a][0], p.anchors.wh[a][1]);
+        double t[4];
+        regr_targets(an, gt[0], gt[1], gt[2], gt[3], t);
+        const int cell = jy * p.W + ix;
+        cls_b[(size_t)a * HW + cell] = 1.0;
+        cls_b[(size_t)(p.A + a) * HW + cell] = 1.0;
+        for (int k = 0; k < 4; ++k) {
+            regr_b[(size_t)(4 * a + k) * HW + cell] = 1.0;
+            regr_b[(size_t)(4 * p.A + 4 * a + k) * HW + cell] = (double)(float)t[k];   // float32 store utils.py:605
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// a4: calc_iou per-RoI loop.  Single CTA, order-preserving compaction by block scan.
+// ----------------------------------------------------------------------------------
+struct RoiTargetParams {
+    const int32_t *rois; int R;
+    const double *gt; const int32_t *gt_class; int G;
+    int n_cls, bg_class;
+    double min_overlap, max_overlap;
+    double std4[4];
+    int32_t *x_roi; int32_t *y_class; double *y_regr; double *ious; int32_t *count;
+};
+
+__global__ void __launch_bounds__(1024) roi_targets_kernel(RoiTargetParams p) {
+    __shared__ int s_warp[33];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int n_regr = 4 * (p.n_cls - 1);
+    for (int r0 = 0; r0 < p.R; r0 += 1024) {
+        const int r = r0 + threadIdx.x;
+        bool keep = false;
+        double best = 0.0;
+        int best_g = -1;
+        int x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+        if (r < p.R) {
+            int4 bx = reinterpret_cast<const int4 *>(p.rois)[r];
+            x1 = bx.x; y1 = bx.y; x2 = bx.z; y2 = bx.w;
+            for (int g = 0; g < p.G; ++g) {                                        // rpn.py:220-226
+                const double *q = p.gt + 4 * g;
+                double cur = ref_iou(q[0], q[2], q[1], q[3], (double)x1, (double)y1, (double)x2, (double)y2);
+                if (cur > best) { best = cur; best_g = g; }
+            }
+            keep = !(best < p.min_overlap);                                        // rpn.py:228
+        }
+        // order-preserving slot
+        unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[w] = __popc(km);
+        __syncthreads();
+        if (w == 0) {
+            int v = s_warp[lane], inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += n;
+            }
+            s_warp[lane] = inc - v;
+            if (lane == 31) s_warp[32] = inc;
+        }
+        __syncthreads();
+        const int base = s_base;
+        if (keep) {
+            const int slot = base + s_warp[w] + __popc(km & lanemask_lt());
+            const int wd = x2 - x1, ht = y2 - y1;
+            reinterpret_cast<int4 *>(p.x_roi)[slot] = make_int4(x1, y1, wd, ht);   // rpn.py:234-236
+            p.ious[slot] = best;
+            int cls = p.bg_class;
+            double t[4] = {0, 0, 0, 0};
+            if (best >= p.max_overlap) {                                           // rpn.py:244-256
+                cls = p.gt_class[best_g];
+                const double *q = p.gt + 4 * best_g;
+                double cxg = __ddiv_rn(__dadd_rn(q[0], q[1]), 2.0), cyg = __ddiv_rn(__dadd_rn(q[2], q[3]), 2.0);
+                double cx = __dadd_rn((double)x1, __ddiv_rn((double)wd, 2.0));
+                double cy = __dadd_rn((double)y1, __ddiv_rn((double)ht, 2.0));
+                t[0] = __ddiv_rn(__dsub_rn(cxg, cx), (double)wd);
+                t[1] = __ddiv_rn(__dsub_rn(cyg, cy), (double)ht);
+                t[2] = log(__ddiv_rn(__dsub_rn(q[1], q[0]), (double)wd));
+                t[3] = log(__ddiv_rn(__dsub_rn(q[3], q[2]), (double)ht));
+            }
+            int32_t *yc = p.y_class + (size_t)slot * p.n_cls;
+            for (int c = 0; c < p.n_cls; ++c) yc[c] = (c == cls) ? 1 : 0;          // rpn.py:263-266
+            double *yr = p.y_regr + (size_t)slot * 2 * n_regr;
+            for (int c = 0; c < 2 * n_regr; ++c) yr[c] = 0.0;
+            if (cls != p.bg_class) {                                               // rpn.py:270-277
+                for (int k = 0; k < 4; ++k) {
+                    yr[4 * cls + k] = 1.0;
+                    yr[n_regr + 4 * cls + k] = __dmul_rn(p.std4[k], t[k]);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + s_warp[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *p.count = s_base;
+}
+
+}  // namespace radnet
+
+using namespace radnet;
+
+extern "C" size_t radnet_rpn_targets_workspace_bytes(int B, int Gmax) {
+    if (B < 1 || Gmax < 0) return 0;
+    return align_up((size_t)B * (Gmax > 0 ? Gmax : 1) * sizeof(unsigned long long), 256);
+}
+
+extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, const int32_t *gt_count, int B,
+                                  int Gmax, int H, int W, int A, int n_ratios, const double *h_anchor_px,
+                                  double rpn_stride, const double *img_wh, double max_overlap,
+                                  double *y_rpn_cls, double *y_rpn_regr, int32_t *best_anchor, int32_t *n_hits,
+                                  void *ws, size_t ws_bytes, void *stream) {
+    RADNET_CHECK_ARG(gt_count && h_anchor_px && img_wh && y_rpn_cls && y_rpn_regr && ws, "rpn_targets: null pointer");
+    RADNET_CHECK_ARG(Gmax == 0 || (gt && gt_is_bg && best_anchor && n_hits), "rpn_targets: null GT buffers");
+    RADNET_CHECK_ARG(B >= 1 && B <= 65535 && H >= 1 && W >= 1 && A >= 1 && A <= kMaxAnchors && n_ratios >= 1 && Gmax >= 0,
+                     "rpn_targets: bad sizes B=%d H=%d W=%d A=%d Gmax=%d", B, H, W, A, Gmax);
+    RADNET_CHECK_ARG((long long)A * H * W < 0x7fffffffLL, "rpn_targets: anchor count overflows the loop-order key");
+    size_t need = radnet_rpn_targets_workspace_bytes(B, Gmax);
+    if (ws_bytes < need) {
+        set_error("rpn_targets: workspace %zu < %zu", ws_bytes, need);
+        return RADNET_E_WORKSPACE;
+    }
+    size_t smem = (size_t)Gmax * (4 * 8 + 8 + 4 + 1) + 16;
+    RADNET_CHECK_ARG(smem <= 200 * 1024, "rpn_targets: Gmax=%d too large for shared memory", Gmax);
+    RpnTargetParams p{};
+    p.gt = gt; p.gt_is_bg = gt_is_bg; p.gt_count = gt_count;
+    p.Gmax = Gmax; p.H = H; p.W = W; p.A = A; p.n_ratios = n_ratios;
+    for (int a = 0; a < A; ++a) {
+        p.anchors.wh[a][0] = h_anchor_px[2 * a];
+        p.anchors.wh[a][1] = h_anchor_px[2 * a + 1];
+    }
+    p.stride = rpn_stride; p.img_wh = img_wh; p.max_overlap = max_overlap;
+    p.y_cls = y_rpn_cls; p.y_regr = y_rpn_regr; p.best_anchor = best_anchor; p.n_hits = n_hits;
+    p.best_key = reinterpret_cast<unsigned long long *>(ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    RADNET_CUDA(cudaMemsetAsync(ws, 0, need, st));
+    if (Gmax > 0) RADNET_CUDA(cudaMemsetAsync(n_hits, 0, sizeof(int32_t) * (size_t)B * Gmax, st));
+    if (smem > 48 * 1024)
+        RADNET_CUDA(cudaFuncSetAttribute(rpn_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((H * W + kTgtThreads - 1) / kTgtThreads, A, B);
+    rpn_targets_kernel<<<grid, kTgtThreads, smem, st>>>(p);
+    int rc = check_launch("rpn_targets_kernel");
+    if (rc) return rc;
+    if (Gmax > 0) {
+        rpn_targets_finalize_kernel<<<(B + 63) / 64, 64, 0, st>>>(p, B);
+        rc = check_launch("rpn_targets_finalize_kernel");
+    }
+    return rc;
+}
+
+extern "C" int radnet_roi_targets(const int32_t *rois, int R, const double *gt, const int32_t *gt_class, int G,
+                                  int n_cls, int bg_class, double min_overlap, double max_overlap,
+                                  const double *h_regr_std4, int32_t *x_roi, int32_t *y_class, double *y_regr,
+                                  double *ious, int32_t *count, void *stream) {
+    RADNET_CHECK_ARG(rois && h_regr_std4 && x_roi && y_class && y_regr && ious && count, "roi_targets: null pointer");
+    RADNET_CHECK_ARG(R >= 1 && G >= 0 && n_cls >= 2 && bg_class >= 0 && bg_class < n_cls, "roi_targets: bad sizes");
+    RADNET_CHECK_ARG(G == 0 || (gt && gt_class), "roi_targets: null GT buffers");
+    RoiTargetParams p{};
+    p.rois = rois; p.R = R; p.gt = gt; p.gt_class = gt_class; p.G = G;
+    p.n_cls = n_cls; p.bg_class = bg_class; p.min_overlap = min_overlap; p.max_overlap = max_overlap;
+    for (int k = 0; k < 4; ++k) p.std4[k] = h_regr_std4[k];
+    p.x_roi = x_roi; p.y_class = y_class; p.y_regr = y_regr; p.ious = ious; p.count = count;
+    roi_targets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("roi_targets_kernel");
+}

@@ -1,0 +1,149 @@
+"""Batched, device-resident proposal -> NMS -> RoI-pool pipeline.
+
+`ProposalPipeline` keeps every buffer of a batch of panels in HBM (decoded boxes,
+sort scratch, detection records, pooled features) and launches the three kernels
+back to back on the caller's stream:
+
+    K1 radnet_decode_clip_i32   (reference rpn.py:91-166)
+    K2 radnet_sort_nms_i32      (reference rpn.py:380-456, called at rpn.py:170)
+    K4 radnet_roi_pool          (reference RoiPoolingConv.py:48-88, fed as RADNet.py:564-568)
+
+It is what `bench.py` times and what the single-panel drop-in functions in
+`rpn.py` / `RoiPoolingConv.py` are thin wrappers of (B = 1).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _device as D
+from . import _lib
+
+
+def anchor_cells(C):
+    """Anchor (w,h) in feature cells, a = size-major, ratio-minor (reference rpn.py:108-113)."""
+    out = []
+    for scale in C.anchor_box_scales:
+        for ratio in C.anchor_box_ratios:
+            out.append(((scale * ratio[0]) / C.rpn_stride, (scale * ratio[1]) / C.rpn_stride))
+    return D.host_f64(out)
+
+
+def anchor_pixels(C):
+    """Anchor (w,h) in pixels, a = ratio_idx + n_ratios*size_idx (reference utils.py:616-620,725)."""
+    out = []
+    for scale in C.anchor_box_scales:
+        for ratio in C.anchor_box_ratios:
+            out.append((scale * ratio[0], scale * ratio[1]))
+    return D.host_f64(out)
+
+
+class DetectionRecords:
+    """Typed views over the per-panel detection records written by K2
+    (layout: include/radnet_b200.h, `radnet_det_record_bytes`)."""
+
+    def __init__(self, batch, max_boxes, device, raw=None):
+        self.batch = batch
+        self.max_boxes = max_boxes
+        self.stride = _lib.det_record_bytes(max_boxes)
+        self.raw = raw if raw is not None else torch.zeros((batch, self.stride), dtype=torch.uint8, device=device)
+        words = self.raw.view(torch.int32)
+        k = max_boxes
+        self.header = words[:, 0:4]                                   # count, n_candidates, ties, 0
+        self.boxes = words[:, 4:4 + 4 * k].view(batch, k, 4)          # x1,y1,x2,y2
+        self.scores = words[:, 4 + 4 * k:4 + 5 * k].view(torch.float32)
+        self.index = words[:, 4 + 5 * k:4 + 6 * k]
+
+    @property
+    def counts(self):
+        return self.header[:, 0]
+
+    def to_numpy(self):
+        """-> list of dicts with int64 boxes (k,4), float32 scores, int64 flat indices."""
+        hdr = self.header.cpu().numpy()
+        if (hdr[:, 3] != 0).any():
+            raise RuntimeError("radnet_sort_nms_i32: hand-off watchdog fired (kernel bug); results invalid")
+        boxes = self.boxes.cpu().numpy()
+        scores = self.scores.cpu().numpy()
+        index = self.index.cpu().numpy()
+        out = []
+        for b in range(self.batch):
+            n = int(hdr[b, 0])
+            out.append({"boxes": boxes[b, :n].astype(np.int64), "scores": scores[b, :n].copy(),
+                        "index": index[b, :n].astype(np.int64), "n_candidates": int(hdr[b, 1]),
+                        "score_ties": int(hdr[b, 2])})
+        return out
+
+
+class ProposalPipeline:
+    """Decode + NMS + RoI pool for `batch` panels with H x W x A anchors each."""
+
+    def __init__(self, C, batch, H, W, channels=1024, pool_size=14, max_boxes=300,
+                 overlap_thresh=0.7, device=None, alloc_pooled=True):
+        D.require_cuda()
+        _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.C = C
+        self.batch, self.H, self.W = int(batch), int(H), int(W)
+        self.A = len(C.anchor_box_scales) * len(C.anchor_box_ratios)
+        self.N = self.H * self.W * self.A
+        self.channels, self.pool_size = int(channels), int(pool_size)
+        self.max_boxes, self.overlap_thresh = int(max_boxes), float(overlap_thresh)
+        self.std_scaling = float(C.std_scaling)
+        self._anchors = anchor_cells(C)
+        dev = self.device
+        self.boxes = D.empty((self.batch, self.N, 4), np.int32, dev)
+        self.keys = torch.empty((self.batch, self.N), dtype=torch.int32, device=dev)      # uint32 bits
+        self.stats = D.zeros((self.batch, 4), np.int32, dev)
+        self.records = DetectionRecords(self.batch, self.max_boxes, dev)
+        lib = _lib.load()
+        self._ws_bytes = int(lib.radnet_sort_nms_i32_workspace_bytes(self.batch, self.N, self.H, self.W, self.max_boxes))
+        self._ws = torch.empty((max(self._ws_bytes, 16),), dtype=torch.uint8, device=dev)
+        self.pooled = None
+        if alloc_pooled:
+            self.pooled = D.empty((self.batch, self.max_boxes, self.pool_size, self.pool_size, self.channels),
+                                  np.float32, dev)
+
+    # -- individual stages (all asynchronous on the current stream) ------------------
+    def decode(self, cls, regr, use_regr=True):
+        assert cls.shape == (self.batch, self.H, self.W, self.A), cls.shape
+        assert regr.shape == (self.batch, self.H, self.W, 4 * self.A), regr.shape
+        _lib.call("radnet_decode_clip_i32", D.ptr(cls), D.ptr(regr), self.batch, self.H, self.W, self.A,
+                  D.ptr(self._anchors), ctypes.c_float(self.std_scaling), 1 if use_regr else 0,
+                  D.ptr(self.boxes), D.ptr(self.keys), D.ptr(self.stats), D.stream_ptr(self.device))
+
+    def sort_nms(self):
+        _lib.call("radnet_sort_nms_i32", D.ptr(self.boxes), D.ptr(self.keys), self.batch, self.N, self.H, self.W,
+                  self.overlap_thresh, self.max_boxes, D.ptr(self.records.raw), D.ptr(self._ws),
+                  self._ws_bytes, D.stream_ptr(self.device))
+
+    def pool(self, feat, out=None):
+        out = self.pooled if out is None else out
+        assert feat.shape == (self.batch, self.H, self.W, self.channels), feat.shape
+        _lib.call("radnet_roi_pool", D.ptr(feat), self.batch, self.H, self.W, self.channels,
+                  D.ptr(self.records.raw), self.max_boxes, None, None, self.max_boxes, self.pool_size,
+                  D.ptr(out), D.stream_ptr(self.device))
+        return out
+
+    def __call__(self, cls, regr, feat):
+        """cls (B,H,W,A), regr (B,H,W,4A), feat (B,H,W,C): float32 CUDA tensors.
+        Returns (DetectionRecords, pooled (B,max_boxes,pool,pool,C)); nothing is synchronised."""
+        self.decode(cls, regr)
+        self.sort_nms()
+        pooled = self.pool(feat)
+        return self.records, pooled
+
+    # -- bookkeeping ----------------------------------------------------------------
+    def launches_per_step(self):
+        """Kernels of ours launched by one __call__ (decode, sort+nms, pool)."""
+        return 3
+
+    def check_stats(self):
+        """Synchronises.  Raises like the reference when a panel has no candidate left or a
+        non-finite box reaches the NMS assert (reference rpn.py:170, rpn.py:400-401)."""
+        st = self.stats.cpu().numpy()
+        if (st[:, 1] > 0).any():
+            raise AssertionError("non-finite proposal coordinates (np.testing.assert_array_less, rpn.py:400)")
+        if (st[:, 0] == 0).any():
+            raise ValueError("not enough values to unpack (expected 2, got 0)")
+        return st

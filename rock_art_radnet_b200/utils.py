@@ -1,0 +1,121 @@
+"""Drop-in for the hot-path functions of the reference `faster_rcnn/utils.py`:
+`calc_region_props` (upstream keras-frcnn name `calc_rpn`), `get_new_img_size`, `iou`.
+
+The anchor x GT IoU / label / regression-target computation runs in
+libradnet_b200.so (`radnet_rpn_targets`); the host keeps what the reference also
+does on the host with the global NumPy RNG: the 256-region subsampling.
+"""
+import numpy as np
+import torch
+
+from . import _device as D
+from . import _lib
+from .pipeline import anchor_pixels
+
+
+def get_new_img_size(width, height, img_min_side=300):
+    """(resized_width, resized_height) with the short side at img_min_side (reference utils.py:65-75)."""
+    if width <= height:
+        f = float(img_min_side) / width
+        return img_min_side, int(f * height)
+    f = float(img_min_side) / height
+    return int(f * width), img_min_side
+
+
+def iou(a, b):
+    """Scalar IoU of (x1,y1,x2,y2) boxes, host convenience (reference utils.py:77-109)."""
+    if a[0] >= a[2] or a[1] >= a[3] or b[0] >= b[2] or b[1] >= b[3]:
+        return 0.0
+    w = min(a[2], b[2]) - max(a[0], b[0])
+    h = min(a[3], b[3]) - max(a[1], b[1])
+    inter = 0 if (w < 0 or h < 0) else w * h
+    union = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+    return float(inter) / float(union + 1e-6)
+
+
+def rpn_targets_device(C, gt_boxes, gt_is_bg, gt_count, H, W, img_wh, device=None):
+    """Batched device call.  gt_boxes (B,Gmax,4) float64 x1,x2,y1,y2 in resized pixels,
+    gt_is_bg (B,Gmax) uint8, gt_count (B,) int32, img_wh (B,2) float64.
+    Returns CUDA tensors (y_rpn_cls (B,2A,H,W), y_rpn_regr (B,8A,H,W), best_anchor (B,Gmax,4),
+    n_hits (B,Gmax)) BEFORE the RNG subsampling of utils.py:777-813."""
+    D.require_cuda()
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    lib = _lib.load()
+    gt_count = D.to_device(gt_count, np.int32, dev)
+    B = int(gt_count.shape[0])
+    Gmax = int(gt_boxes.shape[1]) if gt_boxes is not None else 0
+    A = len(C.anchor_box_scales) * len(C.anchor_box_ratios)
+    gt_dev = D.to_device(gt_boxes, np.float64, dev) if Gmax else None
+    bg_dev = D.to_device(gt_is_bg, np.uint8, dev) if Gmax else None
+    wh_dev = D.to_device(img_wh, np.float64, dev)
+    y_cls = D.empty((B, 2 * A, H, W), np.float64, dev)
+    y_regr = D.empty((B, 8 * A, H, W), np.float64, dev)
+    best = D.empty((B, max(Gmax, 1), 4), np.int32, dev)
+    hits = D.zeros((B, max(Gmax, 1)), np.int32, dev)
+    ws_bytes = int(lib.radnet_rpn_targets_workspace_bytes(B, Gmax))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    _lib.call("radnet_rpn_targets", D.ptr(gt_dev), D.ptr(bg_dev), D.ptr(gt_count), B, Gmax, H, W, A,
+              len(C.anchor_box_ratios), D.ptr(anchor_pixels(C)), float(C.rpn_stride), D.ptr(wh_dev),
+              float(C.rpn_max_overlap), D.ptr(y_cls), D.ptr(y_regr), D.ptr(best), D.ptr(hits), D.ptr(ws),
+              ws_bytes, D.stream_ptr(dev))
+    return y_cls, y_regr, best[:, :Gmax], hits[:, :Gmax]
+
+
+def _subsample_regions(y_is_box_valid, y_rpn_overlap, max_n_regions=256):
+    """Host half of calc_region_props: random balancing to 256 regions with the legacy global
+    NumPy RNG, in place on the (1,A,H,W) arrays (reference utils.py:777-813).  Returns n_pos."""
+    where_pos = np.where(np.logical_and(y_rpn_overlap[0] == 1, y_is_box_valid[0] == 1))
+    where_neg = np.where(np.logical_and(y_rpn_overlap[0] == 0, y_is_box_valid[0] == 1))
+    n_pos, n_neg = len(where_pos[0]), len(where_neg[0])
+    half = int(max_n_regions / 2)
+
+    def channel_weights(channels, total):
+        # per-candidate probability = (share of its anchor channel) / (size of that channel);
+        # the table is keyed by the NEGATIVE channel ids in both branches, as in utils.py:789,804
+        ids, counts = np.unique(where_neg[0], return_counts=True)
+        share = dict(zip(ids, counts / total))
+        size = dict(zip(ids, counts))
+        return [share[c] / size[c] for c in channels]
+
+    if n_pos > max_n_regions / 2:
+        drop = np.random.choice(n_pos, n_pos - half, replace=False, p=channel_weights(where_pos[0], n_pos))
+        y_is_box_valid[0, where_pos[0][drop], where_pos[1][drop], where_pos[2][drop]] = 0
+        n_pos = half
+    if n_neg + n_pos > max_n_regions:
+        drop = np.random.choice(n_neg, n_neg - n_pos, replace=False, p=channel_weights(where_neg[0], n_neg))
+        y_is_box_valid[0, where_neg[0][drop], where_neg[1][drop], where_neg[2][drop]] = 0
+    return n_pos
+
+
+def calc_region_props(C, img_data, width, height, width_resized, height_resized, get_feat_map_size,
+                      verbose=False):
+    """RPN anchor targets for one image (reference utils.py:554-821).
+
+    Returns (y_rpn_cls (1,2A,fh,fw) float64 = [valid | overlap],
+             y_rpn_regr (1,8A,fh,fw) float64 = [repeat(overlap,4) | regr],
+             best_anchor_for_bbox (G,4) int64, n_pos)."""
+    fw, fh = get_feat_map_size(width_resized, height_resized)                 # utils.py:592
+    bboxes = img_data['bboxes']
+    G = len(bboxes)
+    gt = np.zeros((1, max(G, 1), 4))
+    is_bg = np.zeros((1, max(G, 1)), dtype=np.uint8)
+    for k, bb in enumerate(bboxes):                                           # utils.py:608-613
+        gt[0, k, 0] = bb['x1'] * (width_resized / float(width))
+        gt[0, k, 1] = bb['x2'] * (width_resized / float(width))
+        gt[0, k, 2] = bb['y1'] * (height_resized / float(height))
+        gt[0, k, 3] = bb['y2'] * (height_resized / float(height))
+        is_bg[0, k] = 1 if bb['class'] == 'bg' else 0
+    y_cls_d, y_regr_d, best_d, _ = rpn_targets_device(
+        C, gt if G else None, is_bg if G else None, np.array([G], dtype=np.int32), int(fh), int(fw),
+        np.array([[float(width_resized), float(height_resized)]]))
+    A = y_cls_d.shape[1] // 2
+    y_cls = y_cls_d.cpu().numpy()
+    y_rpn_regr = y_regr_d.cpu().numpy()
+    y_is_box_valid = y_cls[:, :A]
+    y_rpn_overlap = y_cls[:, A:]
+    n_pos = _subsample_regions(y_is_box_valid, y_rpn_overlap)
+    best_anchor_for_bbox = best_d[0].cpu().numpy().astype(np.int64).reshape(G, 4)
+    return np.copy(y_cls), np.copy(y_rpn_regr), best_anchor_for_bbox, n_pos
+
+
+calc_rpn = calc_region_props

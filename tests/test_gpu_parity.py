@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path (through the ctypes C-ABI and the drop-in functions)
+against the CPU oracle and the committed reference golden vectors.
+
+Bars (BASELINE.json north_star): kept-proposal indices and anchor labels bit-exact;
+decoded boxes bit-exact here (integer valued; exp() near-ties are counted by the kernel);
+regression targets within 1e-12 relative (device log() vs NumPy log(), <= 1-2 ulp);
+pooled features bit-exact against the float32 restatement (tolerance allowed 1e-5 rel).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from conftest import dense_regr  # noqa: E402
+from oracle import radnet_oracle as O  # noqa: E402
+from oracle.make_golden import a3_inputs, nms_inputs  # noqa: E402
+from rock_art_radnet_b200 import synthetic as S  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+REGR_RTOL = 1e-12      # float64 targets: log() ulp differences only
+POOL_RTOL = 1e-5       # north_star tolerance for pooled features (we expect bit-exact)
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    import rock_art_radnet_b200 as R
+    from rock_art_radnet_b200 import _lib
+    _lib.load()
+    return R
+
+
+# ----------------------------------------------------------------------------- a1 / K1+K2
+def test_rpn_to_roi_matches_reference_golden(pkg, manifest, golden_a1):
+    for case in manifest["a1"]:
+        C = S.HotPathConfig(case["scales"])
+        cls, regr = S.rpn_maps(case["seed"], case["H"], case["W"], C.num_anchors, case["realistic"])
+        R = pkg.rpn_to_roi(cls, regr, C, use_regr=case["use_regr"], max_boxes=case["max_boxes"],
+                           overlap_thresh=case["thr"])
+        ref = golden_a1[case["name"] + "/R"]
+        assert R.dtype == ref.dtype and R.flags.writeable
+        assert np.array_equal(R, ref), case["name"]
+
+
+def test_decode_boxes_and_kept_indices_bit_exact(pkg):
+    from rock_art_radnet_b200.pipeline import ProposalPipeline
+    C = S.HotPathConfig()
+    B, H, W = 6, 38, 38
+    maps = [S.rpn_maps(100 + s, H, W, 9, realistic=bool(s % 2)) for s in range(B)]
+    cls = torch.from_numpy(np.concatenate([m[0] for m in maps])).cuda()
+    regr = torch.from_numpy(np.concatenate([m[1] for m in maps])).cuda()
+    pipe = ProposalPipeline(C, B, H, W, alloc_pooled=False)
+    pipe.decode(cls, regr)
+    pipe.sort_nms()
+    stats = pipe.check_stats()
+    boxes = pipe.boxes.cpu().numpy()
+    keys = pipe.keys.cpu().numpy().view(np.uint32)
+    dets = pipe.records.to_numpy()
+    for b in range(B):
+        dbg = O.rpn_to_roi(maps[b][0], maps[b][1], C, max_boxes=300, overlap_thresh=0.7, return_debug=True)
+        keep = dbg["keep_mask"]
+        assert stats[b, 0] == keep.sum() and stats[b, 1] == 0
+        assert np.array_equal((keys[b] != 0), keep)
+        assert np.array_equal(boxes[b][keep].astype(np.float64), dbg["all_boxes"][keep])   # decoded boxes
+        assert np.array_equal(dets[b]["index"], dbg["pick_flat"])                         # kept indices
+        assert np.array_equal(dets[b]["boxes"], dbg["boxes"])
+        assert np.array_equal(dets[b]["scores"], dbg["probs"])
+        assert dets[b]["n_candidates"] == keep.sum() and dets[b]["score_ties"] == 0
+
+
+@pytest.mark.parametrize("H,W,scales,thr,mb", [
+    (38, 50, (128, 256, 512), 0.7, 300),      # 600x800 panel
+    (38, 38, (64, 128, 256, 512), 0.7, 300),  # reference default 12 anchors -> global-memory sort path
+    (100, 100, (128, 256, 512), 0.7, 300),    # un-tiled 1600-px stress: 90,000 candidates in one segment
+    (38, 38, (128, 256, 512), 0.3, 2000),     # kept list larger than the shared-memory list
+    (7, 5, (128, 256, 512), 0.9, 300),
+    (1, 1, (128,), 0.7, 300),
+])
+def test_rpn_to_roi_shapes_and_paths(pkg, H, W, scales, thr, mb):
+    C = S.HotPathConfig(scales)
+    cls, regr = S.rpn_maps(7, H, W, C.num_anchors)
+    try:
+        ref = O.rpn_to_roi(cls, regr, C, max_boxes=mb, overlap_thresh=thr)
+    except ValueError:
+        with pytest.raises(ValueError):
+            pkg.rpn_to_roi(cls, regr, C, max_boxes=mb, overlap_thresh=thr)
+        return
+    got = pkg.rpn_to_roi(cls, regr, C, max_boxes=mb, overlap_thresh=thr)
+    assert np.array_equal(got, ref)
+
+
+def test_rpn_to_roi_score_ties_follow_documented_rule(pkg):
+    C = S.HotPathConfig()
+    cls, regr = S.rpn_maps(11)
+    cls = (np.floor(cls * 40) / 40).astype(np.float32)          # ~40 distinct scores -> many ties
+    ref = O.rpn_to_roi(cls, regr, C, max_boxes=300, overlap_thresh=0.7)
+    got = pkg.rpn_to_roi(cls, regr, C, max_boxes=300, overlap_thresh=0.7)
+    assert np.array_equal(got, ref)
+    from rock_art_radnet_b200.rpn import _single_panel_pipeline
+    pipe = _single_panel_pipeline(C, 38, 38, 300, 0.7)
+    flat = cls.transpose((0, 3, 1, 2)).reshape(-1)
+    dbg = O.decode_proposals(cls, regr, C)
+    assert pipe.records.to_numpy()[0]["score_ties"] == O.count_score_ties(flat[dbg[2]])
+
+
+def test_rpn_to_roi_errors(pkg):
+    C = S.HotPathConfig()
+    cls, regr = S.rpn_maps(0, 4, 4, 9)
+    with pytest.raises(AssertionError):
+        pkg.rpn_to_roi(np.concatenate([cls, cls]), np.concatenate([regr, regr]), C)
+    bad = regr.copy()
+    bad[0, 1, 1, 2] = np.float32(4000.0)     # exp overflow -> inf - inf = NaN survives to the NMS assert
+    with pytest.raises(AssertionError):
+        O.rpn_to_roi(cls, bad, C)
+    with pytest.raises(AssertionError):
+        pkg.rpn_to_roi(cls, bad, C)
+
+
+def test_apply_regr_np(pkg):
+    rng = np.random.default_rng(3)
+    X = np.stack([rng.uniform(-5, 40, (18, 25)), rng.uniform(-5, 40, (18, 25)),
+                  rng.uniform(1, 30, (18, 25)), rng.uniform(1, 30, (18, 25))])
+    T = (0.3 * rng.standard_normal((4, 18, 25))).astype(np.float32)
+    got = pkg.apply_regr_np(X, T)
+    ref = O.apply_regr_np(X, T)
+    assert got.dtype == np.float64 and got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    assert pkg.apply_regr_np(X, T[:3]) is X      # swallowed exception returns X (rpn.py:342-344)
+
+
+# ----------------------------------------------------------------------------- a2 general NMS
+def test_nms_matches_reference_golden(pkg, manifest, golden_a2):
+    for case in manifest["a2"]:
+        b, p = nms_inputs(case["seed"], case["M"], case["kind"])
+        boxes, probs = pkg.non_max_suppression_fast(b, p, overlap_thresh=case["thr"], max_boxes=case["max_boxes"])
+        n = case["name"]
+        assert boxes.dtype == golden_a2[n + "/boxes"].dtype
+        assert np.array_equal(boxes, golden_a2[n + "/boxes"]), n
+        assert np.array_equal(probs, golden_a2[n + "/probs"]), n
+        from rock_art_radnet_b200.rpn import nms_with_indices
+        pick, ties = nms_with_indices(b, p, case["thr"], case["max_boxes"])
+        assert np.array_equal(pick, golden_a2[n + "/pick"]) and ties == 0
+
+
+def test_nms_edge_cases(pkg):
+    assert pkg.non_max_suppression_fast(np.zeros((0, 4)), np.zeros((0,))) == []
+    with pytest.raises(AssertionError):
+        pkg.non_max_suppression_fast(np.array([[5.0, 0, 5.0, 4]]), np.array([0.5]))
+    b, p = nms_inputs(3, 50, False)
+    boxes, _ = pkg.non_max_suppression_fast(b, p, max_boxes=0)
+    assert boxes.shape == (1, 4)
+    # large M, float64 scores that do not fit float32, default threshold
+    rng = np.random.default_rng(9)
+    b, _ = nms_inputs(21, 20000, False)
+    p = rng.random(20000)
+    ref = O.non_max_suppression_fast(b, p, return_pick=True)
+    got = pkg.non_max_suppression_fast(b, p)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    # near-threshold IoUs: identical translated boxes (IoU lattice), every threshold on the lattice
+    base = np.array([[0.0, 0.0, 10.0, 10.0]])
+    shifts = np.arange(0, 40)[:, None] * np.array([[1.0, 0.0, 1.0, 0.0]])
+    bb = base + shifts
+    pp = np.linspace(1.0, 0.1, 40)
+    for thr in (9.0 / 11.0, 8.0 / 12.0, 0.5, 1.0 / 3.0):
+        ref = O.non_max_suppression_fast(bb, pp, overlap_thresh=thr, return_pick=True)
+        got = pkg.non_max_suppression_fast(bb, pp, overlap_thresh=thr)
+        assert np.array_equal(got[0], ref[0]), thr
+
+
+# ----------------------------------------------------------------------------- a3 / K3
+def test_calc_region_props_matches_reference_golden(pkg, manifest, golden_a3):
+    C = S.HotPathConfig()
+    for case in manifest["a3"]:
+        n = case["name"]
+        img = a3_inputs(case["seed"], case["width"], case["height"], case["n_gt"], tuple(case["classes"]),
+                        small=(n == "small_gt"))
+        wr, hr = case["resized"]
+        np.random.seed(case["seed"])
+        y_cls, y_regr, best, n_pos = pkg.calc_region_props(C, img, case["width"], case["height"], wr, hr,
+                                                           S.resnet50_map_size)
+        assert y_cls.dtype == np.float64 and y_regr.dtype == np.float64 and best.dtype == np.int64
+        assert y_cls.flags.writeable and y_regr.flags.writeable
+        assert np.array_equal(y_cls, golden_a3[n + "/y_rpn_cls"].astype(np.float64)), n      # labels bit-exact
+        ref_regr = dense_regr(golden_a3, n)
+        assert np.array_equal(y_regr != 0, ref_regr != 0), n
+        np.testing.assert_allclose(y_regr, ref_regr, rtol=REGR_RTOL, atol=0)
+        assert np.array_equal(best, golden_a3[n + "/best_anchor"]), n
+        assert int(n_pos) == int(golden_a3[n + "/n_pos"])
+    assert pkg.calc_rpn is pkg.calc_region_props
+
+
+def test_rpn_targets_batched_presample_vs_oracle(pkg):
+    from rock_art_radnet_b200.utils import rpn_targets_device
+    C = S.HotPathConfig((64, 128, 256, 512))          # 12 anchors
+    sizes = [(600, 600, 20), (800, 600, 9), (600, 750, 33), (600, 600, 0)]
+    B, Gmax = len(sizes), 33
+    gt = np.zeros((B, Gmax, 4)); bg = np.zeros((B, Gmax), np.uint8); cnt = np.zeros(B, np.int32)
+    wh = np.zeros((B, 2)); imgs = []
+    for b, (w, h, g) in enumerate(sizes):
+        img = S.gt_figures(40 + b, g, w, h, classes=("boat", "bg", "human"))
+        imgs.append(img)
+        for k, bb in enumerate(img["bboxes"]):
+            gt[b, k] = [bb["x1"], bb["x2"], bb["y1"], bb["y2"]]
+            bg[b, k] = bb["class"] == "bg"
+        cnt[b] = g
+        wh[b] = [w, h]
+    # batched call needs one map size: use the 600x600 map for every panel (anchors outside the
+    # smaller image are skipped by the img_wh test, as in the reference)
+    fw, fh = 50, 47
+    y_cls, y_regr, best, hits = rpn_targets_device(C, gt, bg, cnt, fh, fw, wh)
+    y_cls, y_regr, best, hits = (t.cpu().numpy() for t in (y_cls, y_regr, best, hits))
+    A = 12
+    for b, (w, h, g) in enumerate(sizes):
+        valid, overlap, regr, ba, nh = O.rpn_targets_presample(C, imgs[b], w, h, w, h, lambda *_: (fw, fh))
+        assert np.array_equal(y_cls[b, :A], valid.transpose(2, 0, 1))
+        assert np.array_equal(y_cls[b, A:], overlap.transpose(2, 0, 1))
+        assert np.array_equal(y_regr[b, :4 * A], np.repeat(overlap.transpose(2, 0, 1), 4, axis=0))
+        np.testing.assert_allclose(y_regr[b, 4 * A:], regr.transpose(2, 0, 1), rtol=REGR_RTOL, atol=0)
+        assert np.array_equal(best[b, :g], ba) and (best[b, g:] == -1).all()
+        assert np.array_equal(hits[b, :g], nh)
+
+
+# ----------------------------------------------------------------------------- a4
+def test_calc_iou_matches_reference_golden(pkg, manifest, golden_a4):
+    C = S.HotPathConfig()
+    for case in manifest["a4"]:
+        img = S.gt_figures(case["seed"], case["n_gt"], 600, 600, classes=tuple(case["classes"]))
+        cls, regr = S.rpn_maps(case["seed"])
+        R = pkg.rpn_to_roi(cls, regr, C, max_boxes=300, overlap_thresh=0.7)
+        X, Y1, Y2, ious = pkg.calc_iou(R, img, C, C.class_mapping)
+        n = case["name"]
+        assert X.dtype == np.int64 and Y1.dtype == np.int64 and Y2.dtype == golden_a4[n + "/Y2"].dtype
+        assert np.array_equal(X, golden_a4[n + "/X"]) and np.array_equal(Y1, golden_a4[n + "/Y1"])
+        ref = golden_a4[n + "/Y2"]
+        assert np.array_equal(Y2 != 0, ref != 0)
+        np.testing.assert_allclose(Y2, ref, rtol=REGR_RTOL, atol=0)
+        assert np.array_equal(np.asarray(ious), golden_a4[n + "/ious"]) and isinstance(ious, list)
+    far = {"bboxes": [{"class": "boat", "x1": 0, "x2": 2, "y1": 0, "y2": 2}], "width": 600, "height": 600}
+    cls, regr = S.rpn_maps(0)
+    R = pkg.rpn_to_roi(cls, regr, C, max_boxes=20, overlap_thresh=0.7)
+    assert pkg.calc_iou(R, far, C, C.class_mapping) == (None, None, None, None)
+    # many RoIs (> one block pass) and no GT at all
+    rng = np.random.default_rng(5)
+    x1 = rng.integers(0, 30, 2500); y1 = rng.integers(0, 30, 2500)
+    Rbig = np.stack([x1, y1, x1 + rng.integers(1, 8, 2500), y1 + rng.integers(1, 8, 2500)], 1)
+    img = S.gt_figures(3, 15, 600, 600, classes=("boat", "wheel"))
+    ref = O.calc_iou(Rbig, img, C, C.class_mapping)
+    got = pkg.calc_iou(Rbig, img, C, C.class_mapping)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    np.testing.assert_allclose(got[2], ref[2], rtol=REGR_RTOL, atol=0)
+    assert pkg.calc_iou(Rbig, {"bboxes": [], "width": 600, "height": 600}, C, C.class_mapping) == (None,) * 4
+
+
+# ----------------------------------------------------------------------------- a5 / K4
+def _all_size_rois(H, W):
+    rois = []
+    for w in range(1, W):
+        h = 1 + (w * 7) % (H - 1)
+        rois.append([(w * 3) % (W - w), (w * 5) % (H - h), w, h])
+    for h in (1, 14, 28, H - 1):
+        for w in (1, 14, 28, W - 1):
+            rois.append([0, 0, w, h])
+    return np.array(rois, dtype=np.int64)[None]
+
+
+@pytest.mark.parametrize("H,W,Cn,pool", [(38, 38, 1024, 14), (38, 50, 1024, 14), (38, 38, 512, 7),
+                                         (20, 16, 36, 3), (9, 11, 7, 5)])
+def test_roi_pooling_conv_vs_oracle(pkg, H, W, Cn, pool):
+    feat = S.feature_map(1, H, W, Cn)
+    rois = _all_size_rois(H, W)
+    layer = pkg.RoiPoolingConv(pool, rois.shape[1])
+    got = layer([feat, rois])
+    ref = O.roi_pooling_conv(feat, rois, pool)
+    assert got.shape == ref.shape == (1, rois.shape[1], pool, pool, Cn) and got.dtype == np.float32
+    assert layer.compute_output_shape([feat.shape, rois.shape]) == (None, rois.shape[1], pool, pool, Cn)
+    assert layer.get_config() == {"pool_size": pool, "num_rois": rois.shape[1]}
+    np.testing.assert_allclose(got, ref, rtol=POOL_RTOL, atol=1e-6)
+    assert np.array_equal(got, ref), "expected bit-exact float32 (no FMA contraction)"
+
+
+def test_roi_pooling_direct_kernel_matches(pkg, monkeypatch):
+    monkeypatch.setenv("RADNET_ROIPOOL_FORCE_DIRECT", "1")
+    feat = S.feature_map(2, 38, 38, 256)
+    rois = _all_size_rois(38, 38)
+    got = pkg.RoiPoolingConv(14, rois.shape[1])([feat, rois])
+    assert np.array_equal(got, O.roi_pooling_conv(feat, rois, 14))
+
+
+def test_roi_pooling_clamp_float_and_errors(pkg):
+    feat = S.feature_map(3, 12, 12, 64)
+    rois = np.array([[[2.9, 3.2, 20.7, 4.0], [0, 0, 12, 12], [11, 11, 5, 5]]])   # float rois truncate, ends clamp
+    got = pkg.RoiPoolingConv(7, 3)([feat, rois])
+    assert np.array_equal(got, O.roi_pooling_conv(feat, rois, 7))
+    with pytest.raises(ValueError):
+        pkg.RoiPoolingConv(7, 1)([feat, np.array([[[12, 0, 3, 3]]])])
+    with pytest.raises(ValueError):
+        pkg.RoiPoolingConv(7, 1)([feat, np.array([[[-1, 0, 3, 3]]])])
+    t = torch.from_numpy(feat).cuda()
+    out = pkg.RoiPoolingConv(7, 3)([t, rois])
+    assert out.is_cuda and np.array_equal(out.cpu().numpy(), got)
+
+
+# ----------------------------------------------------------------------------- full path
+def test_pipeline_batch_end_to_end(pkg):
+    from rock_art_radnet_b200.pipeline import ProposalPipeline
+    C = S.HotPathConfig()
+    B, H, W, Cn = 3, 38, 38, 1024
+    maps = [S.rpn_maps(200 + s) for s in range(B)]
+    feats = [S.feature_map(200 + s) for s in range(B)]
+    maps[2] = (maps[2][0], (maps[2][1] * 0).astype(np.float32))     # panel with < 300 survivors
+    pipe = ProposalPipeline(C, B, H, W, channels=Cn, pool_size=14, max_boxes=300, overlap_thresh=0.7)
+    rec, pooled = pipe(torch.from_numpy(np.concatenate([m[0] for m in maps])).cuda(),
+                       torch.from_numpy(np.concatenate([m[1] for m in maps])).cuda(),
+                       torch.from_numpy(np.concatenate(feats)).cuda())
+    pipe.check_stats()
+    dets = rec.to_numpy()
+    pooled = pooled.cpu().numpy()
+    for b in range(B):
+        R = O.rpn_to_roi(maps[b][0], maps[b][1], C, max_boxes=300, overlap_thresh=0.7)
+        assert np.array_equal(dets[b]["boxes"], R)
+        xywh = R.copy()
+        xywh[:, 2] -= xywh[:, 0]
+        xywh[:, 3] -= xywh[:, 1]                                     # RADNet.py:564-565
+        ref = O.roi_pooling_conv(feats[b], xywh[None], 14)[0]
+        k = R.shape[0]
+        assert np.array_equal(pooled[b, :k], ref)
+        assert not pooled[b, k:].any()                               # unused slots are zero-filled
+    assert dets[2]["boxes"].shape[0] < 300

@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the RADNet proposal -> NMS -> RoI-pool hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[2]): a batch of 64 synthetic 600-px panels per GPU
+(38x38 ResNet-50 stride-16 maps, 9 anchors, 1024 feature channels), decode + sort + NMS
+(overlap 0.7, 300 kept boxes) + 14x14 RoI pool.  One "step" = one pass of the hot path over
+one batch per GPU.  Metric: panels/sec, whole job (all GPUs), weak scaling.
+
+  value  device-resident throughput: inputs already in HBM, CUDA events on the launching stream
+  e2e    same metric through the public host API (HostPanelStream): pinned host buffers ->
+         H2D -> kernels -> detection records D2H, every step
+  roofline   the dominant kernel (roi_pool_slice_kernel) against the MEASURED HBM copy peak
+  cpu_baseline  the oracle port of the reference's NumPy path on this box's host cores
+
+`--impl reference` times the CPU path only (rank 0), same metric/config, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PANELS_PER_GPU = 64
+H = W = 38
+A = 9
+CH = 1024
+POOL = 14
+MAX_BOXES = 300
+THR = 0.7
+FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def config_dict(n_gpus):
+    return {
+        "workload": "BASELINE configs[2]: batch of 64 synthetic 600-px panels per GPU, decode+NMS+14x14 RoI pool",
+        "panels_per_gpu": PANELS_PER_GPU, "map": [H, W], "anchors": A, "feature_channels": CH,
+        "pool": POOL, "max_boxes": MAX_BOXES, "overlap_thresh": THR,
+        "parallelism": "per-panel sharding x%d, NCCL all-gather of detection records" % n_gpus,
+        "l2_policy": "inputs larger than L2 (378 MB of feature maps in, 15.4 GB of pooled features out per step)",
+    }
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def _cpu_one_panel(seed):
+    """Reference path for one panel on one core: rpn_to_roi + RoiPoolingConv over the kept boxes."""
+    from oracle import radnet_oracle as O
+    from rock_art_radnet_b200 import synthetic as S
+    C = S.HotPathConfig()
+    cls, regr = S.rpn_maps(seed, H, W, A)
+    feat = S.feature_map(seed, H, W, CH)
+    t0 = time.perf_counter()
+    R = O.rpn_to_roi(cls, regr, C, max_boxes=MAX_BOXES, overlap_thresh=THR)
+    R[:, 2] -= R[:, 0]
+    R[:, 3] -= R[:, 1]
+    out = O.roi_pooling_conv(feat, R[None], POOL)
+    return time.perf_counter() - t0, int(R.shape[0]), float(out[0, 0, 0, 0, 0])
+
+
+def cpu_sample(n_panels, workers, seed0=0):
+    """Run n_panels reference panels over `workers` processes; returns (panels/s, wall s)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_one_panel, range(seed0, seed0 + workers))          # warm the workers (imports, caches)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_one_panel, range(seed0 + 1000, seed0 + 1000 + n_panels), chunksize=1)
+        wall = time.perf_counter() - t0
+    assert all(r[1] > 0 for r in res)
+    return n_panels / wall, wall
+
+
+def host_workers():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workers = host_workers()
+    per_step = workers                       # one panel per worker per step (about 1.2 s of wall each)
+    for _ in range(args.warmup):
+        cpu_sample(per_step, workers)
+    t_total, n_total = 0.0, 0
+    for k in range(args.steps):
+        v, wall = cpu_sample(per_step, workers, seed0=5000 + k * per_step)
+        t_total += wall
+        n_total += per_step
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": "panels_per_sec", "value": value, "unit": "panels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 decode/NMS + f32 pooling (NumPy)", "data": "synthetic",
+        "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "panels/s", "cores": workers, "kind": "port",
+                         "sample": "%d panels per step (one per worker process), %d steps; oracle port of "
+                                   "rpn_to_roi + RoiPoolingConv (TF-1 bilinear restatement)" % (per_step, args.steps)},
+        "e2e": {"value": value, "unit": "panels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def run_b200_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # CPU baseline first: worker processes are forked before this process touches CUDA
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        workers = host_workers()
+        v, wall = cpu_sample(2 * workers, workers)
+        cpu_baseline = {"value": v, "unit": "panels/s", "cores": workers, "kind": "port",
+                        "sample": "%d panels over %d worker processes (%.1f s wall); oracle port of "
+                                  "rpn_to_roi + RoiPoolingConv" % (2 * workers, workers, wall)}
+
+    import torch
+    import torch.distributed as dist
+    from rock_art_radnet_b200 import synthetic as S
+    from rock_art_radnet_b200 import sharding
+    from rock_art_radnet_b200.pipeline import HostPanelStream, ProposalPipeline
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    C = S.HotPathConfig()
+    B = args.panels
+    # synthetic panels of this rank (global panel id = rank + world*i), generated on the host
+    ids = [rank + world * i for i in range(B)]
+    cls_h = torch.empty((B, H, W, A), dtype=torch.float32).pin_memory()
+    regr_h = torch.empty((B, H, W, 4 * A), dtype=torch.float32).pin_memory()
+    feat_h = torch.empty((B, H, W, CH), dtype=torch.float32).pin_memory()
+    for i, pid in enumerate(ids):
+        c, r = S.rpn_maps(pid, H, W, A)
+        cls_h[i] = torch.from_numpy(c[0])
+        regr_h[i] = torch.from_numpy(r[0])
+        feat_h[i] = torch.from_numpy(S.feature_map(pid, H, W, CH)[0])
+    cls_d, regr_d, feat_d = cls_h.to(dev), regr_h.to(dev), feat_h.to(dev)
+
+    pipe = ProposalPipeline(C, B, H, W, channels=CH, pool_size=POOL, max_boxes=MAX_BOXES, overlap_thresh=THR,
+                            device=dev)
+    gathered = torch.empty((world, B, pipe.records.stride), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step(evs=None):
+        s = torch.cuda.current_stream()
+        if evs:
+            evs[0].record(s)
+        pipe.decode(cls_d, regr_d)
+        if evs:
+            evs[1].record(s)
+        pipe.sort_nms()
+        if evs:
+            evs[2].record(s)
+        work = None
+        if world > 1:
+            _, work = sharding.gather_detections(pipe.records.raw, async_op=True, out=gathered)
+        pipe.pool(feat_d)
+        if evs:
+            evs[3].record(s)
+        if work is not None:
+            work.wait()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    pipe.check_stats()
+    counts = pipe.records.counts.cpu().numpy()
+
+    # ---- timed region: K steps, device-resident inputs ------------------------------
+    K = args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(K):
+        step(evs[k])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = t_start.elapsed_time(t_end)
+    dec_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
+    nms_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    pool_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+
+    # ---- NMS latency: single-panel launches, p50 / p95 ------------------------------
+    single = ProposalPipeline(C, 1, H, W, alloc_pooled=False, device=dev)
+    lat = []
+    for i in range(40):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        single.decode(cls_d[i % B:i % B + 1], regr_d[i % B:i % B + 1])
+        a.record()
+        single.sort_nms()
+        b_.record()
+        b_.synchronize()
+        if i >= 8:
+            lat.append(a.elapsed_time(b_) * 1e3)
+    lat.sort()
+
+    # ---- e2e: public host API, H2D + kernels + D2H of the records every step --------
+    stream = HostPanelStream(pipe)
+    for _ in range(2):
+        stream.submit(cls_h, regr_h, feat_h)
+        stream.collect()
+    barrier()
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    inflight = 0
+    checksum = 0
+    for k in range(K):
+        stream.submit(cls_h, regr_h, feat_h)
+        inflight += 1
+        if inflight == 2:
+            checksum += int(stream.collect()[0, 0])
+            inflight -= 1
+    while inflight:
+        checksum += int(stream.collect()[0, 0])
+        inflight -= 1
+    torch.cuda.synchronize()
+    e1.record()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    # ---- max over ranks ------------------------------------------------------------
+    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        panels = world * B * K
+        value = panels / (elapsed_ms * 1e-3)
+        kept = int(counts.sum())
+        # algorithmic bytes of the RoI-pool launch: map once + rois + pooled output
+        pool_bytes = B * (H * W * CH * 4) + kept * 16 + kept * POOL * POOL * CH * 4
+        peak, peak_src = measured_hbm_peak()
+        achieved = pool_bytes / (pool_ms * 1e-3) / 1e9
+        line = {
+            "metric": "panels_per_sec", "value": value, "unit": "panels/s", "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 decode, int32 exact NMS, f32 pooling", "data": "synthetic",
+            "config": dict(config_dict(world), panels_per_gpu=B), "impl": "b200",
+            "clocks": clocks,
+            "e2e": {"value": panels / (e2e_ms * 1e-3), "unit": "panels/s",
+                    "h2d_bytes_per_step": stream.h2d_bytes_per_batch, "d2h_bytes_per_step": stream.d2h_bytes_per_batch,
+                    "note": "HostPanelStream: pinned host maps -> H2D -> decode+NMS+pool -> detection records D2H; "
+                            "pooled features stay in HBM for the classifier head"},
+            "gpu_launches": 3 * K,
+            "kernels_ms_per_step": {"decode_clip": dec_ms, "sort_nms": nms_ms, "roi_pool": pool_ms},
+            "nms_latency_us": {"p50": lat[len(lat) // 2], "p95": lat[int(len(lat) * 0.95) - 1], "n": len(lat),
+                               "what": "radnet_sort_nms_i32, one 600-px panel (12,996 candidates) per launch"},
+            "roofline": {"kernel": "roi_pool_slice_kernel<8>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": pool_bytes, "avg_launch_ms": pool_ms},
+            "kept_boxes_per_step": kept,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--panels", type=int, default=PANELS_PER_GPU,
+                    help="panels per GPU per step (default = the BASELINE workload; smaller only for profiling)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

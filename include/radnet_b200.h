@@ -43,7 +43,8 @@ enum {
 
 /* Per-panel detection record written by radnet_sort_nms_i32 and exchanged between
  * ranks (one NCCL gather per batch).  A record is
- *   int32 header[4] = {count, n_candidates, n_score_ties, reserved}
+ *   int32 header[4] = {count (-1 = internal fault), n_candidates, n_score_ties among the
+ *                      n_sorted top-scoring candidates the kernel had to sort, n_sorted}
  *   int32 boxes [max_boxes][4]   x1,y1,x2,y2 in feature cells, score-descending
  *   float scores[max_boxes]
  *   int32 index [max_boxes]      flat anchor index a*H*W + r*W + c of each kept box
@@ -116,7 +117,8 @@ int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *keys, int B, i
  *   valid [M] uint8 or NULL: rows with valid==0 are skipped (the rows rpn_to_roi deletes
  *         as degenerate, rpn.py:163-166); NULL = all rows are candidates
  *   pick  [min(max_boxes,M)] int32 picked row indices, score-descending
- *   count [2] int32 {n_picked, n_score_ties}
+ *   count [3] int32 {n_picked (-1 = internal fault), n_score_ties among the n_sorted
+ *         top-scoring candidates the kernel had to sort, n_sorted}
  */
 size_t radnet_nms_f64_workspace_bytes(int M, int max_boxes);
 int radnet_nms_f64(const double *boxes, const double *probs, const uint8_t *valid, int M, double thr,

@@ -25,7 +25,6 @@
 namespace radnet {
 
 constexpr int kPoolThreads = 512;
-constexpr int kRoiChunk = 32;
 constexpr int kMaxPool = 32;
 
 struct RoiPoolParams {
@@ -40,12 +39,12 @@ struct RoiPoolParams {
     int pool;
     float *out;              // [B][R][pool][pool][C]
     int n_slices;
+    int roi_chunk;           // RoIs whose y tables fit in shared memory at once
 };
 
-struct AxisEntry {           // 16 bytes, one LDS.128
-    int off0, off1;          // byte offsets into the shared slice
+struct YEntry {              // 8 bytes, one LDS.64
+    unsigned short r0, r1;   // pixel index of the first cell of source rows y+y0 / y+y1
     float lerp;
-    int pad;
 };
 
 // RoI k of panel b as (x,y,w,h), already int32-truncated by the caller (RoiPoolingConv.py:69-72);
@@ -82,8 +81,31 @@ __device__ __forceinline__ void legacy_axis(int i, int in_size, int pool, int &l
 __device__ __forceinline__ float lerp1(float a, float b, float t) {
     return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
 }
+
+// a + (b-a)*t on two lanes at once: packed subtract and multiply (FADD2/FMUL2), SCALAR final
+// adds.  ptxas 12.9 contracts a packed multiply feeding a packed add into FFMA2 even for
+// explicitly rounded PTX (and for the __fmul2_rn/__fadd2_rn intrinsics), which would break
+// bit-parity with TF's unfused arithmetic; a scalar add.rn.f32 is never contracted.
+// tests/test_build_sass.py checks the SASS of these kernels for FFMA.
+__device__ __forceinline__ void lerp2(float a0, float a1, float b0, float b1, unsigned long long tt,
+                                      float &r0, float &r1) {
+    unsigned long long a, b, d, m;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(b), "l"(a));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(d), "l"(tt));
+    float m0, m1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(m0), "=f"(m1) : "l"(m));
+    r0 = __fadd_rn(a0, m0);
+    r1 = __fadd_rn(a1, m1);
+}
 __device__ __forceinline__ float4 lerp4(const float4 &a, const float4 &b, float t) {
-    return make_float4(lerp1(a.x, b.x, t), lerp1(a.y, b.y, t), lerp1(a.z, b.z, t), lerp1(a.w, b.w, t));
+    unsigned long long tt;
+    asm("mov.b64 %0, {%1,%1};" : "=l"(tt) : "f"(t));
+    float4 r;
+    lerp2(a.x, a.y, b.x, b.y, tt, r.x, r.y);
+    lerp2(a.z, a.w, b.z, b.w, tt, r.z, r.w);
+    return r;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -93,81 +115,108 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// LANES = float4 lanes per pixel in the slice (8 -> 32 channels, 4 -> 16, 2 -> 8, 1 -> 4)
+// LANES = float4 lanes per pixel in the slice (8 -> 32 channels, 4 -> 16, 2 -> 8, 1 -> 4).
+//
+// Work decomposition: a group of LANES threads owns one output COLUMN (roi, px) and walks
+// py = 0..pool-1.  The horizontal interpolation of a source row, hrow(r) = tl + (tr-tl)*xlerp,
+// does not depend on py, so the two rows an output needs are cached in registers and reused
+// while y0/y1 repeat (always, when the RoI is upsampled: h < pool); only rows that change are
+// re-sampled (2 LDS.128 each).  top/bottom of TF's formula are exactly hrow(y0)/hrow(y1), so
+// the result is bit-identical to evaluating all four taps per output.
 template <int LANES>
 __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPoolParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int kPixBytes = LANES * 16;
+    constexpr int G = kPoolThreads / LANES;          // columns in flight per CTA
     const int HW = p.H * p.W;
-    float4 *s_map = reinterpret_cast<float4 *>(smem);                              // [HW+1][LANES]
-    AxisEntry *s_tab = reinterpret_cast<AxisEntry *>(smem + (size_t)(HW + 1) * kPixBytes);  // [chunk][2][pool]
+    const int pool = p.pool, PP = pool * pool;
+    float4 *s_map = reinterpret_cast<float4 *>(smem);                                   // [HW+1][LANES]
+    YEntry *s_ytab = reinterpret_cast<YEntry *>(smem + (size_t)(HW + 1) * kPixBytes);   // [chunk][pool]
+    int2 *s_roi = reinterpret_cast<int2 *>(s_ytab + (size_t)p.roi_chunk * pool);        // [chunk] {x, cw}
 
     const int b = blockIdx.x / p.n_slices;
     const int s = blockIdx.x - b * p.n_slices;
     const int C4 = p.C >> 2;
     const int q = threadIdx.x % LANES;
     const int g = threadIdx.x / LANES;
-    constexpr int G = kPoolThreads / LANES;          // pixel groups per CTA iteration
 
-    // ---- stage the channel slice of the whole map ---------------------------------
+    // ---- stage the channel slice of the whole map (read from HBM exactly once) --------
     {
         const float4 *src = reinterpret_cast<const float4 *>(p.feat) + (size_t)b * HW * C4 + (size_t)s * LANES + q;
         for (int pix = g; pix < HW; pix += G) cp_async16(&s_map[pix * LANES + q], src + (size_t)pix * C4);
         if (g == 0) s_map[HW * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);      // the "zero pixel"
         cp_async_wait_all();
     }
-    const int pool = p.pool, PP = pool * pool;
-    // per-iteration stepping of (roi, py, px) by G pixels
-    const int d_roi = G / PP, d_rem = G % PP, d_py = d_rem / pool, d_px = d_rem % pool;
     const unsigned char *mapb = reinterpret_cast<const unsigned char *>(s_map) + q * 16;
+    const size_t py_step = (size_t)pool * C4;
 
-    for (int r0 = 0; r0 < p.R; r0 += kRoiChunk) {
-        const int nr = min(kRoiChunk, p.R - r0);
+    for (int r0 = 0; r0 < p.R; r0 += p.roi_chunk) {
+        const int nr = min(p.roi_chunk, p.R - r0);
         __syncthreads();     // previous chunk done with the tables (and the map has landed)
-        for (int e = threadIdx.x; e < nr * 2 * pool; e += kPoolThreads) {
-            int rl = e / (2 * pool);
-            int rem = e - rl * 2 * pool;
-            int axis = rem / pool;               // 0 = x, 1 = y
-            int i = rem - axis * pool;
+        for (int e = threadIdx.x; e < nr * pool; e += kPoolThreads) {
+            int rl = e / pool, i = e - rl * pool;
             int x, y, cw, ch;
-            AxisEntry en;
+            YEntry en;
             if (fetch_roi(p, b, r0 + rl, x, y, cw, ch)) {
                 int lo, hi;
-                legacy_axis(i, axis ? ch : cw, pool, lo, hi, en.lerp);
-                int stride = axis ? p.W * kPixBytes : kPixBytes;
-                int org = axis ? y : x;
-                en.off0 = (org + lo) * stride;
-                en.off1 = (org + hi) * stride;
+                legacy_axis(i, ch, pool, lo, hi, en.lerp);
+                en.r0 = (unsigned short)((y + lo) * p.W);
+                en.r1 = (unsigned short)((y + hi) * p.W);
+                if (i == 0) s_roi[rl] = make_int2(x, cw);
             } else {
-                // x entries point at the zero pixel, y entries add nothing: output is exactly 0
-                en.off0 = en.off1 = axis ? 0 : HW * kPixBytes;
+                // rows add nothing and the column points at the zero pixel: output is exactly 0
+                en.r0 = en.r1 = 0;
                 en.lerp = 0.f;
+                if (i == 0) s_roi[rl] = make_int2(0, 0);
             }
-            en.pad = 0;
-            s_tab[e] = en;
+            s_ytab[e] = en;
         }
         __syncthreads();
 
-        // walk the chunk's output pixels: item = rl*PP + py*pool + px, G items per iteration
-        int rl = g / PP, rem = g - rl * PP;
-        int py = rem / pool, px = rem - py * pool;
-        float4 *dst = reinterpret_cast<float4 *>(p.out) +
-                      (((size_t)b * p.R + r0) * PP + g) * C4 + (size_t)s * LANES + q;
-        const size_t dst_step = (size_t)G * C4;
-        while (rl < nr) {
-            const AxisEntry ex = s_tab[(rl * 2 + 0) * pool + px];
-            const AxisEntry ey = s_tab[(rl * 2 + 1) * pool + py];
-            const float4 tl = *reinterpret_cast<const float4 *>(mapb + ey.off0 + ex.off0);
-            const float4 tr = *reinterpret_cast<const float4 *>(mapb + ey.off0 + ex.off1);
-            const float4 bl = *reinterpret_cast<const float4 *>(mapb + ey.off1 + ex.off0);
-            const float4 br = *reinterpret_cast<const float4 *>(mapb + ey.off1 + ex.off1);
-            const float4 top = lerp4(tl, tr, ex.lerp);
-            const float4 bot = lerp4(bl, br, ex.lerp);
-            st_stream_f4(dst, lerp4(top, bot, ey.lerp));
-            dst += dst_step;
-            rl += d_roi; py += d_py; px += d_px;
-            if (px >= pool) { px -= pool; ++py; }
-            if (py >= pool) { py -= pool; ++rl; }
+        const int ncol = nr * pool;
+        for (int col = g; col < ncol; col += G) {
+            const int rl = col / pool, px = col - rl * pool;
+            const int2 rx = s_roi[rl];
+            int xo0, xo1;
+            float lx;
+            if (rx.y > 0) {
+                int lo, hi;
+                legacy_axis(px, rx.y, pool, lo, hi, lx);
+                xo0 = (rx.x + lo) * kPixBytes;
+                xo1 = (rx.x + hi) * kPixBytes;
+            } else {
+                xo0 = xo1 = HW * kPixBytes;
+                lx = 0.f;
+            }
+            const YEntry *yt = s_ytab + rl * pool;
+            float4 *dst = reinterpret_cast<float4 *>(p.out) +
+                          (((size_t)b * p.R + r0 + rl) * PP + px) * C4 + (size_t)s * LANES + q;
+            int cur0 = -1, cur1 = -1;
+            float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+#pragma unroll 2
+            for (int py = 0; py < pool; ++py) {
+                const YEntry e = yt[py];
+                const int ra = e.r0, rb = e.r1;
+                float4 n0, n1;
+                if (ra == cur0) n0 = h0;
+                else if (ra == cur1) n0 = h1;
+                else {
+                    const unsigned char *row = mapb + ra * kPixBytes;
+                    n0 = lerp4(*reinterpret_cast<const float4 *>(row + xo0),
+                               *reinterpret_cast<const float4 *>(row + xo1), lx);
+                }
+                if (rb == ra) n1 = n0;
+                else if (rb == cur1) n1 = h1;
+                else if (rb == cur0) n1 = h0;
+                else {
+                    const unsigned char *row = mapb + rb * kPixBytes;
+                    n1 = lerp4(*reinterpret_cast<const float4 *>(row + xo0),
+                               *reinterpret_cast<const float4 *>(row + xo1), lx);
+                }
+                h0 = n0; h1 = n1; cur0 = ra; cur1 = rb;
+                st_stream_f4(dst, lerp4(h0, h1, e.lerp));
+                dst += py_step;
+            }
         }
     }
 }
@@ -250,18 +299,21 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
     int dev = 0, smem_limit = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
     RADNET_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t tab_bytes = (size_t)kRoiChunk * 2 * pool * sizeof(AxisEntry);
     const size_t HW = (size_t)H * W;
-    if (C % 4 == 0 && !force_direct() && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&
+    const size_t per_roi = (size_t)pool * sizeof(YEntry) + sizeof(int2);
+    if (C % 4 == 0 && !force_direct() && HW < 65536 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const int C4 = C / 4;
         const int lanes_opts[4] = {8, 4, 2, 1};
         for (int li = 0; li < 4; ++li) {
             int L = lanes_opts[li];
-            size_t smem = (HW + 1) * L * 16 + tab_bytes;
-            if (C4 % L != 0 || smem > (size_t)smem_limit) continue;
-            if (HW * L * 16 >= 0x7fffffffULL) continue;
+            size_t map_bytes = (HW + 1) * L * 16;
+            if (C4 % L != 0 || map_bytes + 8 * per_roi > (size_t)smem_limit) continue;
+            size_t chunk = ((size_t)smem_limit - map_bytes) / per_roi;
+            if (chunk > (size_t)rois_per_panel) chunk = rois_per_panel;
+            size_t smem = map_bytes + chunk * per_roi;
             p.n_slices = C4 / L;
+            p.roi_chunk = (int)chunk;
             if ((long long)B * p.n_slices >= 0x7fffffffLL) continue;
             switch (L) {
                 case 8: return launch_slice<8>(p, B, smem, st);

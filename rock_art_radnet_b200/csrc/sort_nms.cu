@@ -88,6 +88,7 @@ struct SortNmsParams {
     int max_boxes;            // effective K = min(max_boxes, N)
     double thr;
     int table_entries;        // i32 only: umax + 1
+    int sel_target;           // candidates the first (selective) sort round aims for
     // outputs
     unsigned char *det;       // i32: detection records
     size_t det_stride;
@@ -131,33 +132,60 @@ __device__ __forceinline__ int block_exscan(int v, int *s_warp, int *total) {
     return s_warp[w] + inc - v;
 }
 
-// One stable radix pass over n_in elements.  first=true: input is the raw key array
-// (index = position, key 0 skipped).  Returns number of elements written (block-uniform),
-// or -1 when the pass was skipped because every element shares the digit.
-template <typename KeyT, typename IdxT>
-__device__ int radix_pass(const KeyT *in_k, const IdxT *in_i, KeyT *out_k, IdxT *out_i, int n_in,
-                          int shift, bool first, uint32_t *s_cnt, int *s_scan, int *s_flag) {
+// Lanes of the warp holding the same 8-bit digit as me (valid for active lanes).  Eight
+// ballots instead of __match_any_sync: MATCH.ANY serialises over the distinct values of the
+// warp (~30 for a random byte) and was the top stall of the first version of this kernel.
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d, bool act) {
+    uint32_t peers = __ballot_sync(0xffffffffu, act);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool bit = (d >> k) & 1u;
+        const uint32_t b = __ballot_sync(0xffffffffu, act && bit);
+        peers &= bit ? b : ~b;
+    }
+    return peers;
+}
+
+template <typename KeyT>
+__device__ __forceinline__ bool in_range(KeyT k, KeyT lo, KeyT hi) { return k >= lo && k <= hi; }
+
+// Per-warp digit histogram of the keys in [lo,hi] (warp w owns a contiguous slice of the
+// array and the counter row s_cnt[w][*]).  No atomics: one leader lane per digit and row.
+template <typename KeyT>
+__device__ void count_walk(const KeyT *in_k, int n_in, int shift, KeyT lo, KeyT hi, uint32_t *s_cnt) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kNmsWarps * kCntStride; i += kNmsThreads) s_cnt[i] = 0;
-    if (threadIdx.x == 0) *s_flag = 0;
     __syncthreads();
-    int chunk = ((n_in + kNmsWarps - 1) / kNmsWarps + 31) & ~31;
-    int wbeg = min(w * chunk, n_in), wend = min(wbeg + chunk, n_in);
+    const int chunk = ((n_in + kNmsWarps - 1) / kNmsWarps + 31) & ~31;
+    const int wbeg = min(w * chunk, n_in), wend = min(wbeg + chunk, n_in);
     uint32_t *cnt = s_cnt + w * kCntStride;
     for (int base = wbeg; base < wend; base += 32) {
-        int i = base + lane;
-        bool act = i < wend;
-        KeyT key = act ? in_k[i] : (KeyT)0;
-        if (first) act = act && key != (KeyT)0;
-        uint32_t am = __ballot_sync(0xffffffffu, act);
-        if (act) {
-            uint32_t d = (uint32_t)(key >> shift) & 0xFFu;
-            uint32_t m = __match_any_sync(am, d);
-            if ((m & lanemask_lt()) == 0) cnt[d] += __popc(m);
-        }
+        const int i = base + lane;
+        const KeyT key = (i < wend) ? in_k[i] : (KeyT)0;
+        const bool act = (i < wend) && in_range(key, lo, hi);
+        const uint32_t d = (uint32_t)(key >> shift) & 0xFFu;
+        const uint32_t peers = digit_peers(d, act);
+        if (act && (peers & lanemask_lt()) == 0) cnt[d] += __popc(peers);
         __syncwarp();
     }
     __syncthreads();
+}
+
+// One stable radix pass.  Elements outside [lo,hi] are dropped (used by the first pass, where
+// the input is the raw key array and the payload is the position itself: `in_i == nullptr`).
+// Returns the number of elements written (block-uniform), or -1 when the pass was skipped
+// because every element shares the digit.
+template <typename KeyT, typename IdxT>
+__device__ int radix_pass(const KeyT *in_k, const IdxT *in_i, KeyT *out_k, IdxT *out_i, int n_in,
+                          int shift, KeyT lo, KeyT hi, bool may_skip, uint32_t *s_cnt, int *s_scan,
+                          int *s_flag) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) *s_flag = 0;
+    count_walk<KeyT>(in_k, n_in, shift, lo, hi, s_cnt);
+    const int chunk = ((n_in + kNmsWarps - 1) / kNmsWarps + 31) & ~31;
+    const int wbeg = min(w * chunk, n_in), wend = min(wbeg + chunk, n_in);
+    uint32_t *cnt = s_cnt + w * kCntStride;
+    int total;
     // scan in (digit major, warp minor) order; thread t owns digit t>>2, warps (t&3)*8..+7
     {
         const int d = threadIdx.x >> 2, wq = (threadIdx.x & 3) * 8;
@@ -171,9 +199,8 @@ __device__ int radix_pass(const KeyT *in_k, const IdxT *in_i, KeyT *out_k, IdxT 
         int dsum = sum;
         dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
         dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
-        int total;
         int ex = block_exscan(sum, s_scan, &total);
-        if (!first && dsum == total && total > 0 && (threadIdx.x & 3) == 0) *s_flag = 1;
+        if (may_skip && dsum == total && total > 0 && (threadIdx.x & 3) == 0) *s_flag = 1;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             s_cnt[(wq + j) * kCntStride + d] = (uint32_t)ex;
@@ -181,48 +208,100 @@ __device__ int radix_pass(const KeyT *in_k, const IdxT *in_i, KeyT *out_k, IdxT 
         }
         __syncthreads();
         if (*s_flag) return -1;
-        n_in = first ? total : n_in;
-        if (first && threadIdx.x == 0) s_scan[33] = total;
     }
     for (int base = wbeg; base < wend; base += 32) {
-        int i = base + lane;
-        bool act = i < wend;
-        KeyT key = act ? in_k[i] : (KeyT)0;
-        if (first) act = act && key != (KeyT)0;
-        uint32_t am = __ballot_sync(0xffffffffu, act);
-        uint32_t d = 0, m = 0, off = 0;
+        const int i = base + lane;
+        const KeyT key = (i < wend) ? in_k[i] : (KeyT)0;
+        const bool act = (i < wend) && in_range(key, lo, hi);
+        const uint32_t d = (uint32_t)(key >> shift) & 0xFFu;
+        const uint32_t peers = digit_peers(d, act);
+        uint32_t off = 0;
         if (act) {
-            IdxT idx = first ? (IdxT)i : in_i[i];
-            d = (uint32_t)(key >> shift) & 0xFFu;
-            m = __match_any_sync(am, d);
+            const IdxT idx = in_i ? in_i[i] : (IdxT)i;
             off = cnt[d];
-            uint32_t pos = off + __popc(m & lanemask_lt());
+            const uint32_t pos = off + __popc(peers & lanemask_lt());
             out_k[pos] = key;
             out_i[pos] = idx;
         }
         __syncwarp();
-        if (act && (m & lanemask_lt()) == 0) cnt[d] = off + __popc(m);
+        if (act && (peers & lanemask_lt()) == 0) cnt[d] = off + __popc(peers);
         __syncwarp();
     }
     __syncthreads();
-    return n_in;
+    return total;
 }
+
+// Warp 0: in a 256-bin histogram (bin totals = column sums of the per-warp counters) find the
+// highest bin `b` with  count(bins > b) < need <= count(bins >= b).  Writes {b, count(bins > b),
+// hist[b], grand total} to s_out.  All 1024 threads must call (two block barriers inside).
+__device__ void find_top_bin(const uint32_t *s_cnt, int need, uint32_t *s_hist, int *s_out) {
+    if (threadIdx.x < 256) {
+        uint32_t t = 0;
+        for (int w = 0; w < kNmsWarps; ++w) t += s_cnt[w * kCntStride + threadIdx.x];
+        s_hist[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        // lane l owns bins 255-8l .. 248-8l (descending), so lane order = descending key order
+        uint32_t loc[8];
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            loc[j] = s_hist[255 - 8 * lane - j];
+            sum += (int)loc[j];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += n;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        int above = inc - sum;                      // keys in bins owned by lower lanes (= larger keys)
+        const bool mine = above < need && need <= inc;
+        if (mine) {
+            int b = 255 - 8 * lane, cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (above + (int)loc[j] >= need) { b = 255 - 8 * lane - j; cnt = (int)loc[j]; break; }
+                above += (int)loc[j];
+            }
+            s_out[0] = b; s_out[1] = above; s_out[2] = cnt;
+        }
+        if (lane == 0) {
+            s_out[3] = total;
+            if (need > total) { s_out[0] = 0; s_out[1] = total; s_out[2] = 0; }   // everything is selected
+        }
+    }
+    __syncthreads();
+}
+
+template <typename KeyT> struct KeyMax;
+template <> struct KeyMax<uint32_t> { static constexpr uint32_t v = 0xFFFFFFFFu; };
+template <> struct KeyMax<uint64_t> { static constexpr uint64_t v = ~0ull; };
 
 template <typename Traits, typename KeyT, typename IdxT, bool kSmemSort, bool kKeptSmem>
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams p) {
     using Box = typename Traits::Box;
     using Area = typename Traits::Area;
     constexpr bool kI32 = sizeof(Box) == sizeof(int4);
+    constexpr int kBits = (int)sizeof(KeyT) * 8;
+    constexpr KeyT kMaxKey = KeyMax<KeyT>::v;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);                 // 8 B
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);                 // TMA barrier
     int *s_misc = reinterpret_cast<int *>(smem + 16);                     // 16 ints
     int *s_scan = reinterpret_cast<int *>(smem + 96);                     // 34 ints
+    uint64_t *s_turn = reinterpret_cast<uint64_t *>(smem + 256);          // [32] hand-off barriers
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + 512);          // [256]
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + p.sm_off_cnt);  // [32][257]
     volatile int *s_kcount = s_misc + 0;
-    volatile int *s_wdone = s_misc + 1;
     int *s_flag = s_misc + 2;
     int *s_ties = s_misc + 3;
+    int *s_sel = s_misc + 4;                                              // 4 ints
+    volatile int *s_fault = s_misc + 8;
+    volatile int *s_kafter = reinterpret_cast<volatile int *>(smem + 1536);         // [32] kept count after row w
 
     const int seg = blockIdx.x;
     const int N = p.N;
@@ -248,38 +327,29 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
 
     if (threadIdx.x == 0) {
         *s_kcount = 0;
-        *s_wdone = 0;
         *s_ties = 0;
+        *s_fault = 0;
+        mbar_init(s_bar, 1);
+        for (int i = 0; i < kNmsWarps; ++i) mbar_init(&s_turn[i], 1);
+        mbar_fence_init();
     }
+    __syncthreads();
 
-    // ---- stage keys (TMA bulk copy into shared memory on the hot path) -------------
-    const KeyT *in_k;
-    const IdxT *in_i = nullptr;
-    KeyT *out_k;
-    IdxT *out_i;
+    // ---- stage the raw keys (one TMA bulk copy into shared memory on the hot path) -----
+    const KeyT *raw_k = g_keys;
     if (kSmemSort) {
-        size_t bytes = (size_t)N * sizeof(KeyT);
-        uint32_t bulk = ((reinterpret_cast<uintptr_t>(g_keys) & 15) == 0) ? (uint32_t)(bytes & ~(size_t)15) : 0u;
-        if (threadIdx.x == 0) {
-            mbar_init(s_bar, 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
+        const size_t bytes = (size_t)N * sizeof(KeyT);
+        const uint32_t bulk = ((reinterpret_cast<uintptr_t>(g_keys) & 15) == 0) ? (uint32_t)(bytes & ~(size_t)15) : 0u;
         if (threadIdx.x == 0 && bulk) {
             mbar_expect_tx(s_bar, bulk);
             tma_bulk_g2s(kA, g_keys, bulk, s_bar);
         }
         // tail (and the whole array when the source is not 16-byte aligned)
         for (int i = (int)(bulk / sizeof(KeyT)) + threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
-        if (bulk) mbar_wait(s_bar, 0);
-        __syncthreads();
-        in_k = kA; out_k = kB; out_i = iB;
-    } else {
-        __syncthreads();
-        in_k = g_keys; out_k = kA; out_i = iA;
+        raw_k = kA;
     }
 
-    // ---- build the suppression table while the keys land (i32 path) ----------------
+    // ---- suppression table, built while the keys land (i32 path) ------------------------
     uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem + p.sm_off_table);
     if (kI32) {
         const double thr = p.thr;
@@ -294,159 +364,193 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             s_tab[u] = ok ? (uint16_t)c : (uint16_t)0xFFFF;
         }
     }
-
-    // ---- stage 1: radix sort --------------------------------------------------------
-    int M = 0;
-    {
-        int n_in = N;
-        bool first = true;
-#pragma unroll 1
-        for (int pass = 0; pass < KeyBits<KeyT>::passes; ++pass) {
-            int r = radix_pass<KeyT, IdxT>(in_k, in_i, out_k, out_i, n_in, pass * 8, first, s_cnt, s_scan, s_flag);
-            if (r >= 0) {
-                n_in = r;
-                const KeyT *nk = out_k;
-                const IdxT *ni = out_i;
-                // next output buffer is "the other one"
-                if (out_k == kA) { out_k = kB; out_i = iB; } else { out_k = kA; out_i = iA; }
-                in_k = nk; in_i = ni;
-            }
-            first = false;
-            if (n_in == 0) break;
-        }
-        M = n_in;
+    if (kSmemSort) {
+        const size_t bytes = (size_t)N * sizeof(KeyT);
+        const bool bulk = ((reinterpret_cast<uintptr_t>(g_keys) & 15) == 0) && (bytes & ~(size_t)15) != 0;
+        if (bulk) mbar_wait(s_bar, 0);
     }
-    // in_k / in_i now hold M entries ascending by (score, flat index)
+    __syncthreads();
 
-    // ---- score ties among the candidates (reported) -----------------
-    {
-        int t = 0;
-        for (int i = threadIdx.x; i < M; i += kNmsThreads) {
-            KeyT k = in_k[i];
-            bool tie = (i > 0 && in_k[i - 1] == k) || (i + 1 < M && in_k[i + 1] == k);
-            t += tie ? 1 : 0;
-        }
-        t = __reduce_add_sync(0xffffffffu, t);
-        if (lane == 0 && t) atomicAdd(s_ties, t);
-    }
-
-    // ---- stage 2: greedy suppression ------------------------------------------------
-    const int K = min(p.max_boxes, M);
+    // kept list
     Box *kbox;
     Area *karea;
     int *kidx;
-    if (kKeptSmem) {
-        unsigned char *kb = smem + p.sm_off_kept;
-        kbox = reinterpret_cast<Box *>(kb);
-        karea = reinterpret_cast<Area *>(kbox + kKeptSmemMax);
-        kidx = reinterpret_cast<int *>(karea + kKeptSmemMax);
-    } else {
-        unsigned char *kb = ws + p.ws_off_kept;
-        int cap = min(p.max_boxes, N);
+    {
+        const int cap = min(p.max_boxes, N);
+        unsigned char *kb = kKeptSmem ? (smem + p.sm_off_kept) : (ws + p.ws_off_kept);
         kbox = reinterpret_cast<Box *>(kb);
         karea = reinterpret_cast<Area *>(kbox + cap);
         kidx = reinterpret_cast<int *>(karea + cap);
     }
-    Box *s_tile = reinterpret_cast<Box *>(s_cnt);   // counters are dead; [kTile] boxes fit
+    Box *s_tile = reinterpret_cast<Box *>(s_cnt);   // counters are dead during the NMS; [kTile] boxes fit
     typename Traits::Ctx ctx;
     if constexpr (kI32) ctx.tab = s_tab; else ctx.thr = p.thr;
-    __syncthreads();
 
+    // ---- round 0: only the top-scoring slice is sorted; round 1 (rare): everything -------
+    // The greedy loop stops at max_boxes keeps, which normally happens within the first few
+    // hundred candidates, so a two-level radix SELECT (histograms of the two top key bytes)
+    // finds a threshold with about `sel_target` keys above it and only those are sorted.
+    int M = 0;            // valid candidates
+    int S = 0;            // candidates sorted so far (ranks [0,S) are final)
+    int done = 0;         // ranks already visited by the NMS
     int k0 = 0;
+    int K = 0;
+    int tile_no = 0;
 #pragma unroll 1
-    for (int base = 0; base < M && k0 < K; base += kTile) {
-        const int r = base + threadIdx.x;
-        const bool active = r < M;
-        Box box;
-        Area ar = 0;
-        int flat = 0;
-        if (active) {
-            flat = (int)in_i[M - 1 - r];
-            box = Traits::load(g_boxes, (size_t)flat);
-            ar = Traits::area(box);
+    for (int round = 0; round < 2; ++round) {
+        KeyT thr_key = (KeyT)1;
+        if (round == 0) {
+            // level 1: top byte over all valid keys
+            count_walk<KeyT>(raw_k, N, kBits - 8, (KeyT)1, kMaxKey, s_cnt);
+            find_top_bin(s_cnt, p.sel_target, s_hist, s_sel);
+            M = s_sel[3];
+            K = min(p.max_boxes, M);
+            if (M > p.sel_target) {
+                const int b1 = s_sel[0], above1 = s_sel[1];
+                const KeyT lo1 = (KeyT)b1 << (kBits - 8);
+                const KeyT hi1 = lo1 | (((KeyT)1 << (kBits - 8)) - 1);
+                __syncthreads();
+                // level 2: second byte inside the boundary bin
+                count_walk<KeyT>(raw_k, N, kBits - 16, lo1, hi1, s_cnt);
+                find_top_bin(s_cnt, p.sel_target - above1, s_hist, s_sel);
+                thr_key = lo1 | ((KeyT)s_sel[0] << (kBits - 16));
+                if (thr_key == 0) thr_key = 1;
+            }
+            __syncthreads();
         } else {
-            if constexpr (kI32) box = make_int4(0, 0, 0, 0); else box = make_double4(0, 0, 0, 0);
-        }
-        s_tile[threadIdx.x] = box;
-        __syncwarp();
-
-        // (a) against boxes kept by earlier tiles
-        bool alive = active;
-        for (int j = 0; j < k0; ++j) {
-            Box kb = kbox[j];
-            Area ka = karea[j];
-            if (Traits::suppress(kb, ka, box, ar, ctx)) alive = false;
-        }
-        // (b) intra-row matrix: which lower lanes of my row overlap me
-        uint32_t row_alive = __ballot_sync(0xffffffffu, alive);
-        uint32_t lower = 0;
-        {
-            uint32_t todo = row_alive;
-            while (todo) {
-                int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                Box ob = s_tile[(w << 5) + j];
-                Area oa = Traits::area(ob);
-                if (j < lane && Traits::suppress(ob, oa, box, ar, ctx)) lower |= 1u << j;
+            if (kSmemSort) {      // the ping-pong buffers overwrote the staged keys: fetch them again
+                for (int i = threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
+                __syncthreads();
             }
         }
-        // (c) systolic hand-off: wait for my turn, testing new keeps as they appear
-        int seen = k0;
-        int kc = k0;
-        unsigned spins = 0;
-        while (true) {
-            if (++spins > (1u << 24)) { *s_flag = 2; break; }   // watchdog: never hang the device
-            int wd = *s_wdone;
-            __threadfence_block();
-            kc = *s_kcount;
-            for (int j = seen; j < kc; ++j) {
+
+        // ---- stable LSD radix sort of the keys >= thr_key --------------------------------
+        const KeyT *in_k = raw_k;
+        const IdxT *in_i = nullptr;
+        KeyT *out_k = kSmemSort ? kB : kA;
+        IdxT *out_i = kSmemSort ? iB : iA;
+        int n_in = N;
+#pragma unroll 1
+        for (int pass = 0; pass < KeyBits<KeyT>::passes; ++pass) {
+            const bool first = pass == 0;
+            int r = radix_pass<KeyT, IdxT>(in_k, in_i, out_k, out_i, n_in, pass * 8, first ? thr_key : (KeyT)0,
+                                           kMaxKey, !first, s_cnt, s_scan, s_flag);
+            if (r >= 0) {
+                n_in = r;
+                in_k = out_k;
+                in_i = out_i;
+                if (out_k == kA) { out_k = kB; out_i = iB; } else { out_k = kA; out_i = iA; }
+            }
+            if (n_in == 0) break;
+        }
+        S = n_in;         // in_k / in_i: S entries ascending by (score, flat index)
+        if (round == 1) M = S;
+
+        // ---- score ties among the sorted candidates (reported) -----------
+        {
+            if (threadIdx.x == 0) *s_ties = 0;
+            __syncthreads();
+            int t = 0;
+            for (int i = threadIdx.x; i < S; i += kNmsThreads) {
+                KeyT k = in_k[i];
+                bool tie = (i > 0 && in_k[i - 1] == k) || (i + 1 < S && in_k[i + 1] == k);
+                t += tie ? 1 : 0;
+            }
+            t = __reduce_add_sync(0xffffffffu, t);
+            if (lane == 0 && t) atomicAdd(s_ties, t);
+        }
+        __syncthreads();
+
+        // ---- greedy suppression over ranks [done, S) -------------------------------------
+#pragma unroll 1
+        for (int base = done; base < S && k0 < K; base += kTile, ++tile_no) {
+            const uint32_t parity = tile_no & 1;
+            const int r = base + threadIdx.x;
+            const bool active = r < S;
+            Box box;
+            Area ar = 0;
+            int flat = 0;
+            if (active) {
+                flat = (int)in_i[S - 1 - r];
+                box = Traits::load(g_boxes, (size_t)flat);
+                ar = Traits::area(box);
+            } else {
+                if constexpr (kI32) box = make_int4(0, 0, 0, 0); else box = make_double4(0, 0, 0, 0);
+            }
+            s_tile[threadIdx.x] = box;
+            __syncwarp();
+
+            // (a) against boxes kept by earlier tiles
+            bool alive = active;
+            for (int j = 0; j < k0; ++j) {
                 Box kb = kbox[j];
                 Area ka = karea[j];
                 if (Traits::suppress(kb, ka, box, ar, ctx)) alive = false;
             }
-            seen = kc;
-            if (kc >= K || wd == w) break;
-        }
-        if (kc < K) {
-            uint32_t und = __ballot_sync(0xffffffffu, alive);
-            uint32_t kept = 0;
-            const bool me0 = alive;
-            while (und) {
-                bool me = me0 && ((und >> lane) & 1u);
-                uint32_t know = __ballot_sync(0xffffffffu, me && !(lower & kept) && !(lower & und));
-                kept |= know;
-                uint32_t dnow = __ballot_sync(0xffffffffu, me && (lower & kept));
-                und &= ~(know | dnow);
+            // (b) intra-row matrix: which lower lanes of my row overlap me
+            uint32_t lower = 0;
+            {
+                uint32_t todo = __ballot_sync(0xffffffffu, alive);
+                while (todo) {
+                    int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    Box ob = s_tile[(w << 5) + j];
+                    Area oa = Traits::area(ob);
+                    if (j < lane && Traits::suppress(ob, oa, box, ar, ctx)) lower |= 1u << j;
+                }
             }
-            int room = K - kc;
-            int nk = __popc(kept);
-            if (nk > room) {                       // keep only the first `room` of this row
-                kept &= (1u << __fns(kept, 0, room + 1)) - 1u;
-                nk = room;
+            // (c) systolic hand-off: rows retire in rank order.  A warp sleeps on the mbarrier of
+            //     each earlier row in turn (hardware wait, no issue slots burnt) and tests its
+            //     candidates against the boxes kept since it last looked.
+            int seen = k0;
+            int kc = k0;
+            for (int pw = 0; pw < w && kc < K; ++pw) {
+                if (!mbar_wait_bounded(&s_turn[pw], parity)) { *s_fault = 1; break; }
+                kc = s_kafter[pw];            // published by exactly the row just acquired
+                for (int j = seen; j < kc; ++j) {
+                    Box kb = kbox[j];
+                    Area ka = karea[j];
+                    if (Traits::suppress(kb, ka, box, ar, ctx)) alive = false;
+                }
+                seen = kc;
             }
-            if ((kept >> lane) & 1u) {
-                int pos = kc + __popc(kept & lanemask_lt());
-                kbox[pos] = box;
-                karea[pos] = ar;
-                kidx[pos] = flat;
+            if (kc < K) {
+                uint32_t und = __ballot_sync(0xffffffffu, alive);
+                uint32_t kept = 0;
+                const bool me0 = alive;
+                while (und) {
+                    bool me = me0 && ((und >> lane) & 1u);
+                    uint32_t know = __ballot_sync(0xffffffffu, me && !(lower & kept) && !(lower & und));
+                    kept |= know;
+                    uint32_t dnow = __ballot_sync(0xffffffffu, me && (lower & kept));
+                    und &= ~(know | dnow);
+                }
+                int room = K - kc;
+                int nk = __popc(kept);
+                if (nk > room) {                       // keep only the first `room` of this row
+                    kept &= (1u << __fns(kept, 0, room + 1)) - 1u;
+                    nk = room;
+                }
+                if ((kept >> lane) & 1u) {
+                    int pos = kc + __popc(kept & lanemask_lt());
+                    kbox[pos] = box;
+                    karea[pos] = ar;
+                    kidx[pos] = flat;
+                }
+                kc += nk;
             }
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
-                *s_kcount = kc + nk;
-                __threadfence_block();
-                *s_wdone = w + 1;
+                s_kafter[w] = kc;
+                if (kc > *s_kcount) *s_kcount = kc;       // rows retire in order, so this only grows
+                mbar_arrive(&s_turn[w]);                  // release: keeps + counts visible to waiters
             }
-        } else if (lane == 0) {
-            // list is full: just pass the baton so later warps can leave too
-            __threadfence_block();
-            if (*s_wdone == w) *s_wdone = w + 1;
+            __syncthreads();
+            k0 = *s_kcount;
+            __syncthreads();
         }
-        __syncthreads();
-        k0 = *s_kcount;
-        __syncthreads();
-        if (threadIdx.x == 0) *s_wdone = 0;
-        __syncthreads();
+        done = S;
+        if (k0 >= K || S >= M) break;
     }
     const int kept_n = *s_kcount;
 
@@ -458,10 +562,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         float *rs = reinterpret_cast<float *>(rec + 16 + (size_t)p.det_max_boxes * 16);
         int32_t *ri = reinterpret_cast<int32_t *>(rec + 16 + (size_t)p.det_max_boxes * 20);
         if (threadIdx.x == 0) {
-            hdr[0] = kept_n;
+            hdr[0] = *s_fault ? -1 : kept_n;        // -1: hand-off wait timed out (kernel bug), results invalid
             hdr[1] = M;
             hdr[2] = *s_ties;
-            hdr[3] = (*s_flag == 2) ? 1 : 0;   // hand-off watchdog fired: results invalid
+            hdr[3] = S;
         }
         for (int j = threadIdx.x; j < p.det_max_boxes; j += kNmsThreads) {
             if (j < kept_n) {
@@ -477,8 +581,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         }
     } else {
         if (threadIdx.x == 0) {
-            p.count[0] = (*s_flag == 2) ? -1 : kept_n;
+            p.count[0] = *s_fault ? -1 : kept_n;
             p.count[1] = *s_ties;
+            p.count[2] = S;
         }
         for (int j = threadIdx.x; j < kept_n; j += kNmsThreads) p.pick[j] = kidx[j];
     }
@@ -510,7 +615,7 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     NmsPlan pl{};
     SortNmsParams &p = pl.p;
     const int K = max_boxes < N ? max_boxes : N;
-    size_t off = 256;                                   // barrier + misc + scan scratch
+    size_t off = 2048;                                  // barriers, misc, scan scratch, 256-bin histogram, row counts
     p.sm_off_cnt = (int)off;
     size_t cnt_bytes = (size_t)kNmsWarps * kCntStride * 4;
     size_t tile_bytes = (size_t)kTile * sizeof(Box);
@@ -519,7 +624,9 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     off += align_up((size_t)table_entries * 2, 128);
     pl.kept_smem = K <= kKeptSmemMax;
     p.sm_off_kept = (int)off;
-    if (pl.kept_smem) off += align_up((size_t)kKeptSmemMax * (sizeof(Box) + sizeof(Area) + 4), 128);
+    if (pl.kept_smem) off += align_up((size_t)K * (sizeof(Box) + sizeof(Area) + 4) + 64, 128);
+    // first sort round: about this many top-scoring candidates (see the kernel)
+    p.sel_target = (4 * K > 2048) ? 4 * K : 2048;
     // shared-memory sort: keys ping-pong + uint16 index ping-pong
     size_t cap = align_up((size_t)N, 64);
     size_t sort_bytes = 2 * cap * sizeof(KeyT) + 2 * cap * sizeof(uint16_t);

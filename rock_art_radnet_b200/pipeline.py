@@ -49,7 +49,7 @@ class DetectionRecords:
         self.raw = raw if raw is not None else torch.zeros((batch, self.stride), dtype=torch.uint8, device=device)
         words = self.raw.view(torch.int32)
         k = max_boxes
-        self.header = words[:, 0:4]                                   # count, n_candidates, ties, 0
+        self.header = words[:, 0:4]                                   # count, n_candidates, ties, n_sorted
         self.boxes = words[:, 4:4 + 4 * k].view(batch, k, 4)          # x1,y1,x2,y2
         self.scores = words[:, 4 + 4 * k:4 + 5 * k].view(torch.float32)
         self.index = words[:, 4 + 5 * k:4 + 6 * k]
@@ -61,8 +61,8 @@ class DetectionRecords:
     def to_numpy(self):
         """-> list of dicts with int64 boxes (k,4), float32 scores, int64 flat indices."""
         hdr = self.header.cpu().numpy()
-        if (hdr[:, 3] != 0).any():
-            raise RuntimeError("radnet_sort_nms_i32: hand-off watchdog fired (kernel bug); results invalid")
+        if (hdr[:, 0] < 0).any():
+            raise RuntimeError("radnet_sort_nms_i32: hand-off wait timed out (kernel bug); results invalid")
         boxes = self.boxes.cpu().numpy()
         scores = self.scores.cpu().numpy()
         index = self.index.cpu().numpy()
@@ -71,7 +71,7 @@ class DetectionRecords:
             n = int(hdr[b, 0])
             out.append({"boxes": boxes[b, :n].astype(np.int64), "scores": scores[b, :n].copy(),
                         "index": index[b, :n].astype(np.int64), "n_candidates": int(hdr[b, 1]),
-                        "score_ties": int(hdr[b, 2])})
+                        "score_ties": int(hdr[b, 2]), "n_sorted": int(hdr[b, 3])})
         return out
 
 
@@ -147,3 +147,59 @@ class ProposalPipeline:
         if (st[:, 0] == 0).any():
             raise ValueError("not enough values to unpack (expected 2, got 0)")
         return st
+
+
+class HostPanelStream:
+    """Public end-to-end entry for HOST buffers: batches of panels whose RPN maps and feature
+    maps live in (pinned) host memory go host -> device -> decode -> sort+NMS -> RoI pool, and
+    the detection records come back to the host.  Pooled features stay on the device, where
+    the classifier head consumes them (in the reference they never leave the TF graph either,
+    RoiPoolingConv.py:75-86).
+
+    Two device input slots and a dedicated copy stream overlap the upload of batch k+1 with
+    the kernels of batch k; `submit` returns immediately, `collect` blocks for one batch.
+    """
+
+    def __init__(self, pipe, slots=2):
+        self.pipe = pipe
+        dev = pipe.device
+        B, H, W, A, Cn = pipe.batch, pipe.H, pipe.W, pipe.A, pipe.channels
+        self.slots = slots
+        self.cls = [D.empty((B, H, W, A), np.float32, dev) for _ in range(slots)]
+        self.regr = [D.empty((B, H, W, 4 * A), np.float32, dev) for _ in range(slots)]
+        self.feat = [D.empty((B, H, W, Cn), np.float32, dev) for _ in range(slots)]
+        self.rec_host = [torch.empty((B, pipe.records.stride), dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.compute_stream = torch.cuda.Stream(device=dev)
+        self.uploaded = [torch.cuda.Event() for _ in range(slots)]
+        self.consumed = [torch.cuda.Event() for _ in range(slots)]
+        self.done = [torch.cuda.Event() for _ in range(slots)]
+        self._n = 0
+        self._pending = []
+        self.h2d_bytes_per_batch = 4 * (B * H * W * A * 5 + B * H * W * Cn)
+        self.d2h_bytes_per_batch = B * pipe.records.stride
+
+    def submit(self, cls_h, regr_h, feat_h):
+        """cls_h/regr_h/feat_h: float32 CPU tensors (pinned for asynchronous copies)."""
+        s = self._n % self.slots
+        if self._n >= self.slots:
+            self.copy_stream.wait_event(self.consumed[s])      # slot inputs no longer being read
+        with torch.cuda.stream(self.copy_stream):
+            self.cls[s].copy_(cls_h, non_blocking=True)
+            self.regr[s].copy_(regr_h, non_blocking=True)
+            self.feat[s].copy_(feat_h, non_blocking=True)
+            self.uploaded[s].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(self.uploaded[s])
+            rec, _ = self.pipe(self.cls[s], self.regr[s], self.feat[s])
+            self.consumed[s].record(self.compute_stream)
+            self.rec_host[s].copy_(rec.raw, non_blocking=True)
+            self.done[s].record(self.compute_stream)
+        self._pending.append(s)
+        self._n += 1
+
+    def collect(self):
+        """Wait for the oldest submitted batch; returns its records as a host uint8 tensor."""
+        s = self._pending.pop(0)
+        self.done[s].synchronize()
+        return self.rec_host[s]

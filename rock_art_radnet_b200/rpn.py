@@ -87,7 +87,7 @@ def _nms_device(boxes_dev, probs_dev, valid_dev, overlap_thresh, max_boxes):
     ws_bytes = int(lib.radnet_nms_f64_workspace_bytes(M, mb))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     pick = D.empty((min(mb, M),), np.int32, dev)
-    count = D.zeros((2,), np.int32, dev)
+    count = D.zeros((3,), np.int32, dev)
     _lib.call("radnet_nms_f64", D.ptr(boxes_dev), D.ptr(probs_dev), D.ptr(valid_dev), M,
               float(overlap_thresh), mb, D.ptr(pick), D.ptr(count), D.ptr(ws), ws_bytes, D.stream_ptr(dev))
     cnt = count.cpu().numpy()

@@ -1,0 +1,69 @@
+"""Per-image sharding across the GPUs of one box and the single collective of the path.
+
+The reference is single-process, batch 1 (rpn.py:96); every hot-path function is
+per image, so panels (or tiles of one panel, RADNet.py:543-604) shard with no data
+exchange: panel i is processed by rank i % world.  The only collective is a gather
+of the fixed-size detection records written by K2; pooled features
+stay on the GPU that produced them (they feed that GPU's classifier head).
+
+One process per GPU (`torchrun`), `torch.distributed` with the NCCL backend over
+NVLink/NVSwitch; the same code runs on the gloo backend with CPU tensors, which is
+how the CPU test-suite covers the world_size > 1 path.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_panels, rank, world):
+    """Global panel ids owned by `rank`: i % world == rank (interleaved, balanced to +-1)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world %d" % (rank, world))
+    return np.arange(rank, n_panels, world, dtype=np.int64)
+
+
+def shard_sizes(n_panels, world):
+    return [len(range(r, n_panels, world)) for r in range(world)]
+
+
+def global_order(n_panels, world, per_rank):
+    """Index array that maps the rank-major gathered layout [world][per_rank] back to global
+    panel order; padded slots (rank has fewer than per_rank panels) are dropped."""
+    order = np.full((n_panels,), -1, dtype=np.int64)
+    for r in range(world):
+        ids = shard_indices(n_panels, r, world)
+        if len(ids) > per_rank:
+            raise ValueError("per_rank=%d too small for %d panels on rank %d" % (per_rank, len(ids), r))
+        order[ids] = r * per_rank + np.arange(len(ids))
+    assert (order >= 0).all()
+    return order
+
+
+def gather_detections(raw, group=None, async_op=False, out=None):
+    """All-gather the per-panel detection records of every rank.
+
+    raw: (B, stride) uint8 tensor on this rank (DetectionRecords.raw).  Returns
+    (gathered (world, B, stride) uint8, work-or-None).  With NCCL this is one
+    ncclAllGather of B*stride bytes per rank over NVLink; it is latency-bound (tens of
+    microseconds for 64 panels), so callers issue it once per batch, asynchronously, and
+    overlap it with the RoI-pool kernel of the same batch."""
+    if not dist.is_initialized():
+        g = raw.unsqueeze(0) if out is None else out.copy_(raw.unsqueeze(0))
+        return g, None
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world,) + tuple(raw.shape), dtype=raw.dtype, device=raw.device)
+    work = dist.all_gather_into_tensor(out.view(-1), raw.contiguous().view(-1), group=group, async_op=async_op)
+    return out, work
+
+
+def split_gathered(gathered, n_panels, max_boxes):
+    """(world, per_rank, stride) uint8 -> list over GLOBAL panel ids of dicts
+    {boxes int64 (k,4), scores float32 (k,), index int64 (k,)}."""
+    from .pipeline import DetectionRecords
+    world, per_rank = int(gathered.shape[0]), int(gathered.shape[1])
+    flat = gathered.reshape(world * per_rank, -1).contiguous()
+    rec = DetectionRecords(world * per_rank, max_boxes, flat.device, raw=flat)
+    dets = rec.to_numpy()
+    order = global_order(n_panels, world, per_rank)
+    return [dets[int(j)] for j in order]

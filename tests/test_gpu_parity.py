@@ -68,6 +68,7 @@ def test_decode_boxes_and_kept_indices_bit_exact(pkg):
         assert np.array_equal(dets[b]["boxes"], dbg["boxes"])
         assert np.array_equal(dets[b]["scores"], dbg["probs"])
         assert dets[b]["n_candidates"] == keep.sum() and dets[b]["score_ties"] == 0
+        assert 2048 <= dets[b]["n_sorted"] <= 2048 + 256      # radix select: only the top slice is sorted
 
 
 @pytest.mark.parametrize("H,W,scales,thr,mb", [
@@ -75,6 +76,8 @@ def test_decode_boxes_and_kept_indices_bit_exact(pkg):
     (38, 38, (64, 128, 256, 512), 0.7, 300),  # reference default 12 anchors -> global-memory sort path
     (100, 100, (128, 256, 512), 0.7, 300),    # un-tiled 1600-px stress: 90,000 candidates in one segment
     (38, 38, (128, 256, 512), 0.3, 2000),     # kept list larger than the shared-memory list
+    (38, 38, (128, 256, 512), 0.05, 300),     # heavy suppression: top slice exhausted -> full-sort round
+    (38, 50, (64, 128, 256, 512), 0.1, 300),  # same on the global-memory sort path
     (7, 5, (128, 256, 512), 0.9, 300),
     (1, 1, (128,), 0.7, 300),
 ])
@@ -102,7 +105,10 @@ def test_rpn_to_roi_score_ties_follow_documented_rule(pkg):
     pipe = _single_panel_pipeline(C, 38, 38, 300, 0.7)
     flat = cls.transpose((0, 3, 1, 2)).reshape(-1)
     dbg = O.decode_proposals(cls, regr, C)
-    assert pipe.records.to_numpy()[0]["score_ties"] == O.count_score_ties(flat[dbg[2]])
+    det = pipe.records.to_numpy()[0]
+    # ties are counted among the n_sorted top-scoring candidates the kernel had to sort
+    top = np.sort(flat[dbg[2]])[::-1][:det["n_sorted"]]
+    assert det["n_sorted"] >= 2048 and det["score_ties"] == O.count_score_ties(top)
 
 
 def test_rpn_to_roi_errors(pkg):
@@ -309,7 +315,11 @@ def test_pipeline_batch_end_to_end(pkg):
     B, H, W, Cn = 3, 38, 38, 1024
     maps = [S.rpn_maps(200 + s) for s in range(B)]
     feats = [S.feature_map(200 + s) for s in range(B)]
-    maps[2] = (maps[2][0], (maps[2][1] * 0).astype(np.float32))     # panel with < 300 survivors
+    # panel with < 300 candidates: push every anchor outside row 0 / cols < 20 off the map (degenerate)
+    far = maps[2][1].copy()
+    far[0, 1:, :, 0::4] = 4000.0
+    far[0, 0, 20:, 0::4] = 4000.0
+    maps[2] = (maps[2][0], far)
     pipe = ProposalPipeline(C, B, H, W, channels=Cn, pool_size=14, max_boxes=300, overlap_thresh=0.7)
     rec, pooled = pipe(torch.from_numpy(np.concatenate([m[0] for m in maps])).cuda(),
                        torch.from_numpy(np.concatenate([m[1] for m in maps])).cuda(),

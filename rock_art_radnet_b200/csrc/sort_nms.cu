@@ -2,26 +2,35 @@
 //
 // Replaces non_max_suppression_fast (reference faster_rcnn/rpn.py:380-456).
 //
-// Stage 1  stable LSD radix sort of the candidate keys (8-bit digits).  Each warp owns a
-//          contiguous slice of the array; the rank of an element inside a 32-wide row
-//          comes from __match_any_sync + popc (no atomics), per-warp digit counters live
-//          in shared memory.  Stable + ascending => reading from the end visits equal
-//          scores "higher flat index first", the documented tie rule.  On the hot path
-//          (N*12 B fits) keys are staged into shared memory with one TMA bulk copy
-//          (cp.async.bulk + mbarrier) and all passes run out of shared memory.
-// Stage 2  greedy suppression over tiles of 1024 sorted candidates, one candidate per
-//          thread.  (a) every candidate is tested against the boxes kept by earlier tiles;
-//          (b) each warp builds the 32x32 "lower lane overlaps me" bit matrix of its row
-//          from a shared-memory box tile; (c) warps retire in rank order (a systolic
-//          hand-off through two shared words): a warp tests its row against the boxes
-//          kept since it last looked, resolves its own row with a ballot fixed point and
-//          appends its keeps.  The loop stops as soon as max_boxes are kept
-//          (rpn.py:449-450), so only the top few hundred candidates are ever touched.
+// The reference sorts every candidate and then runs up to max_boxes greedy iterations
+// (rpn.py:415-450).  The greedy loop stops at max_boxes keeps, which normally happens within
+// the first few hundred candidates, so this kernel only orders what it needs:
+//
+// Stage 0  keys (order-preserving uint images of the scores, 0 = deleted) are staged into
+//          shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) on the hot path.
+// Stage 1  SELECT: a block-wide bisection on the key value (one count-compare pass per step,
+//          ~12 steps) finds a threshold with about `sel_target` (>= 2048) keys at or above it;
+//          those keys are compacted in flat-index order.
+// Stage 2  SORT: stable LSD radix sort (8-bit digits) of the selected slice only.  Each warp
+//          owns a contiguous run; the rank of an element inside a 32-wide row comes from warp
+//          ballots (no atomics), per-warp digit counters live in shared memory.  Stable +
+//          ascending => reading from the end visits equal scores "higher flat index first",
+//          the documented tie rule.
+// Stage 3  NMS over tiles of 1024 sorted candidates, one candidate per thread.  (a) test
+//          against the boxes kept by earlier tiles; (b) each warp builds the 32x32 "lower lane
+//          overlaps me" bit matrix of its row from a shared-memory tile; (c) rows retire in
+//          rank order: a warp sleeps on the mbarrier of each earlier row in turn, tests its
+//          candidates against the boxes kept since it last looked, resolves its own row with
+//          a ballot fixed point and appends its keeps.
+// If the selected slice is exhausted before max_boxes boxes are kept (rare), a second round
+// sorts everything and the NMS continues at the first unvisited rank.
 //
 // Exactness: the i32 path evaluates `inter/(union+1e-6) > thr` (rpn.py:443-447) through a
-// per-union table of the smallest suppressing intersection, built at kernel start with
-// the float64 division itself; the f64 path performs the float64 arithmetic directly in
-// the reference's association order.  Both are bit-exact decisions.
+// per-union table of the smallest suppressing intersection, built at kernel start with the
+// float64 division itself (boxes are integers, so inter and union are exact); coordinates
+// are packed 2 x int16 and compared with VIMNMX.S16x2 / VIADDMNMX.S16x2.RELU.  The f64 path
+// performs the float64 arithmetic in the reference's association order.  Both decide
+// bit-exactly like NumPy.
 #include "common.cuh"
 
 namespace radnet {
@@ -32,60 +41,81 @@ constexpr int kCntStride = 257;                 // padded digit row: conflict-fr
 constexpr int kTile = kNmsThreads;              // candidates per NMS tile
 constexpr int kMaxTableEntries = 65535;
 constexpr int kKeptSmemMax = 1024;              // kept boxes held in shared memory
+constexpr int kSmemHeader = 2048;               // barriers, misc words, scan scratch, row counts
 
 // ----------------------------------------------------------------------------------
-// box traits
+// candidate representations
 // ----------------------------------------------------------------------------------
 struct BoxI32 {
-    using Box = int4;          // x1,y1,x2,y2
-    using Area = int;
+    // packed candidate: x = (-y1 << 16) | (-x1 & 0xffff), y = (y2 << 16) | x2, z = area, w = flat index
+    using Cand = int4;
+    static constexpr size_t kBoxBytes = sizeof(int4);
     struct Ctx { const uint16_t *tab; };
-    static __device__ __forceinline__ Box load(const void *boxes, size_t i) {
-        return __ldg(reinterpret_cast<const int4 *>(boxes) + i);
+    static __device__ __forceinline__ Cand empty() { return make_int4(0, 0, 0, 0); }
+    static __device__ __forceinline__ Cand load(const void *boxes, size_t i, int flat) {
+        const int4 b = __ldg(reinterpret_cast<const int4 *>(boxes) + i);     // x1,y1,x2,y2
+        Cand c;
+        c.x = (int)((((unsigned)(-b.y)) << 16) | (((unsigned)(-b.x)) & 0xFFFFu));
+        c.y = (int)((((unsigned)b.w) << 16) | (((unsigned)b.z) & 0xFFFFu));
+        c.z = (b.z - b.x) * (b.w - b.y);                                     // area, no +1 (rpn.py:412)
+        c.w = flat;
+        return c;
     }
-    static __device__ __forceinline__ Area area(const Box &b) { return (b.z - b.x) * (b.w - b.y); }
-    // true when a kept box `k` suppresses candidate `c`
-    static __device__ __forceinline__ bool suppress(const Box &k, Area ka, const Box &c, Area ca,
-                                                    const Ctx &ctx) {
-        int iw = max(min(k.z, c.z) - max(k.x, c.x), 0);
-        int ih = max(min(k.w, c.w) - max(k.y, c.y), 0);
-        int inter = iw * ih;
-        int uni = ka + ca - inter;
+    static __device__ __forceinline__ int flat(const Cand &c) { return c.w; }
+    static __device__ __forceinline__ int4 unpack(const Cand &c) {
+        const int nx1 = (int)(short)(c.x & 0xFFFF), ny1 = c.x >> 16;
+        return make_int4(-nx1, -ny1, (int)(short)(c.y & 0xFFFF), c.y >> 16);
+    }
+    // true when kept box `k` suppresses candidate `c`
+    static __device__ __forceinline__ bool suppress(const Cand &k, const Cand &c, const Ctx &ctx) {
+        const unsigned nlo = __vmins2((unsigned)k.x, (unsigned)c.x);         // -(max x1), -(max y1)
+        const unsigned hi = __vmins2((unsigned)k.y, (unsigned)c.y);          //   min x2 ,   min y2
+        const unsigned wh = __viaddmax_s16x2_relu(hi, nlo, 0u);              // max(0, w), max(0, h)
+        const int inter = (int)(wh & 0xFFFFu) * (int)(wh >> 16);
+        const int uni = k.z + c.z - inter;
         return inter >= (int)ctx.tab[uni];
     }
 };
 
+struct CandF64 {
+    double x1, y1, x2, y2, area;
+    int flat, pad;
+};
+
 struct BoxF64 {
-    using Box = double4;
-    using Area = double;
+    using Cand = CandF64;
+    static constexpr size_t kBoxBytes = sizeof(double4);
     struct Ctx { double thr; };
-    static __device__ __forceinline__ Box load(const void *boxes, size_t i) {
-        return reinterpret_cast<const double4 *>(boxes)[i];
+    static __device__ __forceinline__ Cand empty() { return Cand{0, 0, 0, 0, 0, 0, 0}; }
+    static __device__ __forceinline__ Cand load(const void *boxes, size_t i, int flat) {
+        const double4 b = reinterpret_cast<const double4 *>(boxes)[i];
+        Cand c;
+        c.x1 = b.x; c.y1 = b.y; c.x2 = b.z; c.y2 = b.w;
+        c.area = __dmul_rn(__dsub_rn(b.z, b.x), __dsub_rn(b.w, b.y));                // rpn.py:412
+        c.flat = flat; c.pad = 0;
+        return c;
     }
-    static __device__ __forceinline__ Area area(const Box &b) {
-        return __dmul_rn(__dsub_rn(b.z, b.x), __dsub_rn(b.w, b.y));                 // rpn.py:412
-    }
-    static __device__ __forceinline__ bool suppress(const Box &k, Area ka, const Box &c, Area ca,
-                                                    const Ctx &ctx) {
-        double xx1 = fmax(k.x, c.x), yy1 = fmax(k.y, c.y);                           // rpn.py:429-430
-        double xx2 = fmin(k.z, c.z), yy2 = fmin(k.w, c.w);                           // rpn.py:431-432
+    static __device__ __forceinline__ int flat(const Cand &c) { return c.flat; }
+    static __device__ __forceinline__ bool suppress(const Cand &k, const Cand &c, const Ctx &ctx) {
+        double xx1 = fmax(k.x1, c.x1), yy1 = fmax(k.y1, c.y1);                       // rpn.py:429-430
+        double xx2 = fmin(k.x2, c.x2), yy2 = fmin(k.y2, c.y2);                       // rpn.py:431-432
         double ww = fmax(0.0, __dsub_rn(xx2, xx1));                                  // rpn.py:434
         double hh = fmax(0.0, __dsub_rn(yy2, yy1));                                  // rpn.py:435
         double inter = __dmul_rn(ww, hh);                                            // rpn.py:437
-        double uni = __dsub_rn(__dadd_rn(ka, ca), inter);                            // rpn.py:440
+        double uni = __dsub_rn(__dadd_rn(k.area, c.area), inter);                    // rpn.py:440
         return __ddiv_rn(inter, __dadd_rn(uni, 1e-6)) > ctx.thr;                     // rpn.py:443,447
     }
 };
 
-template <typename KeyT> struct KeyBits;
-template <> struct KeyBits<uint32_t> { static constexpr int passes = 4; };
-template <> struct KeyBits<uint64_t> { static constexpr int passes = 8; };
+template <typename KeyT> struct KeyInfo;
+template <> struct KeyInfo<uint32_t> { static constexpr int passes = 4; static constexpr uint32_t max = 0xFFFFFFFFu; };
+template <> struct KeyInfo<uint64_t> { static constexpr int passes = 8; static constexpr uint64_t max = ~0ull; };
 
 struct SortNmsParams {
-    const void *boxes;        // [B][N] Box
+    const void *boxes;        // [B][N] boxes (int4 or double4)
     const void *keys;         // [B][N] KeyT, 0 = deleted
     int N;
-    int max_boxes;            // effective K = min(max_boxes, N)
+    int max_boxes;            // effective K = min(max_boxes, valid candidates)
     double thr;
     int table_entries;        // i32 only: umax + 1
     int sel_target;           // candidates the first (selective) sort round aims for
@@ -94,7 +124,7 @@ struct SortNmsParams {
     size_t det_stride;
     int det_max_boxes;
     int32_t *pick;            // f64: picked indices
-    int32_t *count;           // f64: {n, ties}
+    int32_t *count;           // f64: {n, ties, n_sorted}
     // global scratch per panel (generic-path sort buffers, big kept lists)
     unsigned char *ws;
     size_t ws_stride;
@@ -146,46 +176,28 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d, bool act) {
     return peers;
 }
 
-template <typename KeyT>
-__device__ __forceinline__ bool in_range(KeyT k, KeyT lo, KeyT hi) { return k >= lo && k <= hi; }
-
-// Per-warp digit histogram of the keys in [lo,hi] (warp w owns a contiguous slice of the
-// array and the counter row s_cnt[w][*]).  No atomics: one leader lane per digit and row.
-template <typename KeyT>
-__device__ void count_walk(const KeyT *in_k, int n_in, int shift, KeyT lo, KeyT hi, uint32_t *s_cnt) {
+// One stable radix pass over n elements (all of them take part).  Returns false when the pass
+// was skipped because every element shares the digit (block-uniform).
+template <typename KeyT, typename IdxT>
+__device__ bool radix_pass(const KeyT *in_k, const IdxT *in_i, KeyT *out_k, IdxT *out_i, int n, int shift,
+                           uint32_t *s_cnt, int *s_scan, int *s_flag) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kNmsWarps * kCntStride; i += kNmsThreads) s_cnt[i] = 0;
+    if (threadIdx.x == 0) *s_flag = 0;
     __syncthreads();
-    const int chunk = ((n_in + kNmsWarps - 1) / kNmsWarps + 31) & ~31;
-    const int wbeg = min(w * chunk, n_in), wend = min(wbeg + chunk, n_in);
+    const int chunk = ((n + kNmsWarps - 1) / kNmsWarps + 31) & ~31;
+    const int wbeg = min(w * chunk, n), wend = min(wbeg + chunk, n);
     uint32_t *cnt = s_cnt + w * kCntStride;
     for (int base = wbeg; base < wend; base += 32) {
         const int i = base + lane;
-        const KeyT key = (i < wend) ? in_k[i] : (KeyT)0;
-        const bool act = (i < wend) && in_range(key, lo, hi);
+        const bool act = i < wend;
+        const KeyT key = act ? in_k[i] : (KeyT)0;
         const uint32_t d = (uint32_t)(key >> shift) & 0xFFu;
         const uint32_t peers = digit_peers(d, act);
         if (act && (peers & lanemask_lt()) == 0) cnt[d] += __popc(peers);
         __syncwarp();
     }
     __syncthreads();
-}
-
-// One stable radix pass.  Elements outside [lo,hi] are dropped (used by the first pass, where
-// the input is the raw key array and the payload is the position itself: `in_i == nullptr`).
-// Returns the number of elements written (block-uniform), or -1 when the pass was skipped
-// because every element shares the digit.
-template <typename KeyT, typename IdxT>
-__device__ int radix_pass(const KeyT *in_k, const IdxT *in_i, KeyT *out_k, IdxT *out_i, int n_in,
-                          int shift, KeyT lo, KeyT hi, bool may_skip, uint32_t *s_cnt, int *s_scan,
-                          int *s_flag) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) *s_flag = 0;
-    count_walk<KeyT>(in_k, n_in, shift, lo, hi, s_cnt);
-    const int chunk = ((n_in + kNmsWarps - 1) / kNmsWarps + 31) & ~31;
-    const int wbeg = min(w * chunk, n_in), wend = min(wbeg + chunk, n_in);
-    uint32_t *cnt = s_cnt + w * kCntStride;
-    int total;
     // scan in (digit major, warp minor) order; thread t owns digit t>>2, warps (t&3)*8..+7
     {
         const int d = threadIdx.x >> 2, wq = (threadIdx.x & 3) * 8;
@@ -199,115 +211,187 @@ __device__ int radix_pass(const KeyT *in_k, const IdxT *in_i, KeyT *out_k, IdxT 
         int dsum = sum;
         dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
         dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+        int total;
         int ex = block_exscan(sum, s_scan, &total);
-        if (may_skip && dsum == total && total > 0 && (threadIdx.x & 3) == 0) *s_flag = 1;
+        if (dsum == total && total > 0 && (threadIdx.x & 3) == 0) *s_flag = 1;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             s_cnt[(wq + j) * kCntStride + d] = (uint32_t)ex;
             ex += (int)c[j];
         }
         __syncthreads();
-        if (*s_flag) return -1;
+        if (*s_flag) return false;
     }
     for (int base = wbeg; base < wend; base += 32) {
         const int i = base + lane;
-        const KeyT key = (i < wend) ? in_k[i] : (KeyT)0;
-        const bool act = (i < wend) && in_range(key, lo, hi);
+        const bool act = i < wend;
+        const KeyT key = act ? in_k[i] : (KeyT)0;
         const uint32_t d = (uint32_t)(key >> shift) & 0xFFu;
         const uint32_t peers = digit_peers(d, act);
         uint32_t off = 0;
         if (act) {
-            const IdxT idx = in_i ? in_i[i] : (IdxT)i;
             off = cnt[d];
             const uint32_t pos = off + __popc(peers & lanemask_lt());
             out_k[pos] = key;
-            out_i[pos] = idx;
+            out_i[pos] = in_i[i];
         }
         __syncwarp();
         if (act && (peers & lanemask_lt()) == 0) cnt[d] = off + __popc(peers);
         __syncwarp();
     }
     __syncthreads();
-    return total;
+    return true;
 }
 
-// Warp 0: in a 256-bin histogram (bin totals = column sums of the per-warp counters) find the
-// highest bin `b` with  count(bins > b) < need <= count(bins >= b).  Writes {b, count(bins > b),
-// hist[b], grand total} to s_out.  All 1024 threads must call (two block barriers inside).
-__device__ void find_top_bin(const uint32_t *s_cnt, int need, uint32_t *s_hist, int *s_out) {
-    if (threadIdx.x < 256) {
-        uint32_t t = 0;
-        for (int w = 0; w < kNmsWarps; ++w) t += s_cnt[w * kCntStride + threadIdx.x];
-        s_hist[threadIdx.x] = t;
-    }
+__device__ __forceinline__ void atomic_min_key(uint32_t *a, uint32_t v) { atomicMin(a, v); }
+__device__ __forceinline__ void atomic_max_key(uint32_t *a, uint32_t v) { atomicMax(a, v); }
+__device__ __forceinline__ void atomic_min_key(uint64_t *a, uint64_t v) {
+    atomicMin(reinterpret_cast<unsigned long long *>(a), (unsigned long long)v);
+}
+__device__ __forceinline__ void atomic_max_key(uint64_t *a, uint64_t v) {
+    atomicMax(reinterpret_cast<unsigned long long *>(a), (unsigned long long)v);
+}
+
+// count of keys >= t over the block; `slot` rotates over three shared counters so that one
+// barrier per call is enough
+template <typename KeyT>
+__device__ __forceinline__ int count_ge(const KeyT *keys, int N, KeyT t, int *s_cnt3, int &slot) {
+    int c = 0;
+    for (int i = threadIdx.x; i < N; i += kNmsThreads) c += (keys[i] >= t) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt3[slot], c);
+    const int nxt = slot == 2 ? 0 : slot + 1;
+    if (threadIdx.x == 0) s_cnt3[nxt] = 0;      // last read two barriers ago
     __syncthreads();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        // lane l owns bins 255-8l .. 248-8l (descending), so lane order = descending key order
-        uint32_t loc[8];
-        int sum = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            loc[j] = s_hist[255 - 8 * lane - j];
-            sum += (int)loc[j];
+    const int r = s_cnt3[slot];
+    slot = nxt;
+    return r;
+}
+
+// SELECT: largest threshold t (>= 1) with count(key >= t) >= target, stopped early once the count
+// is within 12.5 % of the target.  M = number of valid (non-zero) keys, S = count(key >= t).
+template <typename KeyT>
+__device__ KeyT select_threshold(const KeyT *keys, int N, int target, int *s_cnt3, KeyT *s_minmax, int &M,
+                                 int &S) {
+    // valid count, min and max key
+    {
+        int c = 0;
+        KeyT mn = KeyInfo<KeyT>::max, mx = 0;
+        for (int i = threadIdx.x; i < N; i += kNmsThreads) {
+            const KeyT k = keys[i];
+            if (k) {
+                ++c;
+                mn = k < mn ? k : mn;
+                mx = k > mx ? k : mx;
+            }
         }
-        int inc = sum;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const KeyT on = __shfl_xor_sync(0xffffffffu, mn, d), ox = __shfl_xor_sync(0xffffffffu, mx, d);
+            mn = on < mn ? on : mn;
+            mx = ox > mx ? ox : mx;
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (threadIdx.x == 0) {
+            s_cnt3[0] = 0; s_cnt3[1] = 0; s_cnt3[2] = 0;
+            s_minmax[0] = KeyInfo<KeyT>::max;
+            s_minmax[1] = 0;
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && c) {
+            atomicAdd(&s_cnt3[0], c);
+            atomic_min_key(&s_minmax[0], mn);
+            atomic_max_key(&s_minmax[1], mx);
+        }
+        __syncthreads();
+    }
+    M = s_cnt3[0];
+    KeyT lo = s_minmax[0], hi = s_minmax[1];
+    __syncthreads();
+    if (threadIdx.x == 0) { s_cnt3[0] = 0; s_cnt3[1] = 0; s_cnt3[2] = 0; }
+    __syncthreads();
+    S = M;
+    if (M <= target) return (KeyT)1;
+    int slot = 0;
+    // invariant: count(>= lo) = S >= target ; count(>= hi) < target (checked first for hi = max key)
+    const int c_hi = count_ge<KeyT>(keys, N, hi, s_cnt3, slot);
+    if (c_hi >= target) { S = c_hi; return hi; }
+    const int slack = target + (target >> 3);
+    while (hi - lo > 1 && S > slack) {
+        const KeyT mid = lo + (hi - lo) / 2;
+        const int c = count_ge<KeyT>(keys, N, mid, s_cnt3, slot);
+        if (c >= target) { lo = mid; S = c; } else hi = mid;
+    }
+    return lo;
+}
+
+// order-preserving compaction of the keys >= t with their positions; returns the count
+template <typename KeyT, typename IdxT>
+__device__ int compact_ge(const KeyT *keys, int N, KeyT t, KeyT *out_k, IdxT *out_i, int *s_scan) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int chunk = ((N + kNmsWarps - 1) / kNmsWarps + 31) & ~31;
+    const int wbeg = min(w * chunk, N), wend = min(wbeg + chunk, N);
+    int cnt = 0;
+    for (int base = wbeg; base < wend; base += 32) {
+        const int i = base + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, i < wend && keys[i] >= t));
+    }
+    if (lane == 0) s_scan[w] = cnt;
+    __syncthreads();
+    if (w == 0) {
+        const int v = s_scan[lane];
+        int inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int n = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += n;
         }
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
-        int above = inc - sum;                      // keys in bins owned by lower lanes (= larger keys)
-        const bool mine = above < need && need <= inc;
-        if (mine) {
-            int b = 255 - 8 * lane, cnt = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (above + (int)loc[j] >= need) { b = 255 - 8 * lane - j; cnt = (int)loc[j]; break; }
-                above += (int)loc[j];
-            }
-            s_out[0] = b; s_out[1] = above; s_out[2] = cnt;
-        }
-        if (lane == 0) {
-            s_out[3] = total;
-            if (need > total) { s_out[0] = 0; s_out[1] = total; s_out[2] = 0; }   // everything is selected
-        }
+        s_scan[lane] = inc - v;
+        if (lane == 31) s_scan[32] = inc;
     }
     __syncthreads();
+    int pos = s_scan[w];
+    const int total = s_scan[32];
+    for (int base = wbeg; base < wend; base += 32) {
+        const int i = base + lane;
+        const KeyT k = (i < wend) ? keys[i] : (KeyT)0;
+        const bool act = (i < wend) && k >= t;
+        const uint32_t m = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const int o = pos + __popc(m & lanemask_lt());
+            out_k[o] = k;
+            out_i[o] = (IdxT)i;
+        }
+        pos += __popc(m);
+    }
+    __syncthreads();
+    return total;
 }
-
-template <typename KeyT> struct KeyMax;
-template <> struct KeyMax<uint32_t> { static constexpr uint32_t v = 0xFFFFFFFFu; };
-template <> struct KeyMax<uint64_t> { static constexpr uint64_t v = ~0ull; };
 
 template <typename Traits, typename KeyT, typename IdxT, bool kSmemSort, bool kKeptSmem>
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams p) {
-    using Box = typename Traits::Box;
-    using Area = typename Traits::Area;
-    constexpr bool kI32 = sizeof(Box) == sizeof(int4);
-    constexpr int kBits = (int)sizeof(KeyT) * 8;
-    constexpr KeyT kMaxKey = KeyMax<KeyT>::v;
+    using Cand = typename Traits::Cand;
+    constexpr bool kI32 = sizeof(Cand) == sizeof(int4);
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);                 // TMA barrier
     int *s_misc = reinterpret_cast<int *>(smem + 16);                     // 16 ints
     int *s_scan = reinterpret_cast<int *>(smem + 96);                     // 34 ints
     uint64_t *s_turn = reinterpret_cast<uint64_t *>(smem + 256);          // [32] hand-off barriers
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + 512);          // [256]
+    KeyT *s_minmax = reinterpret_cast<KeyT *>(smem + 512);                // [2]
+    volatile int *s_kafter = reinterpret_cast<volatile int *>(smem + 1536);   // [32] kept count after row w
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + p.sm_off_cnt);  // [32][257]
     volatile int *s_kcount = s_misc + 0;
     int *s_flag = s_misc + 2;
     int *s_ties = s_misc + 3;
-    int *s_sel = s_misc + 4;                                              // 4 ints
+    int *s_cnt3 = s_misc + 4;                                             // 3 ints
     volatile int *s_fault = s_misc + 8;
-    volatile int *s_kafter = reinterpret_cast<volatile int *>(smem + 1536);         // [32] kept count after row w
 
     const int seg = blockIdx.x;
     const int N = p.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const KeyT *g_keys = reinterpret_cast<const KeyT *>(p.keys) + (size_t)seg * N;
-    const unsigned char *g_boxes = reinterpret_cast<const unsigned char *>(p.boxes) + (size_t)seg * N * sizeof(Box);
+    const unsigned char *g_boxes = reinterpret_cast<const unsigned char *>(p.boxes) + (size_t)seg * N * Traits::kBoxBytes;
     unsigned char *ws = p.ws + (size_t)seg * p.ws_stride;
 
     KeyT *kA, *kB;
@@ -335,8 +419,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     }
     __syncthreads();
 
-    // ---- stage the raw keys (one TMA bulk copy into shared memory on the hot path) -----
+    // ---- stage 0: raw keys -> shared memory (one TMA bulk copy on the hot path) ----------
     const KeyT *raw_k = g_keys;
+    bool tma_pending = false;
     if (kSmemSort) {
         const size_t bytes = (size_t)N * sizeof(KeyT);
         const uint32_t bulk = ((reinterpret_cast<uintptr_t>(g_keys) & 15) == 0) ? (uint32_t)(bytes & ~(size_t)15) : 0u;
@@ -347,6 +432,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         // tail (and the whole array when the source is not 16-byte aligned)
         for (int i = (int)(bulk / sizeof(KeyT)) + threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
         raw_k = kA;
+        tma_pending = bulk != 0;
     }
 
     // ---- suppression table, built while the keys land (i32 path) ------------------------
@@ -364,32 +450,19 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             s_tab[u] = ok ? (uint16_t)c : (uint16_t)0xFFFF;
         }
     }
-    if (kSmemSort) {
-        const size_t bytes = (size_t)N * sizeof(KeyT);
-        const bool bulk = ((reinterpret_cast<uintptr_t>(g_keys) & 15) == 0) && (bytes & ~(size_t)15) != 0;
-        if (bulk) mbar_wait(s_bar, 0);
-    }
+    if (tma_pending) mbar_wait(s_bar, 0);
     __syncthreads();
 
     // kept list
-    Box *kbox;
-    Area *karea;
-    int *kidx;
+    Cand *kept;
     {
-        const int cap = min(p.max_boxes, N);
         unsigned char *kb = kKeptSmem ? (smem + p.sm_off_kept) : (ws + p.ws_off_kept);
-        kbox = reinterpret_cast<Box *>(kb);
-        karea = reinterpret_cast<Area *>(kbox + cap);
-        kidx = reinterpret_cast<int *>(karea + cap);
+        kept = reinterpret_cast<Cand *>(kb);
     }
-    Box *s_tile = reinterpret_cast<Box *>(s_cnt);   // counters are dead during the NMS; [kTile] boxes fit
+    Cand *s_tile = reinterpret_cast<Cand *>(s_cnt);   // counters are dead during the NMS
     typename Traits::Ctx ctx;
     if constexpr (kI32) ctx.tab = s_tab; else ctx.thr = p.thr;
 
-    // ---- round 0: only the top-scoring slice is sorted; round 1 (rare): everything -------
-    // The greedy loop stops at max_boxes keeps, which normally happens within the first few
-    // hundred candidates, so a two-level radix SELECT (histograms of the two top key bytes)
-    // finds a threshold with about `sel_target` keys above it and only those are sorted.
     int M = 0;            // valid candidates
     int S = 0;            // candidates sorted so far (ranks [0,S) are final)
     int done = 0;         // ranks already visited by the NMS
@@ -398,53 +471,41 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     int tile_no = 0;
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
+        // ---- stage 1: select + compact ---------------------------------------------------
         KeyT thr_key = (KeyT)1;
         if (round == 0) {
-            // level 1: top byte over all valid keys
-            count_walk<KeyT>(raw_k, N, kBits - 8, (KeyT)1, kMaxKey, s_cnt);
-            find_top_bin(s_cnt, p.sel_target, s_hist, s_sel);
-            M = s_sel[3];
+            thr_key = select_threshold<KeyT>(raw_k, N, p.sel_target, s_cnt3, s_minmax, M, S);
             K = min(p.max_boxes, M);
-            if (M > p.sel_target) {
-                const int b1 = s_sel[0], above1 = s_sel[1];
-                const KeyT lo1 = (KeyT)b1 << (kBits - 8);
-                const KeyT hi1 = lo1 | (((KeyT)1 << (kBits - 8)) - 1);
-                __syncthreads();
-                // level 2: second byte inside the boundary bin
-                count_walk<KeyT>(raw_k, N, kBits - 16, lo1, hi1, s_cnt);
-                find_top_bin(s_cnt, p.sel_target - above1, s_hist, s_sel);
-                thr_key = lo1 | ((KeyT)s_sel[0] << (kBits - 16));
-                if (thr_key == 0) thr_key = 1;
-            }
+        } else if (kSmemSort) {
+            // the ping-pong buffers overwrote the staged keys: fetch them again
+            for (int i = threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
             __syncthreads();
-        } else {
-            if (kSmemSort) {      // the ping-pong buffers overwrote the staged keys: fetch them again
-                for (int i = threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
-                __syncthreads();
-            }
         }
-
-        // ---- stable LSD radix sort of the keys >= thr_key --------------------------------
-        const KeyT *in_k = raw_k;
-        const IdxT *in_i = nullptr;
-        KeyT *out_k = kSmemSort ? kB : kA;
-        IdxT *out_i = kSmemSort ? iB : iA;
-        int n_in = N;
-#pragma unroll 1
-        for (int pass = 0; pass < KeyBits<KeyT>::passes; ++pass) {
-            const bool first = pass == 0;
-            int r = radix_pass<KeyT, IdxT>(in_k, in_i, out_k, out_i, n_in, pass * 8, first ? thr_key : (KeyT)0,
-                                           kMaxKey, !first, s_cnt, s_scan, s_flag);
-            if (r >= 0) {
-                n_in = r;
-                in_k = out_k;
-                in_i = out_i;
-                if (out_k == kA) { out_k = kB; out_i = iB; } else { out_k = kA; out_i = iA; }
-            }
-            if (n_in == 0) break;
-        }
-        S = n_in;         // in_k / in_i: S entries ascending by (score, flat index)
+        // smem path: raw keys live in kA, so the compacted slice goes to kB
+        KeyT *ck = kSmemSort ? kB : kA;
+        IdxT *ci = kSmemSort ? iB : iA;
+        S = compact_ge<KeyT, IdxT>(raw_k, N, thr_key, ck, ci, s_scan);
         if (round == 1) M = S;
+
+        // ---- stage 2: stable LSD radix sort of the slice -----------------------------------
+        const KeyT *in_k = ck;
+        const IdxT *in_i = ci;
+        KeyT *out_k = (ck == kA) ? kB : kA;
+        IdxT *out_i = (ci == iA) ? iB : iA;
+        if (S > 1) {
+#pragma unroll 1
+            for (int pass = 0; pass < KeyInfo<KeyT>::passes; ++pass) {
+                if (radix_pass<KeyT, IdxT>(in_k, in_i, out_k, out_i, S, pass * 8, s_cnt, s_scan, s_flag)) {
+                    const KeyT *nk = out_k;
+                    const IdxT *ni = out_i;
+                    out_k = const_cast<KeyT *>(in_k);
+                    out_i = const_cast<IdxT *>(in_i);
+                    in_k = nk;
+                    in_i = ni;
+                }
+            }
+        }
+        // in_k / in_i: S entries ascending by (score, flat index)
 
         // ---- score ties among the sorted candidates (reported) -----------
         {
@@ -461,82 +522,66 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         }
         __syncthreads();
 
-        // ---- greedy suppression over ranks [done, S) -------------------------------------
+        // ---- stage 3: greedy suppression over ranks [done, S) ----------------------------
 #pragma unroll 1
         for (int base = done; base < S && k0 < K; base += kTile, ++tile_no) {
             const uint32_t parity = tile_no & 1;
             const int r = base + threadIdx.x;
             const bool active = r < S;
-            Box box;
-            Area ar = 0;
-            int flat = 0;
+            Cand cand = Traits::empty();
             if (active) {
-                flat = (int)in_i[S - 1 - r];
-                box = Traits::load(g_boxes, (size_t)flat);
-                ar = Traits::area(box);
-            } else {
-                if constexpr (kI32) box = make_int4(0, 0, 0, 0); else box = make_double4(0, 0, 0, 0);
+                const int flat = (int)in_i[S - 1 - r];
+                cand = Traits::load(g_boxes, (size_t)flat, flat);
             }
-            s_tile[threadIdx.x] = box;
+            s_tile[threadIdx.x] = cand;
             __syncwarp();
 
             // (a) against boxes kept by earlier tiles
             bool alive = active;
-            for (int j = 0; j < k0; ++j) {
-                Box kb = kbox[j];
-                Area ka = karea[j];
-                if (Traits::suppress(kb, ka, box, ar, ctx)) alive = false;
-            }
+            for (int j = 0; j < k0; ++j)
+                if (Traits::suppress(kept[j], cand, ctx)) alive = false;
             // (b) intra-row matrix: which lower lanes of my row overlap me
             uint32_t lower = 0;
             {
                 uint32_t todo = __ballot_sync(0xffffffffu, alive);
                 while (todo) {
-                    int j = __ffs(todo) - 1;
+                    const int j = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    Box ob = s_tile[(w << 5) + j];
-                    Area oa = Traits::area(ob);
-                    if (j < lane && Traits::suppress(ob, oa, box, ar, ctx)) lower |= 1u << j;
+                    const Cand ob = s_tile[(w << 5) + j];
+                    if (j < lane && Traits::suppress(ob, cand, ctx)) lower |= 1u << j;
                 }
             }
-            // (c) systolic hand-off: rows retire in rank order.  A warp sleeps on the mbarrier of
-            //     each earlier row in turn (hardware wait, no issue slots burnt) and tests its
-            //     candidates against the boxes kept since it last looked.
+            // (c) rows retire in rank order.  A warp sleeps on the mbarrier of each earlier row in
+            //     turn (hardware wait, no issue slots burnt) and tests its candidates against the
+            //     boxes kept since it last looked; once max_boxes are kept it stops looking.
             int seen = k0;
             int kc = k0;
-            for (int pw = 0; pw < w && kc < K; ++pw) {
+            for (int pw = 0; pw < w; ++pw) {
                 if (!mbar_wait_bounded(&s_turn[pw], parity)) { *s_fault = 1; break; }
                 kc = s_kafter[pw];            // published by exactly the row just acquired
-                for (int j = seen; j < kc; ++j) {
-                    Box kb = kbox[j];
-                    Area ka = karea[j];
-                    if (Traits::suppress(kb, ka, box, ar, ctx)) alive = false;
-                }
+                if (kc >= K) break;
+                for (int j = seen; j < kc; ++j)
+                    if (Traits::suppress(kept[j], cand, ctx)) alive = false;
                 seen = kc;
             }
             if (kc < K) {
                 uint32_t und = __ballot_sync(0xffffffffu, alive);
-                uint32_t kept = 0;
+                uint32_t keep = 0;
                 const bool me0 = alive;
                 while (und) {
-                    bool me = me0 && ((und >> lane) & 1u);
-                    uint32_t know = __ballot_sync(0xffffffffu, me && !(lower & kept) && !(lower & und));
-                    kept |= know;
-                    uint32_t dnow = __ballot_sync(0xffffffffu, me && (lower & kept));
+                    const bool me = me0 && ((und >> lane) & 1u);
+                    const uint32_t know = __ballot_sync(0xffffffffu, me && !(lower & keep) && !(lower & und));
+                    keep |= know;
+                    const uint32_t dnow = __ballot_sync(0xffffffffu, me && (lower & keep));
                     und &= ~(know | dnow);
                 }
-                int room = K - kc;
-                int nk = __popc(kept);
+                const int room = K - kc;
+                int nk = __popc(keep);
                 if (nk > room) {                       // keep only the first `room` of this row
-                    kept &= (1u << __fns(kept, 0, room + 1)) - 1u;
+                    keep &= (1u << __fns(keep, 0, room + 1)) - 1u;
                     nk = room;
                 }
-                if ((kept >> lane) & 1u) {
-                    int pos = kc + __popc(kept & lanemask_lt());
-                    kbox[pos] = box;
-                    karea[pos] = ar;
-                    kidx[pos] = flat;
-                }
+                if ((keep >> lane) & 1u) kept[kc + __popc(keep & lanemask_lt())] = cand;
                 kc += nk;
             }
             __syncwarp();
@@ -569,8 +614,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         }
         for (int j = threadIdx.x; j < p.det_max_boxes; j += kNmsThreads) {
             if (j < kept_n) {
-                int flat = kidx[j];
-                rb[j] = kbox[j];
+                const Cand c = kept[j];
+                const int flat = Traits::flat(c);
+                rb[j] = BoxI32::unpack(reinterpret_cast<const int4 &>(c));
                 rs[j] = key_to_score((uint32_t)g_keys[flat]);
                 ri[j] = flat;
             } else {
@@ -585,7 +631,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             p.count[1] = *s_ties;
             p.count[2] = S;
         }
-        for (int j = threadIdx.x; j < kept_n; j += kNmsThreads) p.pick[j] = kidx[j];
+        for (int j = threadIdx.x; j < kept_n; j += kNmsThreads) p.pick[j] = Traits::flat(kept[j]);
     }
 }
 
@@ -610,21 +656,21 @@ static int max_optin_smem() {
     return v;
 }
 
-template <typename Box, typename Area, typename KeyT>
+template <typename Cand, typename KeyT>
 static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_smem_sort, int smem_limit) {
     NmsPlan pl{};
     SortNmsParams &p = pl.p;
     const int K = max_boxes < N ? max_boxes : N;
-    size_t off = 2048;                                  // barriers, misc, scan scratch, 256-bin histogram, row counts
+    size_t off = kSmemHeader;
     p.sm_off_cnt = (int)off;
     size_t cnt_bytes = (size_t)kNmsWarps * kCntStride * 4;
-    size_t tile_bytes = (size_t)kTile * sizeof(Box);
+    size_t tile_bytes = (size_t)kTile * sizeof(Cand);
     off += align_up(cnt_bytes > tile_bytes ? cnt_bytes : tile_bytes, 128);
     p.sm_off_table = (int)off;
     off += align_up((size_t)table_entries * 2, 128);
     pl.kept_smem = K <= kKeptSmemMax;
     p.sm_off_kept = (int)off;
-    if (pl.kept_smem) off += align_up((size_t)K * (sizeof(Box) + sizeof(Area) + 4) + 64, 128);
+    if (pl.kept_smem) off += align_up((size_t)K * sizeof(Cand) + 64, 128);
     // first sort round: about this many top-scoring candidates (see the kernel)
     p.sel_target = (4 * K > 2048) ? 4 * K : 2048;
     // shared-memory sort: keys ping-pong + uint16 index ping-pong
@@ -641,7 +687,7 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     p.ws_off_kB = w; w += align_up(cap * sizeof(KeyT), 256);
     p.ws_off_iA = w; w += align_up(cap * 4, 256);
     p.ws_off_iB = w; w += align_up(cap * 4, 256);
-    p.ws_off_kept = w; w += align_up((size_t)K * (sizeof(Box) + sizeof(Area) + 4) + 64, 256);
+    p.ws_off_kept = w; w += align_up((size_t)K * sizeof(Cand) + 64, 256);
     pl.ws_stride = w;
     p.ws_stride = w;
     return pl;
@@ -652,6 +698,11 @@ static int launch(K kernel, const NmsPlan &pl, int B, cudaStream_t st) {
     RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
     kernel<<<B, kNmsThreads, pl.smem_bytes, st>>>(pl.p);
     return check_launch("sort_nms_kernel");
+}
+
+__global__ void make_keys64_kernel(const double *probs, const uint8_t *valid, int M, uint64_t *keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) keys[i] = (valid && !valid[i]) ? 0ull : score_to_key64(probs[i]);
 }
 
 }  // namespace radnet
@@ -666,7 +717,7 @@ extern "C" size_t radnet_det_record_bytes(int max_boxes) {
 extern "C" size_t radnet_sort_nms_i32_workspace_bytes(int B, int N, int map_h, int map_w, int max_boxes) {
     if (B < 1 || N < 1 || max_boxes < 1) return 0;
     (void)map_h; (void)map_w;
-    NmsPlan pl = make_plan<int4, int, uint32_t>(N, max_boxes, 1, false, 0);
+    NmsPlan pl = make_plan<BoxI32::Cand, uint32_t>(N, max_boxes, 1, false, 0);
     return pl.ws_stride * (size_t)B;
 }
 
@@ -677,11 +728,11 @@ extern "C" int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *key
     RADNET_CHECK_ARG(B >= 1 && N >= 1 && max_boxes >= 1 && map_h >= 1 && map_w >= 1,
                      "sort_nms_i32: bad sizes B=%d N=%d max_boxes=%d", B, N, max_boxes);
     long long umax = 2LL * (map_h - 1) * (map_w - 1);
-    if (umax + 1 > kMaxTableEntries) {
+    if (umax + 1 > kMaxTableEntries || map_h > 16384 || map_w > 16384) {
         set_error("sort_nms_i32: map %dx%d exceeds the exact-table range; use the f64 path", map_h, map_w);
         return RADNET_E_UNSUPPORTED;
     }
-    NmsPlan pl = make_plan<int4, int, uint32_t>(N, max_boxes, (int)umax + 1, true, max_optin_smem());
+    NmsPlan pl = make_plan<BoxI32::Cand, uint32_t>(N, max_boxes, (int)umax + 1, true, max_optin_smem());
     if (pl.smem_bytes > (size_t)max_optin_smem()) {
         set_error("sort_nms_i32: shared memory plan %zu B exceeds the device limit", pl.smem_bytes);
         return RADNET_E_UNSUPPORTED;
@@ -710,22 +761,16 @@ extern "C" int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *key
 extern "C" size_t radnet_nms_f64_workspace_bytes(int M, int max_boxes) {
     if (M < 1 || max_boxes < 1) return 0;
     // +M*8 for the uint64 key image built by the entry point
-    NmsPlan pl = make_plan<double4, double, uint64_t>(M, max_boxes, 1, false, 0);
+    NmsPlan pl = make_plan<BoxF64::Cand, uint64_t>(M, max_boxes, 1, false, 0);
     return pl.ws_stride + align_up((size_t)M * 8, 256);
 }
 
-namespace radnet {
-__global__ void make_keys64_kernel(const double *probs, const uint8_t *valid, int M, uint64_t *keys) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < M) keys[i] = (valid && !valid[i]) ? 0ull : score_to_key64(probs[i]);
-}
-}  // namespace radnet
-
-extern "C" int radnet_nms_f64(const double *boxes, const double *probs, const uint8_t *valid, int M, double thr, int max_boxes,
-                              int32_t *pick, int32_t *count, void *ws, size_t ws_bytes, void *stream) {
+extern "C" int radnet_nms_f64(const double *boxes, const double *probs, const uint8_t *valid, int M, double thr,
+                              int max_boxes, int32_t *pick, int32_t *count, void *ws, size_t ws_bytes,
+                              void *stream) {
     RADNET_CHECK_ARG(boxes && probs && pick && count && ws, "nms_f64: null pointer");
     RADNET_CHECK_ARG(M >= 1 && max_boxes >= 1, "nms_f64: bad sizes M=%d max_boxes=%d", M, max_boxes);
-    NmsPlan pl = make_plan<double4, double, uint64_t>(M, max_boxes, 1, false, max_optin_smem());
+    NmsPlan pl = make_plan<BoxF64::Cand, uint64_t>(M, max_boxes, 1, false, max_optin_smem());
     size_t key_bytes = align_up((size_t)M * 8, 256);
     if (ws_bytes < pl.ws_stride + key_bytes) {
         set_error("nms_f64: workspace %zu < %zu", ws_bytes, pl.ws_stride + key_bytes);

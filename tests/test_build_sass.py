@@ -1,0 +1,57 @@
+"""CPU: properties of the built SASS that the parity and 'B200-native' claims rely on."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from rock_art_radnet_b200 import _lib
+
+
+def _sass():
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(line)
+    return funcs
+
+
+def test_sm100a_and_no_packed_fma_in_roi_pool():
+    funcs = _sass()
+    pool = {k: v for k, v in funcs.items() if "roi_pool" in k}
+    assert len(pool) >= 5
+    for name, lines in pool.items():
+        text = "\n".join(lines)
+        # TF computes a + (b-a)*t with separate multiply and add; ptxas 12.9 contracts packed
+        # mul+add into FFMA2, so the kernels keep the final add scalar (see roipool.cu)
+        assert "FFMA2" not in text, name
+    slice8 = "\n".join(next(v for k, v in pool.items() if "slice_kernelILi8" in k))
+    assert "FMUL2" in slice8 and "FADD2" in slice8          # packed f32x2 math is in use
+    assert "LDGSTS" in slice8                               # cp.async staging of the map slice
+    assert "STG.E.EF.128" in slice8                         # streaming 16-byte stores
+
+
+def test_nms_uses_tma_bulk_copy_mbarrier_and_simd_minmax():
+    funcs = _sass()
+    hot = "\n".join(next(v for k, v in funcs.items() if "sort_nms_kernelINS_6BoxI32EjtLb1ELb1" in k))
+    assert "UBLKCP" in hot                                   # cp.async.bulk (1-D TMA) key staging
+    assert "SYNCS" in hot                                    # mbarrier arrive / try_wait
+    assert "VIMNMX.S16x2" in hot and "VIADDMNMX.S16x2.RELU" in hot
+    assert "MATCH.ANY" not in hot                            # ballot-based ranking
+    assert "VOTE" in hot
+
+
+def test_elf_is_sm_100a_only():
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = {ln.split(".")[-2] for ln in out.splitlines() if "ELF file" in ln}
+    assert archs == {"sm_100a"}, archs

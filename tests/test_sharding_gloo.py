@@ -1,0 +1,67 @@
+"""CPU: the world_size > 1 path (per-panel sharding + detection gather) on the gloo backend."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+from conftest import ROOT  # noqa: E402
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_panels, max_boxes, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rock_art_radnet_b200 import sharding
+    from rock_art_radnet_b200.pipeline import DetectionRecords
+    ids = sharding.shard_indices(n_panels, rank, world)
+    per = max(sharding.shard_sizes(n_panels, world))
+    rec = DetectionRecords(per, max_boxes, "cpu")
+    # fake "detections": panel p keeps (p % max_boxes) + 1 boxes whose coordinates encode p
+    for slot, p in enumerate(ids):
+        k = int(p) % max_boxes + 1
+        rec.header[slot, 0] = k
+        rec.header[slot, 1] = 1000 + int(p)
+        for j in range(k):
+            rec.boxes[slot, j] = torch.tensor([int(p), j, int(p) + 1, j + 1], dtype=torch.int32)
+            rec.scores[slot, j] = float(p) + j / 100.0
+            rec.index[slot, j] = int(p) * 10 + j
+    gathered, work = sharding.gather_detections(rec.raw, async_op=True)
+    work.wait()
+    assert gathered.shape == (world, per, rec.stride)
+    dets = sharding.split_gathered(gathered, n_panels, max_boxes)
+    ok = len(dets) == n_panels
+    for p, d in enumerate(dets):
+        k = p % max_boxes + 1
+        ok &= d["boxes"].shape == (k, 4) and d["n_candidates"] == 1000 + p
+        ok &= d["boxes"][:, 0].tolist() == [p] * k and d["index"].tolist() == [p * 10 + j for j in range(k)]
+    np.save(os.path.join(out_dir, "ok_%d.npy" % rank), np.array([int(ok)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_panels", [(2, 9), (2, 64)])
+def test_gather_detections_world2_gloo(tmp_path, world, n_panels):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_panels, 6, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert np.load(tmp_path / ("ok_%d.npy" % r))[0] == 1
+
+
+def test_gather_without_process_group_is_identity():
+    from rock_art_radnet_b200 import sharding
+    raw = torch.arange(2 * 40, dtype=torch.uint8).reshape(2, 40)
+    g, work = sharding.gather_detections(raw)
+    assert work is None and g.shape == (1, 2, 40) and torch.equal(g[0], raw)

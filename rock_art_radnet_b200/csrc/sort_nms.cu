@@ -41,6 +41,7 @@ constexpr int kCntStride = 257;                 // padded digit row: conflict-fr
 constexpr int kTile = kNmsThreads;              // candidates per NMS tile
 constexpr int kMaxTableEntries = 65535;
 constexpr int kKeptSmemMax = 1024;              // kept boxes held in shared memory
+constexpr int kLookAhead = 6;                   // rows that may run ahead of the retiring row
 constexpr int kSmemHeader = 2048;               // barriers, misc words, scan scratch, row counts
 
 // ----------------------------------------------------------------------------------
@@ -62,6 +63,14 @@ struct BoxI32 {
         return c;
     }
     static __device__ __forceinline__ int flat(const Cand &c) { return c.w; }
+    // one LDS.128 (the compiler otherwise narrows the read to three 32-bit loads)
+    static __device__ __forceinline__ Cand load_shared(const Cand *p) {
+        Cand c;
+        asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+                     : "r"(smem_u32(p)));
+        return c;
+    }
     static __device__ __forceinline__ int4 unpack(const Cand &c) {
         const int nx1 = (int)(short)(c.x & 0xFFFF), ny1 = c.x >> 16;
         return make_int4(-nx1, -ny1, (int)(short)(c.y & 0xFFFF), c.y >> 16);
@@ -96,6 +105,7 @@ struct BoxF64 {
         return c;
     }
     static __device__ __forceinline__ int flat(const Cand &c) { return c.flat; }
+    static __device__ __forceinline__ Cand load_shared(const Cand *p) { return *p; }
     static __device__ __forceinline__ bool suppress(const Cand &k, const Cand &c, const Ctx &ctx) {
         double xx1 = fmax(k.x1, c.x1), yy1 = fmax(k.y1, c.y1);                       // rpn.py:429-430
         double xx2 = fmin(k.x2, c.x2), yy2 = fmin(k.y2, c.y2);                       // rpn.py:431-432
@@ -538,30 +548,41 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
 
             // (a) against boxes kept by earlier tiles
             bool alive = active;
-            for (int j = 0; j < k0; ++j)
-                if (Traits::suppress(kept[j], cand, ctx)) alive = false;
-            // (b) intra-row matrix: which lower lanes of my row overlap me
+            for (int j = 0; j < k0; ++j) {
+                const Cand kb = kKeptSmem ? Traits::load_shared(kept + j) : kept[j];
+                if (Traits::suppress(kb, cand, ctx)) alive = false;
+            }
+            // (b) intra-row matrix: which lower lanes of my row overlap me.  Each unordered pair is
+            //     evaluated once: in step t lane l tests lane (l-t) mod 32 and the ballot hands the
+            //     result to whichever of the two has the higher rank index.
             uint32_t lower = 0;
             {
-                uint32_t todo = __ballot_sync(0xffffffffu, alive);
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const Cand ob = s_tile[(w << 5) + j];
-                    if (j < lane && Traits::suppress(ob, cand, ctx)) lower |= 1u << j;
+                const uint32_t row_alive = __ballot_sync(0xffffffffu, alive);
+#pragma unroll 4
+                for (int t = 1; t <= 16; ++t) {
+                    const int a = (lane - t) & 31, b = (lane + t) & 31;
+                    const Cand ob = Traits::load_shared(s_tile + (w << 5) + a);
+                    const bool hit = alive && ((row_alive >> a) & 1u) && Traits::suppress(ob, cand, ctx);
+                    const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                    if (a < lane && hit) lower |= 1u << a;
+                    if (b < lane && ((hits >> b) & 1u)) lower |= 1u << b;
                 }
             }
-            // (c) rows retire in rank order.  A warp sleeps on the mbarrier of each earlier row in
-            //     turn (hardware wait, no issue slots burnt) and tests its candidates against the
-            //     boxes kept since it last looked; once max_boxes are kept it stops looking.
+            // (c) rows retire in rank order.  A warp first sleeps until the row kLookAhead before it
+            //     has retired (so rows far beyond the cut-off never start), then waits on the mbarrier
+            //     of each remaining earlier row in turn (hardware wait, no issue slots burnt) and tests
+            //     its candidates against the boxes kept since it last looked; once max_boxes are kept
+            //     it stops looking.
             int seen = k0;
             int kc = k0;
-            for (int pw = 0; pw < w; ++pw) {
+            for (int pw = max(0, w - kLookAhead); pw < w; ++pw) {
                 if (!mbar_wait_bounded(&s_turn[pw], parity)) { *s_fault = 1; break; }
                 kc = s_kafter[pw];            // published by exactly the row just acquired
                 if (kc >= K) break;
-                for (int j = seen; j < kc; ++j)
-                    if (Traits::suppress(kept[j], cand, ctx)) alive = false;
+                for (int j = seen; j < kc; ++j) {
+                    const Cand kb = kKeptSmem ? Traits::load_shared(kept + j) : kept[j];
+                    if (Traits::suppress(kb, cand, ctx)) alive = false;
+                }
                 seen = kc;
             }
             if (kc < K) {

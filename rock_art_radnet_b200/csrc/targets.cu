@@ -111,7 +111,9 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
     bool pos = false;
     double loc_best = 0.0;
     int loc_g = -1;
-    for (int g = 0; g < G; ++g) {
+    // most anchors cross the image border (77 % for a 600-px panel): such warps only write zeros
+    const int G_loop = __any_sync(0xffffffffu, inside) ? G : 0;
+    for (int g = 0; g < G_loop; ++g) {
         double iou = 0.0;
         if (inside)
             iou = ref_iou(s_gt[4 * g + 0], s_gt[4 * g + 2], s_gt[4 * g + 1], s_gt[4 * g + 3], an.x1, an.y1,
@@ -161,28 +163,44 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
     }
 }
 
-// forced positives + best_anchor table, one thread per panel, GT in order (utils.py:741-766)
-__global__ void rpn_targets_finalize_kernel(RpnTargetParams p, int B) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// forced positives + best_anchor table (utils.py:741-766).  One CTA per panel, one thread per GT.
+// The reference applies the forced positives in GT order, so when several GT share the same
+// best anchor the LAST one wins: a thread only writes if no later forced GT targets its anchor.
+__global__ void __launch_bounds__(128) rpn_targets_finalize_kernel(RpnTargetParams p) {
+    extern __shared__ unsigned s_order[];          // [Gmax] loop-order id of the forced anchor, or ~0
+    const int b = blockIdx.x;
     const int HW = p.H * p.W;
     const int G = p.gt_count[b];
     double *cls_b = p.y_cls + (size_t)b * 2 * p.A * HW;
     double *regr_b = p.y_regr + (size_t)b * 8 * p.A * HW;
-    for (int g = 0; g < p.Gmax; ++g) {
+    for (int g = threadIdx.x; g < p.Gmax; g += blockDim.x) {
         int32_t *ba = p.best_anchor + ((size_t)b * p.Gmax + g) * 4;
-        unsigned long long key = (g < G) ? p.best_key[(size_t)b * p.Gmax + g] : 0ull;
+        const unsigned long long key = (g < G) ? p.best_key[(size_t)b * p.Gmax + g] : 0ull;
+        unsigned order = 0xFFFFFFFFu;
         if (!key) {
             ba[0] = ba[1] = ba[2] = ba[3] = -1;
-            continue;
+        } else {
+            const unsigned o = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+            const int jy = (int)(o % (unsigned)p.H);
+            const unsigned rest = o / (unsigned)p.H;
+            const int ix = (int)(rest % (unsigned)p.W);
+            const int a = (int)(rest / (unsigned)p.W);
+            ba[0] = jy; ba[1] = ix; ba[2] = a % p.n_ratios; ba[3] = a / p.n_ratios;     // utils.py:697
+            if (p.n_hits[(size_t)b * p.Gmax + g] == 0) order = o;
         }
-        unsigned order = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
-        int jy = (int)(order % (unsigned)p.H);
-        unsigned rest = order / (unsigned)p.H;
-        int ix = (int)(rest % (unsigned)p.W);
-        int a = (int)(rest / (unsigned)p.W);
-        ba[0] = jy; ba[1] = ix; ba[2] = a % p.n_ratios; ba[3] = a / p.n_ratios;     // utils.py:697
-        if (p.n_hits[(size_t)b * p.Gmax + g] != 0) continue;
+        s_order[g] = order;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const unsigned o = s_order[g];
+        if (o == 0xFFFFFFFFu) continue;
+        bool last = true;
+        for (int g2 = g + 1; g2 < G; ++g2) last = last && (s_order[g2] != o);
+        if (!last) continue;
+        const int jy = (int)(o % (unsigned)p.H);
+        const unsigned rest = o / (unsigned)p.H;
+        const int ix = (int)(rest % (unsigned)p.W);
+        const int a = (int)(rest / (unsigned)p.W);
         const double *gt = p.gt + ((size_t)b * p.Gmax + g) * 4;
         AnchorPx an = anchor_px(p.stride, ix, jy, p.anchors.wh[a][0], p.anchors.wh[a][1]);
         double t[4];
@@ -330,7 +348,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     int rc = check_launch("rpn_targets_kernel");
     if (rc) return rc;
     if (Gmax > 0) {
-        rpn_targets_finalize_kernel<<<(B + 63) / 64, 64, 0, st>>>(p, B);
+        rpn_targets_finalize_kernel<<<B, 128, (size_t)Gmax * sizeof(unsigned), st>>>(p);
         rc = check_launch("rpn_targets_finalize_kernel");
     }
     return rc;

@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmarks on one B200 (CUDA events, warm-up, inputs > L2 or L2 flush).
+
+    python tools/bench_kernels.py [--out gpurun_out/kernels.json]
+
+Reports, against the measured HBM copy peak (MEASURED_PEAKS.json):
+  K1 decode_clip   GB/s on 64 and 512 panels          (algorithmic bytes 36*N)
+  K2 sort_nms      latency p50/p95 per panel, batch time for 64 panels, 90k-candidate stress
+  K3 rpn_targets   GB/s on 64 and 512 panels, 20 GT   (algorithmic bytes G*32 + 10*A*H*W*8)
+  a4 roi_targets   latency for 300 RoIs x 20 GT
+  K4 roi_pool      GB/s for 64 panels (38x38x1024, 300 RoIs, pool 14) and for VGG-like 512ch/pool 7
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from rock_art_radnet_b200 import synthetic as S  # noqa: E402
+from rock_art_radnet_b200.pipeline import ProposalPipeline  # noqa: E402
+from rock_art_radnet_b200.utils import rpn_targets_device  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    _flush.fill_(1)
+
+
+def time_ms(fn, iters=20, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return {"p50_ms": ts[len(ts) // 2], "min_ms": ts[0], "p95_ms": ts[max(0, int(len(ts) * 0.95) - 1)]}
+
+
+def tile_maps(B, H=38, W=38, A=9):
+    base = [S.rpn_maps(s, H, W, A) for s in range(8)]
+    cls = np.concatenate([base[i % 8][0] for i in range(B)])
+    regr = np.concatenate([base[i % 8][1] for i in range(B)])
+    return torch.from_numpy(cls).cuda(), torch.from_numpy(regr).cuda()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernels.json"))
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    pk = peak()
+    C = S.HotPathConfig()
+    res = {"hbm_peak_gbs": pk, "gpu": torch.cuda.get_device_name(0)}
+
+    # ---- K1 + K2 ----------------------------------------------------------------------
+    for B in (64, 512):
+        cls, regr = tile_maps(B)
+        pipe = ProposalPipeline(C, B, 38, 38, alloc_pooled=False)
+        t = time_ms(lambda: pipe.decode(cls, regr))
+        nbytes = 36 * pipe.N * B
+        res["decode_clip_B%d" % B] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
+                                           frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk)
+        t = time_ms(lambda: pipe.sort_nms())
+        res["sort_nms_B%d" % B] = dict(t, us_per_panel_amortised=1e3 * t["p50_ms"] / B)
+        del pipe
+    cls, regr = tile_maps(1)
+    pipe = ProposalPipeline(C, 1, 38, 38, alloc_pooled=False)
+    pipe.decode(cls, regr)
+    res["sort_nms_single_panel"] = time_ms(lambda: pipe.sort_nms(), iters=50, flush=False)
+    res["sort_nms_single_panel_cold_l2"] = time_ms(lambda: pipe.sort_nms(), iters=30, flush=True)
+    cls, regr = tile_maps(1, 100, 100)
+    pipe = ProposalPipeline(C, 1, 100, 100, alloc_pooled=False)
+    pipe.decode(cls, regr)
+    res["sort_nms_90k_candidates"] = time_ms(lambda: pipe.sort_nms(), iters=20, flush=False)
+    del pipe
+
+    # ---- K3 ----------------------------------------------------------------------------
+    G = 20
+    for B in (64, 512):
+        gt = np.zeros((B, G, 4)); bg = np.zeros((B, G), np.uint8)
+        for b in range(B):
+            img = S.gt_figures(b, G)
+            for k, bb in enumerate(img["bboxes"]):
+                gt[b, k] = [bb["x1"], bb["x2"], bb["y1"], bb["y2"]]
+        gt_d = torch.from_numpy(gt).cuda(); bg_d = torch.from_numpy(bg).cuda()
+        cnt_d = torch.full((B,), G, dtype=torch.int32, device="cuda")
+        wh_d = torch.tensor([[600.0, 600.0]] * B, dtype=torch.float64, device="cuda")
+        t = time_ms(lambda: rpn_targets_device(C, gt_d, bg_d, cnt_d, 38, 38, wh_d))
+        nbytes = B * (G * 32 + 10 * 9 * 38 * 38 * 8)
+        res["rpn_targets_B%d" % B] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
+                                          frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk,
+                                          note="includes the torch.empty allocations of the shim")
+
+    # ---- a4 ----------------------------------------------------------------------------
+    import rock_art_radnet_b200 as R
+    img = S.gt_figures(0, 20, classes=("boat", "human"))
+    cls1, regr1 = S.rpn_maps(0)
+    Rb = R.rpn_to_roi(cls1, regr1, C, max_boxes=300, overlap_thresh=0.7)
+    import time
+    R.calc_iou(Rb, img, C, C.class_mapping)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        R.calc_iou(Rb, img, C, C.class_mapping)
+    res["calc_iou_dropin_wall_ms"] = (time.perf_counter() - t0) / 20 * 1e3
+    t0 = time.perf_counter()
+    for _ in range(20):
+        R.rpn_to_roi(cls1, regr1, C, max_boxes=300, overlap_thresh=0.7)
+    res["rpn_to_roi_dropin_wall_ms"] = (time.perf_counter() - t0) / 20 * 1e3
+    np.random.seed(0)
+    R.calc_region_props(C, img, 600, 600, 600, 600, S.resnet50_map_size)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        R.calc_region_props(C, img, 600, 600, 600, 600, S.resnet50_map_size)
+    res["calc_region_props_dropin_wall_ms"] = (time.perf_counter() - t0) / 10 * 1e3
+
+    # ---- K4 ----------------------------------------------------------------------------
+    for (B, Cn, pool, tag) in ((64, 1024, 14, "resnet50"), (64, 512, 7, "vgg16")):
+        cls, regr = tile_maps(B)
+        feat = torch.randn((B, 38, 38, Cn), dtype=torch.float32, device="cuda")
+        pipe = ProposalPipeline(C, B, 38, 38, channels=Cn, pool_size=pool)
+        pipe.decode(cls, regr)
+        pipe.sort_nms()
+        kept = int(pipe.records.counts.sum().item())
+        t = time_ms(lambda: pipe.pool(feat), iters=10)
+        nbytes = B * 38 * 38 * Cn * 4 + kept * 16 + kept * pool * pool * Cn * 4
+        res["roi_pool_%s_B%d" % (tag, B)] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
+                                                  frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk)
+        del pipe, feat
+        torch.cuda.empty_cache()
+
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()

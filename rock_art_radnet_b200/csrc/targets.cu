@@ -79,21 +79,37 @@ __device__ __forceinline__ void regr_targets(const AnchorPx &a, double gx1, doub
     t[3] = log(__ddiv_rn(__dsub_rn(gy2, gy1), ha));
 }
 
+// Margin of the float32 IoU estimate used to skip work that cannot matter (see below).  The
+// estimate is off by < 3e-4 absolute for boxes up to a few thousand pixels; 2e-3 is generous.
+constexpr float kIouMargin = 2e-3f;
+
 __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double *s_gt = reinterpret_cast<double *>(smem);                                   // [G][4]
+    double *s_gt = reinterpret_cast<double *>(smem);                                   // [G][4] x1,x2,y1,y2
     unsigned long long *s_best = reinterpret_cast<unsigned long long *>(s_gt + 4 * p.Gmax);
-    int *s_hits = reinterpret_cast<int *>(s_best + p.Gmax);
-    uint8_t *s_bg = reinterpret_cast<uint8_t *>(s_hits + p.Gmax);
+    float4 *s_gt32 = reinterpret_cast<float4 *>(s_best + p.Gmax);                       // [G] x1,y1,x2,y2 rounded
+    float *s_area32 = reinterpret_cast<float *>(s_gt32 + p.Gmax);
+    int *s_hits = reinterpret_cast<int *>(s_area32 + p.Gmax);
+    uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_hits + p.Gmax);                     // bg or degenerate GT
 
     const int b = blockIdx.z, a = blockIdx.y;
     const int HW = p.H * p.W;
     const int G = p.gt_count[b];
-    for (int i = threadIdx.x; i < G * 4; i += kTgtThreads) s_gt[i] = p.gt[(size_t)b * p.Gmax * 4 + i];
     for (int i = threadIdx.x; i < G; i += kTgtThreads) {
-        s_best[i] = 0ull;
+        const double *q = p.gt + ((size_t)b * p.Gmax + i) * 4;
+        const double x1 = q[0], x2 = q[1], y1 = q[2], y2 = q[3];
+        s_gt[4 * i + 0] = x1; s_gt[4 * i + 1] = x2; s_gt[4 * i + 2] = y1; s_gt[4 * i + 3] = y2;
+        s_gt32[i] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
+        s_area32[i] = (float)((x2 - x1) * (y2 - y1));
+        // running maximum starts from what earlier CTAs already published (monotone, so a stale
+        // read only makes the filter below less effective, never wrong)
+        s_best[i] = p.best_key[(size_t)b * p.Gmax + i];
         s_hits[i] = 0;
-        s_bg[i] = p.gt_is_bg[(size_t)b * p.Gmax + i];
+        // 'bg' figures never produce labels (utils.py:690); degenerate ones have IoU 0 (utils.py:103)
+        uint8_t f = ((p.gt_is_bg[(size_t)b * p.Gmax + i] != 0) || (x1 >= x2) || (y1 >= y2)) ? 1 : 0;
+        // the float32 estimate is only trusted for pixel-scale coordinates
+        if (!(fabs(x1) <= 8192.0 && fabs(x2) <= 8192.0 && fabs(y1) <= 8192.0 && fabs(y2) <= 8192.0)) f |= 2;
+        s_skip[i] = f;
     }
     __syncthreads();
 
@@ -103,40 +119,60 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
     const double aw = p.anchors.wh[a][0], ah = p.anchors.wh[a][1];
     const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
     const double img_w = p.img_wh[2 * b], img_h = p.img_wh[2 * b + 1];
-    // anchors crossing the image are skipped entirely (utils.py:629,638)
+    // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
     const bool inside = in_map && !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h);
+    const bool usable = inside && an.x1 < an.x2 && an.y1 < an.y2;
     const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);     // size->ratio->ix->jy
     const int lane = threadIdx.x & 31;
+    const float ax1f = (float)an.x1, ay1f = (float)an.y1, ax2f = (float)an.x2, ay2f = (float)an.y2;
+    const float area_bf = (float)((an.x2 - an.x1) * (an.y2 - an.y1));
+    const float thr32 = (float)p.max_overlap;
+    const bool coords_small = img_w <= 8192.0 && img_h <= 8192.0 && aw <= 8192.0 && ah <= 8192.0;
 
     bool pos = false;
     double loc_best = 0.0;
     int loc_g = -1;
     // most anchors cross the image border (77 % for a 600-px panel): such warps only write zeros
-    const int G_loop = __any_sync(0xffffffffu, inside) ? G : 0;
+    const int G_loop = __any_sync(0xffffffffu, usable) ? G : 0;
     for (int g = 0; g < G_loop; ++g) {
-        double iou = 0.0;
-        if (inside)
-            iou = ref_iou(s_gt[4 * g + 0], s_gt[4 * g + 2], s_gt[4 * g + 1], s_gt[4 * g + 3], an.x1, an.y1,
-                          an.x2, an.y2);
-        const bool fg = !s_bg[g];
-        const float iou32 = (float)iou;
-        unsigned long long key = 0ull;
-        if (fg && iou32 > 0.f) key = ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order);
-        const bool hit = fg && iou > p.max_overlap;                   // utils.py:704
-        if (hit) {
-            pos = true;
-            if (iou > loc_best) { loc_best = iou; loc_g = g; }        // utils.py:710-713
+        const uint8_t gflag = s_skip[g];
+        if (gflag & 1) continue;                                      // block-uniform
+        const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
+        // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
+        const bool isect = usable && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
+        if (!__any_sync(0xffffffffu, isect)) continue;                // warp-uniform
+        // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
+        bool need = false;
+        if (isect) {
+            const float4 gf = s_gt32[g];
+            const float w = fminf(gf.z, ax2f) - fmaxf(gf.x, ax1f);
+            const float h = fminf(gf.w, ay2f) - fmaxf(gf.y, ay1f);
+            const float it = fmaxf(w, 0.f) * fmaxf(h, 0.f);
+            const float q = __fdividef(it, s_area32[g] + area_bf - it);
+            const float best_est = __uint_as_float(reinterpret_cast<volatile unsigned *>(&s_best[g])[1]);
+            need = (q + kIouMargin >= best_est) ||      // could be (or tie with) this GT's best anchor
+                   (q + kIouMargin >= thr32) ||         // could exceed rpn_max_overlap
+                   (gflag & 2) || !coords_small;        // estimate not trusted: always exact
         }
-        // warp-aggregate, then one shared atomic per warp
-        if (__any_sync(0xffffffffu, key != 0ull)) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
-                key = o > key ? o : key;
+        unsigned bits = 0;
+        bool hit = false;
+        if (need) {
+            const double iou = ref_iou(gx1, gy1, gx2, gy2, an.x1, an.y1, an.x2, an.y2);
+            const float iou32 = (float)iou;                           // float32 accumulator (utils.py:603)
+            if (iou32 > 0.f) bits = __float_as_uint(iou32);
+            hit = iou > p.max_overlap;                                // utils.py:704
+            if (hit) {
+                pos = true;
+                if (iou > loc_best) { loc_best = iou; loc_g = g; }    // utils.py:710-713
             }
-            if (lane == 0) atomicMax(&s_best[g], key);
         }
-        unsigned hm = __ballot_sync(0xffffffffu, hit);
+        // best anchor of this GT: max float32 IoU, then first in loop order.  Two REDUX ops.
+        const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+        if (wmax) {
+            const unsigned omin = __reduce_min_sync(0xffffffffu, bits == wmax ? order : 0xFFFFFFFFu);
+            if (lane == 0) atomicMax(&s_best[g], ((unsigned long long)wmax << 32) | (0xFFFFFFFFu - omin));
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
         if (hm && lane == 0) atomicAdd(&s_hits[g], __popc(hm));
     }
 
@@ -326,7 +362,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
         set_error("rpn_targets: workspace %zu < %zu", ws_bytes, need);
         return RADNET_E_WORKSPACE;
     }
-    size_t smem = (size_t)Gmax * (4 * 8 + 8 + 4 + 1) + 16;
+    size_t smem = (size_t)Gmax * (4 * 8 + 8 + 16 + 4 + 4 + 1) + 16;
     RADNET_CHECK_ARG(smem <= 200 * 1024, "rpn_targets: Gmax=%d too large for shared memory", Gmax);
     RpnTargetParams p{};
     p.gt = gt; p.gt_is_bg = gt_is_bg; p.gt_count = gt_count;

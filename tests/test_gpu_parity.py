@@ -228,6 +228,38 @@ def test_rpn_targets_batched_presample_vs_oracle(pkg):
         assert np.array_equal(hits[b, :g], nh)
 
 
+def test_rpn_targets_many_seeds_best_anchor_and_hits(pkg):
+    """Stresses the float32 pre-filter of the IoU kernel: tiny / huge / touching / duplicate figures."""
+    from rock_art_radnet_b200.utils import rpn_targets_device
+    C = S.HotPathConfig()
+    rng = np.random.default_rng(77)
+    imgs = []
+    for s in range(10):
+        lo, hi = [(8, 40), (48, 360), (200, 600), (16, 600)][s % 4]
+        img = S.gt_figures(300 + s, 14, 600, 600, classes=("boat", "human"), lo=lo, hi=min(hi, 600))
+        bbs = img["bboxes"]
+        bbs.append(dict(bbs[0]))                                       # exact duplicate figure
+        bbs.append({"class": "boat", "x1": 0, "x2": 600, "y1": 0, "y2": 600})   # whole image
+        bbs.append({"class": "boat", "x1": 64, "x2": 192, "y1": 64, "y2": 192})  # coincides with an anchor
+        bbs.append({"class": "boat", "x1": 300, "x2": 300, "y1": 10, "y2": 50})  # degenerate
+        imgs.append(img)
+    B, Gmax = len(imgs), max(len(i["bboxes"]) for i in imgs)
+    gt = np.zeros((B, Gmax, 4)); bg = np.zeros((B, Gmax), np.uint8); cnt = np.zeros(B, np.int32)
+    for b, img in enumerate(imgs):
+        for k, bb in enumerate(img["bboxes"]):
+            gt[b, k] = [bb["x1"], bb["x2"], bb["y1"], bb["y2"]]
+        cnt[b] = len(img["bboxes"])
+    wh = np.tile(np.array([[600.0, 600.0]]), (B, 1))
+    y_cls, y_regr, best, hits = (t.cpu().numpy() for t in rpn_targets_device(C, gt, bg, cnt, 38, 38, wh))
+    for b, img in enumerate(imgs):
+        valid, overlap, regr, ba, nh = O.rpn_targets_presample(C, img, 600, 600, 600, 600, S.resnet50_map_size)
+        g = len(img["bboxes"])
+        assert np.array_equal(best[b, :g], ba), b
+        assert np.array_equal(hits[b, :g], nh), b
+        assert np.array_equal(y_cls[b, :9], valid.transpose(2, 0, 1)) and np.array_equal(y_cls[b, 9:], overlap.transpose(2, 0, 1))
+        np.testing.assert_allclose(y_regr[b, 36:], regr.transpose(2, 0, 1), rtol=REGR_RTOL, atol=0)
+
+
 # ----------------------------------------------------------------------------- a4
 def test_calc_iou_matches_reference_golden(pkg, manifest, golden_a4):
     C = S.HotPathConfig()

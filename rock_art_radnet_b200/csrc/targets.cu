@@ -86,9 +86,9 @@ constexpr float kIouMargin = 2e-3f;
 __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     double *s_gt = reinterpret_cast<double *>(smem);                                   // [G][4] x1,x2,y1,y2
-    unsigned long long *s_best = reinterpret_cast<unsigned long long *>(s_gt + 4 * p.Gmax);
-    float4 *s_gt32 = reinterpret_cast<float4 *>(s_best + p.Gmax);                       // [G] x1,y1,x2,y2 rounded
-    float *s_area32 = reinterpret_cast<float *>(s_gt32 + p.Gmax);
+    float4 *s_gt32 = reinterpret_cast<float4 *>(s_gt + 4 * p.Gmax);                      // [G] x1,y1,x2,y2 rounded
+    unsigned long long *s_best = reinterpret_cast<unsigned long long *>(s_gt32 + p.Gmax);
+    float *s_area32 = reinterpret_cast<float *>(s_best + p.Gmax);
     int *s_hits = reinterpret_cast<int *>(s_area32 + p.Gmax);
     uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_hits + p.Gmax);                     // bg or degenerate GT
 

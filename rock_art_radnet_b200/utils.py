@@ -33,32 +33,54 @@ def iou(a, b):
     return float(inter) / float(union + 1e-6)
 
 
+class RpnTargetBatch:
+    """Pre-allocated batched RPN target assignment (K3) for B panels with up to Gmax figures each.
+
+    `run` launches `radnet_rpn_targets` on the current stream and returns the resident output
+    tensors (overwritten by the next call): y_rpn_cls (B,2A,H,W), y_rpn_regr (B,8A,H,W) float64,
+    best_anchor (B,Gmax,4) int32, n_hits (B,Gmax) int32 - BEFORE the RNG subsampling of
+    utils.py:777-813."""
+
+    def __init__(self, C, batch, Gmax, H, W, device=None):
+        D.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.C, self.B, self.Gmax, self.H, self.W = C, int(batch), int(Gmax), int(H), int(W)
+        self.A = len(C.anchor_box_scales) * len(C.anchor_box_ratios)
+        dev = self.device
+        self.y_cls = D.empty((self.B, 2 * self.A, self.H, self.W), np.float64, dev)
+        self.y_regr = D.empty((self.B, 8 * self.A, self.H, self.W), np.float64, dev)
+        self.best = D.empty((self.B, max(self.Gmax, 1), 4), np.int32, dev)
+        self.hits = D.zeros((self.B, max(self.Gmax, 1)), np.int32, dev)
+        self.ws_bytes = int(self.lib.radnet_rpn_targets_workspace_bytes(self.B, self.Gmax))
+        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
+        self._anchors = anchor_pixels(C)
+
+    def run(self, gt_boxes, gt_is_bg, gt_count, img_wh):
+        """gt_boxes (B,Gmax,4) float64 x1,x2,y1,y2 in resized pixels, gt_is_bg (B,Gmax) uint8,
+        gt_count (B,) int32, img_wh (B,2) float64 - CUDA tensors."""
+        C = self.C
+        _lib.call("radnet_rpn_targets", D.ptr(gt_boxes), D.ptr(gt_is_bg), D.ptr(gt_count), self.B, self.Gmax,
+                  self.H, self.W, self.A, len(C.anchor_box_ratios), D.ptr(self._anchors), float(C.rpn_stride),
+                  D.ptr(img_wh), float(C.rpn_max_overlap), D.ptr(self.y_cls), D.ptr(self.y_regr),
+                  D.ptr(self.best), D.ptr(self.hits), D.ptr(self.ws), self.ws_bytes, D.stream_ptr(self.device))
+        return self.y_cls, self.y_regr, self.best[:, :self.Gmax], self.hits[:, :self.Gmax]
+
+
 def rpn_targets_device(C, gt_boxes, gt_is_bg, gt_count, H, W, img_wh, device=None):
-    """Batched device call.  gt_boxes (B,Gmax,4) float64 x1,x2,y1,y2 in resized pixels,
-    gt_is_bg (B,Gmax) uint8, gt_count (B,) int32, img_wh (B,2) float64.
-    Returns CUDA tensors (y_rpn_cls (B,2A,H,W), y_rpn_regr (B,8A,H,W), best_anchor (B,Gmax,4),
-    n_hits (B,Gmax)) BEFORE the RNG subsampling of utils.py:777-813."""
+    """One-shot batched call (allocates its outputs).  gt_boxes (B,Gmax,4) float64 x1,x2,y1,y2 in
+    resized pixels, gt_is_bg (B,Gmax) uint8, gt_count (B,) int32, img_wh (B,2) float64; NumPy or
+    CUDA tensors.  Returns CUDA tensors as RpnTargetBatch.run."""
     D.require_cuda()
     dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-    lib = _lib.load()
     gt_count = D.to_device(gt_count, np.int32, dev)
     B = int(gt_count.shape[0])
     Gmax = int(gt_boxes.shape[1]) if gt_boxes is not None else 0
-    A = len(C.anchor_box_scales) * len(C.anchor_box_ratios)
+    batch = RpnTargetBatch(C, B, Gmax, H, W, device=dev)
     gt_dev = D.to_device(gt_boxes, np.float64, dev) if Gmax else None
     bg_dev = D.to_device(gt_is_bg, np.uint8, dev) if Gmax else None
     wh_dev = D.to_device(img_wh, np.float64, dev)
-    y_cls = D.empty((B, 2 * A, H, W), np.float64, dev)
-    y_regr = D.empty((B, 8 * A, H, W), np.float64, dev)
-    best = D.empty((B, max(Gmax, 1), 4), np.int32, dev)
-    hits = D.zeros((B, max(Gmax, 1)), np.int32, dev)
-    ws_bytes = int(lib.radnet_rpn_targets_workspace_bytes(B, Gmax))
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    _lib.call("radnet_rpn_targets", D.ptr(gt_dev), D.ptr(bg_dev), D.ptr(gt_count), B, Gmax, H, W, A,
-              len(C.anchor_box_ratios), D.ptr(anchor_pixels(C)), float(C.rpn_stride), D.ptr(wh_dev),
-              float(C.rpn_max_overlap), D.ptr(y_cls), D.ptr(y_regr), D.ptr(best), D.ptr(hits), D.ptr(ws),
-              ws_bytes, D.stream_ptr(dev))
-    return y_cls, y_regr, best[:, :Gmax], hits[:, :Gmax]
+    return batch.run(gt_dev, bg_dev, gt_count, wh_dev)
 
 
 def _subsample_regions(y_is_box_valid, y_rpn_overlap, max_n_regions=256):

@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 
 from rock_art_radnet_b200 import synthetic as S  # noqa: E402
 from rock_art_radnet_b200.pipeline import ProposalPipeline  # noqa: E402
-from rock_art_radnet_b200.utils import rpn_targets_device  # noqa: E402
+from rock_art_radnet_b200.utils import RpnTargetBatch  # noqa: E402
 
 
 def peak():
@@ -109,11 +109,13 @@ def main():
         gt_d = torch.from_numpy(gt).cuda(); bg_d = torch.from_numpy(bg).cuda()
         cnt_d = torch.full((B,), G, dtype=torch.int32, device="cuda")
         wh_d = torch.tensor([[600.0, 600.0]] * B, dtype=torch.float64, device="cuda")
-        t = time_ms(lambda: rpn_targets_device(C, gt_d, bg_d, cnt_d, 38, 38, wh_d))
+        tb = RpnTargetBatch(C, B, G, 38, 38)
+        t = time_ms(lambda: tb.run(gt_d, bg_d, cnt_d, wh_d))
         nbytes = B * (G * 32 + 10 * 9 * 38 * 38 * 8)
         res["rpn_targets_B%d" % B] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
                                           frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk,
-                                          note="includes the torch.empty allocations of the shim")
+                                          note="2 memsets + rpn_targets_kernel + finalize kernel, pre-allocated outputs")
+        del tb
 
     # ---- a4 ----------------------------------------------------------------------------
     import rock_art_radnet_b200 as R

@@ -89,30 +89,13 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
     float4 *s_gt32 = reinterpret_cast<float4 *>(s_gt + 4 * p.Gmax);                      // [G] x1,y1,x2,y2 rounded
     unsigned long long *s_best = reinterpret_cast<unsigned long long *>(s_gt32 + p.Gmax);
     float *s_area32 = reinterpret_cast<float *>(s_best + p.Gmax);
-    int *s_hits = reinterpret_cast<int *>(s_area32 + p.Gmax);
-    uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_hits + p.Gmax);                     // bg or degenerate GT
+    unsigned *s_floor = reinterpret_cast<unsigned *>(s_area32 + p.Gmax);                // [G] lower bound of the best IoU (f32 bits)
+    int *s_hits = reinterpret_cast<int *>(s_floor + p.Gmax);
+    uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_hits + p.Gmax);                     // bit0: bg/degenerate, bit1: no filter
 
     const int b = blockIdx.z, a = blockIdx.y;
     const int HW = p.H * p.W;
     const int G = p.gt_count[b];
-    for (int i = threadIdx.x; i < G; i += kTgtThreads) {
-        const double *q = p.gt + ((size_t)b * p.Gmax + i) * 4;
-        const double x1 = q[0], x2 = q[1], y1 = q[2], y2 = q[3];
-        s_gt[4 * i + 0] = x1; s_gt[4 * i + 1] = x2; s_gt[4 * i + 2] = y1; s_gt[4 * i + 3] = y2;
-        s_gt32[i] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
-        s_area32[i] = (float)((x2 - x1) * (y2 - y1));
-        // running maximum starts from what earlier CTAs already published (monotone, so a stale
-        // read only makes the filter below less effective, never wrong)
-        s_best[i] = p.best_key[(size_t)b * p.Gmax + i];
-        s_hits[i] = 0;
-        // 'bg' figures never produce labels (utils.py:690); degenerate ones have IoU 0 (utils.py:103)
-        uint8_t f = ((p.gt_is_bg[(size_t)b * p.Gmax + i] != 0) || (x1 >= x2) || (y1 >= y2)) ? 1 : 0;
-        // the float32 estimate is only trusted for pixel-scale coordinates
-        if (!(fabs(x1) <= 8192.0 && fabs(x2) <= 8192.0 && fabs(y1) <= 8192.0 && fabs(y2) <= 8192.0)) f |= 2;
-        s_skip[i] = f;
-    }
-    __syncthreads();
-
     const int cell = blockIdx.x * kTgtThreads + threadIdx.x;
     const bool in_map = cell < HW;
     const int jy = in_map ? cell / p.W : 0, ix = in_map ? cell - jy * p.W : 0;
@@ -122,17 +105,69 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
     // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
     const bool inside = in_map && !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h);
     const bool usable = inside && an.x1 < an.x2 && an.y1 < an.y2;
+    double *cls_b = p.y_cls + (size_t)b * 2 * p.A * HW;
+    double *regr_b = p.y_regr + (size_t)b * 8 * p.A * HW;
+
+    // Most anchors cross the image border (77 % for a 600-px panel).  A CTA without a single
+    // usable anchor, or a panel without figures, only writes its labels and leaves.
+    if (!__syncthreads_or(usable && G > 0)) {
+        if (in_map) {
+            cls_b[(size_t)a * HW + cell] = (inside && G > 0) ? 1.0 : 0.0;
+            cls_b[(size_t)(p.A + a) * HW + cell] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                regr_b[(size_t)(4 * a + k) * HW + cell] = 0.0;
+                regr_b[(size_t)(4 * p.A + 4 * a + k) * HW + cell] = 0.0;
+            }
+        }
+        return;
+    }
+
+    const bool coords_small = img_w <= 8192.0 && img_h <= 8192.0 && aw <= 8192.0 && ah <= 8192.0;
+    for (int i = threadIdx.x; i < G; i += kTgtThreads) {
+        const double *q = p.gt + ((size_t)b * p.Gmax + i) * 4;
+        const double x1 = q[0], x2 = q[1], y1 = q[2], y2 = q[3];
+        s_gt[4 * i + 0] = x1; s_gt[4 * i + 1] = x2; s_gt[4 * i + 2] = y1; s_gt[4 * i + 3] = y2;
+        s_gt32[i] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
+        s_area32[i] = (float)((x2 - x1) * (y2 - y1));
+        s_best[i] = 0ull;
+        s_hits[i] = 0;
+        s_floor[i] = 0u;
+        // 'bg' figures never produce labels (utils.py:690); degenerate ones have IoU 0 (utils.py:103)
+        uint8_t f = ((p.gt_is_bg[(size_t)b * p.Gmax + i] != 0) || (x1 >= x2) || (y1 >= y2)) ? 1 : 0;
+        // the float32 estimate is only trusted for pixel-scale coordinates
+        if (!coords_small || !(fabs(x1) <= 8192.0 && fabs(x2) <= 8192.0 && fabs(y1) <= 8192.0 && fabs(y2) <= 8192.0)) f |= 2;
+        s_skip[i] = f;
+    }
+    __syncthreads();
+    // A LOWER bound of every figure's best float32 IoU, from the exact IoU with the A anchors of
+    // the cell under the figure's centre (all anchor shapes, not only this CTA's).  Pairs whose
+    // float32 estimate is below it by more than the margin cannot be (or tie with) the best anchor.
+    for (int i = threadIdx.x; i < G * p.A; i += kTgtThreads) {
+        const int g = i / p.A, a2 = i - g * p.A;
+        if (s_skip[g] & 1) continue;
+        const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
+        int cx = (int)floor((gx1 + gx2) * 0.5 / p.stride), cy = (int)floor((gy1 + gy2) * 0.5 / p.stride);
+        cx = min(max(cx, 0), p.W - 1);
+        cy = min(max(cy, 0), p.H - 1);
+        const AnchorPx c = anchor_px(p.stride, cx, cy, p.anchors.wh[a2][0], p.anchors.wh[a2][1]);
+        const bool ok = !(c.x1 < 0.0 || c.x2 > img_w) && !(c.y1 < 0.0 || c.y2 > img_h);
+        if (ok) {
+            const float v = (float)ref_iou(gx1, gy1, gx2, gy2, c.x1, c.y1, c.x2, c.y2);
+            if (v > 0.f) atomicMax(&s_floor[g], __float_as_uint(v));
+        }
+    }
+    __syncthreads();
+
     const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);     // size->ratio->ix->jy
     const int lane = threadIdx.x & 31;
     const float ax1f = (float)an.x1, ay1f = (float)an.y1, ax2f = (float)an.x2, ay2f = (float)an.y2;
     const float area_bf = (float)((an.x2 - an.x1) * (an.y2 - an.y1));
     const float thr32 = (float)p.max_overlap;
-    const bool coords_small = img_w <= 8192.0 && img_h <= 8192.0 && aw <= 8192.0 && ah <= 8192.0;
 
     bool pos = false;
     double loc_best = 0.0;
     int loc_g = -1;
-    // most anchors cross the image border (77 % for a 600-px panel): such warps only write zeros
     const int G_loop = __any_sync(0xffffffffu, usable) ? G : 0;
     for (int g = 0; g < G_loop; ++g) {
         const uint8_t gflag = s_skip[g];
@@ -140,7 +175,6 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
         const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
         // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
         const bool isect = usable && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
-        if (!__any_sync(0xffffffffu, isect)) continue;                // warp-uniform
         // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
         bool need = false;
         if (isect) {
@@ -149,11 +183,11 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
             const float h = fminf(gf.w, ay2f) - fmaxf(gf.y, ay1f);
             const float it = fmaxf(w, 0.f) * fmaxf(h, 0.f);
             const float q = __fdividef(it, s_area32[g] + area_bf - it);
-            const float best_est = __uint_as_float(reinterpret_cast<volatile unsigned *>(&s_best[g])[1]);
-            need = (q + kIouMargin >= best_est) ||      // could be (or tie with) this GT's best anchor
-                   (q + kIouMargin >= thr32) ||         // could exceed rpn_max_overlap
-                   (gflag & 2) || !coords_small;        // estimate not trusted: always exact
+            const float lim = fminf(__uint_as_float(s_floor[g]), thr32);
+            need = (q + kIouMargin >= lim) ||           // could be the best anchor, or exceed rpn_max_overlap
+                   (gflag & 2);                         // estimate not trusted: always exact
         }
+        if (!__any_sync(0xffffffffu, need)) continue;                 // warp-uniform
         unsigned bits = 0;
         bool hit = false;
         if (need) {
@@ -182,8 +216,6 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
         const double ov = pos ? 1.0 : 0.0;
         double t[4] = {0.0, 0.0, 0.0, 0.0};
         if (pos) regr_targets(an, s_gt[4 * loc_g + 0], s_gt[4 * loc_g + 1], s_gt[4 * loc_g + 2], s_gt[4 * loc_g + 3], t);
-        double *cls_b = p.y_cls + (size_t)b * 2 * p.A * HW;
-        double *regr_b = p.y_regr + (size_t)b * 8 * p.A * HW;
         cls_b[(size_t)a * HW + cell] = valid;
         cls_b[(size_t)(p.A + a) * HW + cell] = ov;
 #pragma unroll
@@ -362,7 +394,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
         set_error("rpn_targets: workspace %zu < %zu", ws_bytes, need);
         return RADNET_E_WORKSPACE;
     }
-    size_t smem = (size_t)Gmax * (4 * 8 + 8 + 16 + 4 + 4 + 1) + 16;
+    size_t smem = (size_t)Gmax * (4 * 8 + 16 + 8 + 4 + 4 + 4 + 1) + 16;
     RADNET_CHECK_ARG(smem <= 200 * 1024, "rpn_targets: Gmax=%d too large for shared memory", Gmax);
     RpnTargetParams p{};
     p.gt = gt; p.gt_is_bg = gt_is_bg; p.gt_count = gt_count;

@@ -83,7 +83,9 @@ __device__ __forceinline__ void regr_targets(const AnchorPx &a, double gx1, doub
 // estimate is off by < 3e-4 absolute for boxes up to a few thousand pixels; 2e-3 is generous.
 constexpr float kIouMargin = 2e-3f;
 
-__global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParams p) {
+// One CTA per (panel, anchor shape): the figures and their filters are set up once and the CTA
+// then walks the H*W cells of its anchor plane in chunks of kTgtThreads.
+__global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     double *s_gt = reinterpret_cast<double *>(smem);                                   // [G][4] x1,x2,y1,y2
     float4 *s_gt32 = reinterpret_cast<float4 *>(s_gt + 4 * p.Gmax);                      // [G] x1,y1,x2,y2 rounded
@@ -93,35 +95,14 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
     int *s_hits = reinterpret_cast<int *>(s_floor + p.Gmax);
     uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_hits + p.Gmax);                     // bit0: bg/degenerate, bit1: no filter
 
-    const int b = blockIdx.z, a = blockIdx.y;
+    const int b = blockIdx.y, a = blockIdx.x;
     const int HW = p.H * p.W;
     const int G = p.gt_count[b];
-    const int cell = blockIdx.x * kTgtThreads + threadIdx.x;
-    const bool in_map = cell < HW;
-    const int jy = in_map ? cell / p.W : 0, ix = in_map ? cell - jy * p.W : 0;
     const double aw = p.anchors.wh[a][0], ah = p.anchors.wh[a][1];
-    const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
     const double img_w = p.img_wh[2 * b], img_h = p.img_wh[2 * b + 1];
-    // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
-    const bool inside = in_map && !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h);
-    const bool usable = inside && an.x1 < an.x2 && an.y1 < an.y2;
     double *cls_b = p.y_cls + (size_t)b * 2 * p.A * HW;
     double *regr_b = p.y_regr + (size_t)b * 8 * p.A * HW;
-
-    // Most anchors cross the image border (77 % for a 600-px panel).  A CTA without a single
-    // usable anchor, or a panel without figures, only writes its labels and leaves.
-    if (!__syncthreads_or(usable && G > 0)) {
-        if (in_map) {
-            cls_b[(size_t)a * HW + cell] = (inside && G > 0) ? 1.0 : 0.0;
-            cls_b[(size_t)(p.A + a) * HW + cell] = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                regr_b[(size_t)(4 * a + k) * HW + cell] = 0.0;
-                regr_b[(size_t)(4 * p.A + 4 * a + k) * HW + cell] = 0.0;
-            }
-        }
-        return;
-    }
+    const int lane = threadIdx.x & 31;
 
     const bool coords_small = img_w <= 8192.0 && img_h <= 8192.0 && aw <= 8192.0 && ah <= 8192.0;
     for (int i = threadIdx.x; i < G; i += kTgtThreads) {
@@ -159,69 +140,77 @@ __global__ void __launch_bounds__(kTgtThreads) rpn_targets_kernel(RpnTargetParam
     }
     __syncthreads();
 
-    const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);     // size->ratio->ix->jy
-    const int lane = threadIdx.x & 31;
-    const float ax1f = (float)an.x1, ay1f = (float)an.y1, ax2f = (float)an.x2, ay2f = (float)an.y2;
-    const float area_bf = (float)((an.x2 - an.x1) * (an.y2 - an.y1));
     const float thr32 = (float)p.max_overlap;
-
-    bool pos = false;
-    double loc_best = 0.0;
-    int loc_g = -1;
-    const int G_loop = __any_sync(0xffffffffu, usable) ? G : 0;
-    for (int g = 0; g < G_loop; ++g) {
-        const uint8_t gflag = s_skip[g];
-        if (gflag & 1) continue;                                      // block-uniform
-        const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
-        // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
-        const bool isect = usable && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
-        // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
-        bool need = false;
-        if (isect) {
-            const float4 gf = s_gt32[g];
-            const float w = fminf(gf.z, ax2f) - fmaxf(gf.x, ax1f);
-            const float h = fminf(gf.w, ay2f) - fmaxf(gf.y, ay1f);
-            const float it = fmaxf(w, 0.f) * fmaxf(h, 0.f);
-            const float q = __fdividef(it, s_area32[g] + area_bf - it);
-            const float lim = fminf(__uint_as_float(s_floor[g]), thr32);
-            need = (q + kIouMargin >= lim) ||           // could be the best anchor, or exceed rpn_max_overlap
-                   (gflag & 2);                         // estimate not trusted: always exact
-        }
-        if (!__any_sync(0xffffffffu, need)) continue;                 // warp-uniform
-        unsigned bits = 0;
-        bool hit = false;
-        if (need) {
-            const double iou = ref_iou(gx1, gy1, gx2, gy2, an.x1, an.y1, an.x2, an.y2);
-            const float iou32 = (float)iou;                           // float32 accumulator (utils.py:603)
-            if (iou32 > 0.f) bits = __float_as_uint(iou32);
-            hit = iou > p.max_overlap;                                // utils.py:704
-            if (hit) {
-                pos = true;
-                if (iou > loc_best) { loc_best = iou; loc_g = g; }    // utils.py:710-713
+#pragma unroll 1
+    for (int cell = threadIdx.x; cell < ((HW + 31) & ~31); cell += kTgtThreads) {
+        const bool in_map = cell < HW;
+        const int jy = in_map ? cell / p.W : 0, ix = in_map ? cell - jy * p.W : 0;
+        const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
+        // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
+        const bool inside = in_map && !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h);
+        const bool usable = inside && an.x1 < an.x2 && an.y1 < an.y2;
+        const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);     // size->ratio->ix->jy
+        bool pos = false;
+        double loc_best = 0.0;
+        int loc_g = -1;
+        // most anchors cross the image border (77 % for a 600-px panel): such warps only write zeros
+        if (__any_sync(0xffffffffu, usable)) {
+            const float ax1f = (float)an.x1, ay1f = (float)an.y1, ax2f = (float)an.x2, ay2f = (float)an.y2;
+            const float area_bf = (float)((an.x2 - an.x1) * (an.y2 - an.y1));
+            for (int g = 0; g < G; ++g) {
+                const uint8_t gflag = s_skip[g];
+                if (gflag & 1) continue;                                      // block-uniform
+                const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
+                // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
+                const bool isect = usable && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
+                // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
+                bool need = false;
+                if (isect) {
+                    const float4 gf = s_gt32[g];
+                    const float w = fminf(gf.z, ax2f) - fmaxf(gf.x, ax1f);
+                    const float h = fminf(gf.w, ay2f) - fmaxf(gf.y, ay1f);
+                    const float it = fmaxf(w, 0.f) * fmaxf(h, 0.f);
+                    const float q = __fdividef(it, s_area32[g] + area_bf - it);
+                    const float lim = fminf(__uint_as_float(s_floor[g]), thr32);
+                    need = (q + kIouMargin >= lim) ||       // could be the best anchor, or exceed rpn_max_overlap
+                           (gflag & 2);                     // estimate not trusted: always exact
+                }
+                if (!__any_sync(0xffffffffu, need)) continue;                 // warp-uniform
+                unsigned bits = 0;
+                bool hit = false;
+                if (need) {
+                    const double iou = ref_iou(gx1, gy1, gx2, gy2, an.x1, an.y1, an.x2, an.y2);
+                    const float iou32 = (float)iou;                           // float32 accumulator (utils.py:603)
+                    if (iou32 > 0.f) bits = __float_as_uint(iou32);
+                    hit = iou > p.max_overlap;                                // utils.py:704
+                    if (hit) {
+                        pos = true;
+                        if (iou > loc_best) { loc_best = iou; loc_g = g; }    // utils.py:710-713
+                    }
+                }
+                // best anchor of this GT: max float32 IoU, then first in loop order.  Two REDUX ops.
+                const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+                if (wmax) {
+                    const unsigned omin = __reduce_min_sync(0xffffffffu, bits == wmax ? order : 0xFFFFFFFFu);
+                    if (lane == 0) atomicMax(&s_best[g], ((unsigned long long)wmax << 32) | (0xFFFFFFFFu - omin));
+                }
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hm && lane == 0) atomicAdd(&s_hits[g], __popc(hm));
             }
         }
-        // best anchor of this GT: max float32 IoU, then first in loop order.  Two REDUX ops.
-        const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
-        if (wmax) {
-            const unsigned omin = __reduce_min_sync(0xffffffffu, bits == wmax ? order : 0xFFFFFFFFu);
-            if (lane == 0) atomicMax(&s_best[g], ((unsigned long long)wmax << 32) | (0xFFFFFFFFu - omin));
-        }
-        const unsigned hm = __ballot_sync(0xffffffffu, hit);
-        if (hm && lane == 0) atomicAdd(&s_hits[g], __popc(hm));
-    }
-
-    if (in_map) {
-        // labels are written inside the GT loop of the reference: no GT, no labels (utils.py:722-738)
-        const double valid = (inside && G > 0) ? 1.0 : 0.0;
-        const double ov = pos ? 1.0 : 0.0;
-        double t[4] = {0.0, 0.0, 0.0, 0.0};
-        if (pos) regr_targets(an, s_gt[4 * loc_g + 0], s_gt[4 * loc_g + 1], s_gt[4 * loc_g + 2], s_gt[4 * loc_g + 3], t);
-        cls_b[(size_t)a * HW + cell] = valid;
-        cls_b[(size_t)(p.A + a) * HW + cell] = ov;
+        if (in_map) {
+            // labels are written inside the GT loop of the reference: no GT, no labels (utils.py:722-738)
+            const double valid = (inside && G > 0) ? 1.0 : 0.0;
+            const double ov = pos ? 1.0 : 0.0;
+            double t[4] = {0.0, 0.0, 0.0, 0.0};
+            if (pos) regr_targets(an, s_gt[4 * loc_g + 0], s_gt[4 * loc_g + 1], s_gt[4 * loc_g + 2], s_gt[4 * loc_g + 3], t);
+            cls_b[(size_t)a * HW + cell] = valid;
+            cls_b[(size_t)(p.A + a) * HW + cell] = ov;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            regr_b[(size_t)(4 * a + k) * HW + cell] = ov;                       // np.repeat(overlap,4)
-            regr_b[(size_t)(4 * p.A + 4 * a + k) * HW + cell] = t[k];
+            for (int k = 0; k < 4; ++k) {
+                regr_b[(size_t)(4 * a + k) * HW + cell] = ov;                       // np.repeat(overlap,4)
+                regr_b[(size_t)(4 * p.A + 4 * a + k) * HW + cell] = t[k];
+            }
         }
     }
     __syncthreads();
@@ -411,7 +400,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     if (Gmax > 0) RADNET_CUDA(cudaMemsetAsync(n_hits, 0, sizeof(int32_t) * (size_t)B * Gmax, st));
     if (smem > 48 * 1024)
         RADNET_CUDA(cudaFuncSetAttribute(rpn_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((H * W + kTgtThreads - 1) / kTgtThreads, A, B);
+    dim3 grid(A, B);
     rpn_targets_kernel<<<grid, kTgtThreads, smem, st>>>(p);
     int rc = check_launch("rpn_targets_kernel");
     if (rc) return rc;

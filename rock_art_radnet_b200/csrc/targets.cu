@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     extern __shared__ __align__(16) unsigned char smem[];
     double *s_gt = reinterpret_cast<double *>(smem);                                   // [G][4] x1,x2,y1,y2
     float4 *s_gt32 = reinterpret_cast<float4 *>(s_gt + 4 * p.Gmax);                      // [G] x1,y1,x2,y2 rounded
-    unsigned long long *s_best = reinterpret_cast<unsigned long long *>(s_gt32 + p.Gmax);
+    int4 *s_range = reinterpret_cast<int4 *>(s_gt32 + p.Gmax);                          // [G] ix_lo, ix_hi, jy_lo, jy_hi
+    unsigned long long *s_best = reinterpret_cast<unsigned long long *>(s_range + p.Gmax);
     float *s_area32 = reinterpret_cast<float *>(s_best + p.Gmax);
     unsigned *s_floor = reinterpret_cast<unsigned *>(s_area32 + p.Gmax);                // [G] lower bound of the best IoU (f32 bits)
     int *s_hits = reinterpret_cast<int *>(s_floor + p.Gmax);
@@ -141,6 +142,32 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     __syncthreads();
 
     const float thr32 = (float)p.max_overlap;
+    // Cell window of this anchor shape that can matter for each figure.  IoU >= L needs, on each
+    // axis, an overlap of at least L*max(figure side, anchor side) (because union >= the larger
+    // area and the other overlap <= the smaller side); with L = min(floor, thr) - margin this is
+    // a handful of cells around the figure, and empty when the shapes cannot reach L at all.
+    // One cell of padding on every side absorbs the rounding of this float64 arithmetic.
+    for (int g = threadIdx.x; g < G; g += kTgtThreads) {
+        int4 r = make_int4(0, -1, 0, -1);                                    // empty
+        const uint8_t f = s_skip[g];
+        if (!(f & 1)) {
+            const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
+            double L = (double)fminf(__uint_as_float(s_floor[g]), thr32) - 2.0 * (double)kIouMargin;
+            if ((f & 2) || !(L > 0.0)) L = 0.0;
+            const double mx = L * fmax(gx2 - gx1, aw), my = L * fmax(gy2 - gy1, ah);
+            // centre c = stride*(i+0.5) must satisfy  g1 + m - side/2 <= c <= g2 - m + side/2
+            const double xl = (gx1 + mx - aw * 0.5) / p.stride - 0.5, xh = (gx2 - mx + aw * 0.5) / p.stride - 0.5;
+            const double yl = (gy1 + my - ah * 0.5) / p.stride - 0.5, yh = (gy2 - my + ah * 0.5) / p.stride - 0.5;
+            if (xl <= xh + 2.0 && yl <= yh + 2.0) {
+                r.x = (int)fmax(floor(xl) - 1.0, -1.0);
+                r.y = (int)fmin(ceil(xh) + 1.0, (double)p.W);
+                r.z = (int)fmax(floor(yl) - 1.0, -1.0);
+                r.w = (int)fmin(ceil(yh) + 1.0, (double)p.H);
+            }
+        }
+        s_range[g] = r;
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int cell = threadIdx.x; cell < ((HW + 31) & ~31); cell += kTgtThreads) {
         const bool in_map = cell < HW;
@@ -158,11 +185,13 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
             const float ax1f = (float)an.x1, ay1f = (float)an.y1, ax2f = (float)an.x2, ay2f = (float)an.y2;
             const float area_bf = (float)((an.x2 - an.x1) * (an.y2 - an.y1));
             for (int g = 0; g < G; ++g) {
+                const int4 rg = s_range[g];
+                const bool cand = usable && ix >= rg.x && ix <= rg.y && jy >= rg.z && jy <= rg.w;
+                if (!__any_sync(0xffffffffu, cand)) continue;                 // warp-uniform (also bg / degenerate)
                 const uint8_t gflag = s_skip[g];
-                if (gflag & 1) continue;                                      // block-uniform
                 const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
                 // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
-                const bool isect = usable && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
+                const bool isect = cand && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
                 // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
                 bool need = false;
                 if (isect) {
@@ -383,7 +412,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
         set_error("rpn_targets: workspace %zu < %zu", ws_bytes, need);
         return RADNET_E_WORKSPACE;
     }
-    size_t smem = (size_t)Gmax * (4 * 8 + 16 + 8 + 4 + 4 + 4 + 1) + 16;
+    size_t smem = (size_t)Gmax * (4 * 8 + 16 + 16 + 8 + 4 + 4 + 4 + 1) + 16;
     RADNET_CHECK_ARG(smem <= 200 * 1024, "rpn_targets: Gmax=%d too large for shared memory", Gmax);
     RpnTargetParams p{};
     p.gt = gt; p.gt_is_bg = gt_is_bg; p.gt_count = gt_count;

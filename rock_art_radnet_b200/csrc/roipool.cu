@@ -42,9 +42,21 @@ struct RoiPoolParams {
     int roi_chunk;           // RoIs whose y tables fit in shared memory at once
 };
 
-struct YEntry {              // 8 bytes, one LDS.64
-    unsigned short r0, r1;   // pixel index of the first cell of source rows y+y0 / y+y1
+// Per (RoI, output row) entry of the y table, 8 bytes = one LDS.64.
+//   bits  0..15  pixel index of the first cell of source row y+y0  ((y+y0)*W)
+//   bit   16     1 when y1 = y0+1 (else y1 = y0)
+//   bits 28..30  what the row cache has to do relative to the previous output row (kAct*)
+struct YEntry {
+    unsigned code;
     float lerp;
+};
+enum : unsigned {
+    kActKeep = 0,      // same two source rows as the previous output row
+    kActShift = 1,     // y0 = previous y1, new y1: h0 <- h1, sample h1
+    kActShiftDup = 2,  // y0 = y1 = previous y1: h0 <- h1
+    kActBoth = 3,      // sample both rows
+    kActOneDup = 4,    // y0 = y1, new row: sample h0, h1 <- h0
+    kActExtend = 5     // y0 kept, previous rows were equal, new y1: sample h1
 };
 
 // RoI k of panel b as (x,y,w,h), already int32-truncated by the caller (RoiPoolingConv.py:69-72);
@@ -158,14 +170,22 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
             int x, y, cw, ch;
             YEntry en;
             if (fetch_roi(p, b, r0 + rl, x, y, cw, ch)) {
-                int lo, hi;
+                int lo, hi, plo = -1, phi = -1;
+                float pl;
                 legacy_axis(i, ch, pool, lo, hi, en.lerp);
-                en.r0 = (unsigned short)((y + lo) * p.W);
-                en.r1 = (unsigned short)((y + hi) * p.W);
+                if (i > 0) legacy_axis(i - 1, ch, pool, plo, phi, pl);
+                unsigned act;
+                if (i == 0) act = (hi == lo) ? kActOneDup : kActBoth;
+                else if (lo == plo && hi == phi) act = kActKeep;
+                else if (lo == phi && hi != lo && phi != plo) act = kActShift;
+                else if (lo == phi && hi == lo && phi != plo) act = kActShiftDup;
+                else if (lo == plo && phi == plo && hi != lo) act = kActExtend;
+                else act = (hi == lo) ? kActOneDup : kActBoth;
+                en.code = (unsigned)((y + lo) * p.W) | ((hi != lo) ? 0x10000u : 0u) | (act << 28);
                 if (i == 0) s_roi[rl] = make_int2(x, cw);
             } else {
                 // rows add nothing and the column points at the zero pixel: output is exactly 0
-                en.r0 = en.r1 = 0;
+                en.code = (i == 0) ? (kActOneDup << 28) : (kActKeep << 28);
                 en.lerp = 0.f;
                 if (i == 0) s_roi[rl] = make_int2(0, 0);
             }
@@ -191,29 +211,23 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
             const YEntry *yt = s_ytab + rl * pool;
             float4 *dst = reinterpret_cast<float4 *>(p.out) +
                           (((size_t)b * p.R + r0 + rl) * PP + px) * C4 + (size_t)s * LANES + q;
-            int cur0 = -1, cur1 = -1;
+            const int row_step = p.W * kPixBytes;
             float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
 #pragma unroll 2
             for (int py = 0; py < pool; ++py) {
                 const YEntry e = yt[py];
-                const int ra = e.r0, rb = e.r1;
-                float4 n0, n1;
-                if (ra == cur0) n0 = h0;
-                else if (ra == cur1) n0 = h1;
-                else {
-                    const unsigned char *row = mapb + ra * kPixBytes;
-                    n0 = lerp4(*reinterpret_cast<const float4 *>(row + xo0),
-                               *reinterpret_cast<const float4 *>(row + xo1), lx);
+                const unsigned act = e.code >> 28;
+                if (act != kActKeep) {
+                    const unsigned char *row = mapb + (e.code & 0xFFFFu) * kPixBytes;
+                    if (act == kActShift || act == kActShiftDup) h0 = h1;
+                    if (act == kActBoth || act == kActOneDup)
+                        h0 = lerp4(*reinterpret_cast<const float4 *>(row + xo0),
+                                   *reinterpret_cast<const float4 *>(row + xo1), lx);
+                    if (act == kActOneDup) h1 = h0;
+                    if (act == kActShift || act == kActBoth || act == kActExtend)
+                        h1 = lerp4(*reinterpret_cast<const float4 *>(row + row_step + xo0),
+                                   *reinterpret_cast<const float4 *>(row + row_step + xo1), lx);
                 }
-                if (rb == ra) n1 = n0;
-                else if (rb == cur1) n1 = h1;
-                else if (rb == cur0) n1 = h0;
-                else {
-                    const unsigned char *row = mapb + rb * kPixBytes;
-                    n1 = lerp4(*reinterpret_cast<const float4 *>(row + xo0),
-                               *reinterpret_cast<const float4 *>(row + xo1), lx);
-                }
-                h0 = n0; h1 = n1; cur0 = ra; cur1 = rb;
                 st_stream_f4(dst, lerp4(h0, h1, e.lerp));
                 dst += py_step;
             }

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "_C", "libradnet_b200.so")
+LIB_PATH = os.environ.get("RADNET_B200_LIB", os.path.join(_PKG_DIR, "_C", "libradnet_b200.so"))
 
 c_int = ctypes.c_int
 c_size_t = ctypes.c_size_t

@@ -42,7 +42,7 @@ constexpr int kTile = kNmsThreads;              // candidates per NMS tile
 constexpr int kMaxTableEntries = 65535;
 constexpr int kKeptSmemMax = 1024;              // kept boxes held in shared memory
 constexpr int kLookAhead = 6;                   // rows that may run ahead of the retiring row
-constexpr int kSmemHeader = 2048;               // barriers, misc words, scan scratch, row counts
+constexpr int kSmemHeader = 3072;               // barriers, misc words, scan scratch, row counts, 256-bin histogram
 
 // ----------------------------------------------------------------------------------
 // candidate representations
@@ -262,27 +262,16 @@ __device__ __forceinline__ void atomic_max_key(uint64_t *a, uint64_t v) {
     atomicMax(reinterpret_cast<unsigned long long *>(a), (unsigned long long)v);
 }
 
-// count of keys >= t over the block; `slot` rotates over three shared counters so that one
-// barrier per call is enough
+// SELECT: a threshold t (>= 1) with count(key >= t) >= target and only a small bucket of extra
+// keys.  256-ary search on the key VALUE range: per-warp 256-bin histograms of (key - lo) >> shift
+// (shared-memory RED, no returns), column sums, a suffix scan by warp 0 from the top bin; the
+// bucket that straddles the target rank becomes the new [lo, hi].  One or two rounds in practice
+// (13k keys over 256 bins leave ~50 keys in the boundary bucket).
+// M = number of valid (non-zero) keys, S = count(key >= t).
 template <typename KeyT>
-__device__ __forceinline__ int count_ge(const KeyT *keys, int N, KeyT t, int *s_cnt3, int &slot) {
-    int c = 0;
-    for (int i = threadIdx.x; i < N; i += kNmsThreads) c += (keys[i] >= t) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt3[slot], c);
-    const int nxt = slot == 2 ? 0 : slot + 1;
-    if (threadIdx.x == 0) s_cnt3[nxt] = 0;      // last read two barriers ago
-    __syncthreads();
-    const int r = s_cnt3[slot];
-    slot = nxt;
-    return r;
-}
-
-// SELECT: largest threshold t (>= 1) with count(key >= t) >= target, stopped early once the count
-// is within 12.5 % of the target.  M = number of valid (non-zero) keys, S = count(key >= t).
-template <typename KeyT>
-__device__ KeyT select_threshold(const KeyT *keys, int N, int target, int *s_cnt3, KeyT *s_minmax, int &M,
-                                 int &S) {
+__device__ KeyT select_threshold(const KeyT *keys, int N, int target, uint32_t *s_cnt, uint32_t *s_hist,
+                                 int *s_sel, KeyT *s_minmax, int &M, int &S) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     // valid count, min and max key
     {
         int c = 0;
@@ -303,35 +292,82 @@ __device__ KeyT select_threshold(const KeyT *keys, int N, int target, int *s_cnt
         }
         c = __reduce_add_sync(0xffffffffu, c);
         if (threadIdx.x == 0) {
-            s_cnt3[0] = 0; s_cnt3[1] = 0; s_cnt3[2] = 0;
+            s_sel[0] = 0;
             s_minmax[0] = KeyInfo<KeyT>::max;
             s_minmax[1] = 0;
         }
         __syncthreads();
-        if ((threadIdx.x & 31) == 0 && c) {
-            atomicAdd(&s_cnt3[0], c);
+        if (lane == 0 && c) {
+            atomicAdd(&s_sel[0], c);
             atomic_min_key(&s_minmax[0], mn);
             atomic_max_key(&s_minmax[1], mx);
         }
         __syncthreads();
     }
-    M = s_cnt3[0];
+    M = s_sel[0];
     KeyT lo = s_minmax[0], hi = s_minmax[1];
-    __syncthreads();
-    if (threadIdx.x == 0) { s_cnt3[0] = 0; s_cnt3[1] = 0; s_cnt3[2] = 0; }
-    __syncthreads();
     S = M;
     if (M <= target) return (KeyT)1;
-    int slot = 0;
-    // invariant: count(>= lo) = S >= target ; count(>= hi) < target (checked first for hi = max key)
-    const int c_hi = count_ge<KeyT>(keys, N, hi, s_cnt3, slot);
-    if (c_hi >= target) { S = c_hi; return hi; }
-    const int slack = target + (target >> 3);
-    while (hi - lo > 1 && S > slack) {
-        const KeyT mid = lo + (hi - lo) / 2;
-        const int c = count_ge<KeyT>(keys, N, mid, s_cnt3, slot);
-        if (c >= target) { lo = mid; S = c; } else hi = mid;
+    int above = 0, need = target, inb = M;
+    const int slack = max(target >> 3, 1);
+#pragma unroll 1
+    for (int it = 0; it < (int)sizeof(KeyT) + 1; ++it) {
+        const KeyT range = hi - lo;
+        if (range == 0) break;                                   // a single key value: all ties
+        const int bits = (sizeof(KeyT) == 8) ? 64 - __clzll((long long)range) : 32 - __clz((int)range);
+        const int shift = bits > 8 ? bits - 8 : 0;
+        __syncthreads();                                         // previous round done with s_cnt / s_sel
+        for (int i = threadIdx.x; i < kNmsWarps * kCntStride; i += kNmsThreads) s_cnt[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += kNmsThreads) {
+            const KeyT k = keys[i];
+            if (k >= lo && k <= hi) atomicAdd(&s_cnt[w * kCntStride + (int)((k - lo) >> shift)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            uint32_t t = 0;
+            for (int ww = 0; ww < kNmsWarps; ++ww) t += s_cnt[ww * kCntStride + threadIdx.x];
+            s_hist[threadIdx.x] = t;
+        }
+        __syncthreads();
+        if (w == 0) {
+            // lane l owns bins 255-8l .. 248-8l, so lane order = descending key order
+            uint32_t loc[8];
+            int sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                loc[j] = s_hist[255 - 8 * lane - j];
+                sum += (int)loc[j];
+            }
+            int inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += n;
+            }
+            int abv = inc - sum;                                 // keys in the bins of lower lanes (larger keys)
+            if (abv < need && need <= inc) {                     // exactly one lane (need <= keys in range)
+                int b = 255 - 8 * lane, cnt = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (abv + (int)loc[j] >= need) { b = 255 - 8 * lane - j; cnt = (int)loc[j]; break; }
+                    abv += (int)loc[j];
+                }
+                s_sel[1] = b; s_sel[2] = abv; s_sel[3] = cnt;
+            }
+        }
+        __syncthreads();
+        const int b = s_sel[1];
+        above += s_sel[2];
+        need -= s_sel[2];
+        inb = s_sel[3];
+        const KeyT nlo = lo + ((KeyT)b << shift);
+        const KeyT span = (((KeyT)1) << shift) - 1;
+        hi = (hi - nlo > span) ? nlo + span : hi;
+        lo = nlo;
+        if (shift == 0 || inb <= slack) break;
     }
+    S = above + inb;
     return lo;
 }
 
@@ -378,10 +414,33 @@ __device__ int compact_ge(const KeyT *keys, int N, KeyT t, KeyT *out_k, IdxT *ou
     return total;
 }
 
+// Is candidate `cand` suppressed by any of kept[from, to)?  The kept boxes are fetched in
+// batches of kBatch before any of them is tested, so the dependent LDS -> ALU -> LDS(table)
+// chains of a batch overlap; the last batch re-reads the final entry instead of running a
+// one-by-one remainder loop (testing the same box twice is harmless).
+template <typename Traits, bool kKeptSmem, int kBatch>
+__device__ __forceinline__ bool suppressed_by(const typename Traits::Cand *kept, int from, int to,
+                                              const typename Traits::Cand &cand,
+                                              const typename Traits::Ctx &ctx) {
+    bool hit = false;
+    for (int j = from; j < to; j += kBatch) {
+        typename Traits::Cand kb[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int jj = min(j + u, to - 1);
+            kb[u] = kKeptSmem ? Traits::load_shared(kept + jj) : kept[jj];
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) hit |= Traits::suppress(kb[u], cand, ctx);
+    }
+    return hit;
+}
+
 template <typename Traits, typename KeyT, typename IdxT, bool kSmemSort, bool kKeptSmem>
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams p) {
     using Cand = typename Traits::Cand;
     constexpr bool kI32 = sizeof(Cand) == sizeof(int4);
+    constexpr int kTestBatch = kI32 ? 8 : 2;      // kept boxes fetched per batch (register budget)
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);                 // TMA barrier
@@ -394,7 +453,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     volatile int *s_kcount = s_misc + 0;
     int *s_flag = s_misc + 2;
     int *s_ties = s_misc + 3;
-    int *s_cnt3 = s_misc + 4;                                             // 3 ints
+    int *s_sel = s_misc + 4;                                              // 4 ints
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + 2048);         // [256]
     volatile int *s_fault = s_misc + 8;
 
     const int seg = blockIdx.x;
@@ -419,6 +479,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         iB = reinterpret_cast<IdxT *>(ws + p.ws_off_iB);
     }
 
+#ifdef RADNET_NMS_PROFILE
+    long long *prof = reinterpret_cast<long long *>(ws + p.ws_off_kept + 32768);
+    int prof_n = 0;
+#define NMS_STAMP() do { __syncthreads(); if (threadIdx.x == 0 && prof_n < 16) prof[prof_n] = clock64(); ++prof_n; } while (0)
+#define NMS_ROW_STAMP(k) do { if (lane == 0 && tile_no == 0) prof[16 + w * 8 + (k)] = clock64(); } while (0)
+#else
+#define NMS_STAMP() do {} while (0)
+#define NMS_ROW_STAMP(k) do {} while (0)
+#endif
+    NMS_STAMP();
     if (threadIdx.x == 0) {
         *s_kcount = 0;
         *s_ties = 0;
@@ -462,6 +532,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     }
     if (tma_pending) mbar_wait(s_bar, 0);
     __syncthreads();
+    NMS_STAMP();     // 1: keys staged + table built
 
     // kept list
     Cand *kept;
@@ -484,8 +555,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         // ---- stage 1: select + compact ---------------------------------------------------
         KeyT thr_key = (KeyT)1;
         if (round == 0) {
-            thr_key = select_threshold<KeyT>(raw_k, N, p.sel_target, s_cnt3, s_minmax, M, S);
+            thr_key = select_threshold<KeyT>(raw_k, N, p.sel_target, s_cnt, s_hist, s_sel, s_minmax, M, S);
             K = min(p.max_boxes, M);
+            NMS_STAMP();     // 2: threshold selected
         } else if (kSmemSort) {
             // the ping-pong buffers overwrote the staged keys: fetch them again
             for (int i = threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
@@ -496,6 +568,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         IdxT *ci = kSmemSort ? iB : iA;
         S = compact_ge<KeyT, IdxT>(raw_k, N, thr_key, ck, ci, s_scan);
         if (round == 1) M = S;
+        NMS_STAMP();         // 3: compacted
 
         // ---- stage 2: stable LSD radix sort of the slice -----------------------------------
         const KeyT *in_k = ck;
@@ -516,6 +589,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             }
         }
         // in_k / in_i: S entries ascending by (score, flat index)
+        NMS_STAMP();         // 4: sorted
 
         // ---- score ties among the sorted candidates (reported) -----------
         {
@@ -546,12 +620,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             s_tile[threadIdx.x] = cand;
             __syncwarp();
 
+            NMS_ROW_STAMP(0);    // candidate gathered
             // (a) against boxes kept by earlier tiles
             bool alive = active;
-            for (int j = 0; j < k0; ++j) {
-                const Cand kb = kKeptSmem ? Traits::load_shared(kept + j) : kept[j];
-                if (Traits::suppress(kb, cand, ctx)) alive = false;
-            }
+            if (suppressed_by<Traits, kKeptSmem, kTestBatch>(kept, 0, k0, cand, ctx)) alive = false;
             // (b) intra-row matrix: which lower lanes of my row overlap me.  Each unordered pair is
             //     evaluated once: in step t lane l tests lane (l-t) mod 32 and the ballot hands the
             //     result to whichever of the two has the higher rank index.
@@ -575,16 +647,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             //     it stops looking.
             int seen = k0;
             int kc = k0;
+            NMS_ROW_STAMP(1);    // intra-row matrix done
             for (int pw = max(0, w - kLookAhead); pw < w; ++pw) {
+                if (pw == w - 1) NMS_ROW_STAMP(2);    // about to wait for the immediate predecessor
                 if (!mbar_wait_bounded(&s_turn[pw], parity)) { *s_fault = 1; break; }
                 kc = s_kafter[pw];            // published by exactly the row just acquired
                 if (kc >= K) break;
-                for (int j = seen; j < kc; ++j) {
-                    const Cand kb = kKeptSmem ? Traits::load_shared(kept + j) : kept[j];
-                    if (Traits::suppress(kb, cand, ctx)) alive = false;
-                }
+                if (suppressed_by<Traits, kKeptSmem, kTestBatch>(kept, seen, kc, cand, ctx)) alive = false;
                 seen = kc;
             }
+            NMS_ROW_STAMP(3);    // my turn: all earlier keeps tested
             if (kc < K) {
                 uint32_t und = __ballot_sync(0xffffffffu, alive);
                 uint32_t keep = 0;
@@ -611,10 +683,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                 if (kc > *s_kcount) *s_kcount = kc;       // rows retire in order, so this only grows
                 mbar_arrive(&s_turn[w]);                  // release: keeps + counts visible to waiters
             }
+            NMS_ROW_STAMP(4);    // retired
             __syncthreads();
             k0 = *s_kcount;
             __syncthreads();
         }
+        NMS_STAMP();         // 5: NMS tiles done
         done = S;
         if (k0 >= K || S >= M) break;
     }
@@ -646,6 +720,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                 ri[j] = 0;
             }
         }
+        NMS_STAMP();         // 6: record written
     } else {
         if (threadIdx.x == 0) {
             p.count[0] = *s_fault ? -1 : kept_n;
@@ -708,7 +783,7 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     p.ws_off_kB = w; w += align_up(cap * sizeof(KeyT), 256);
     p.ws_off_iA = w; w += align_up(cap * 4, 256);
     p.ws_off_iB = w; w += align_up(cap * 4, 256);
-    p.ws_off_kept = w; w += align_up((size_t)K * sizeof(Cand) + 64, 256);
+    p.ws_off_kept = w; w += align_up((size_t)K * sizeof(Cand) + 64, 256) + 32768 + 256;   // + optional profile stamps
     pl.ws_stride = w;
     p.ws_stride = w;
     return pl;

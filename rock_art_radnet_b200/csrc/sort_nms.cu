@@ -578,7 +578,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         if (S > 1) {
 #pragma unroll 1
             for (int pass = 0; pass < KeyInfo<KeyT>::passes; ++pass) {
-                if (radix_pass<KeyT, IdxT>(in_k, in_i, out_k, out_i, S, pass * 8, s_cnt, s_scan, s_flag)) {
+                const bool moved = radix_pass<KeyT, IdxT>(in_k, in_i, out_k, out_i, S, pass * 8, s_cnt, s_scan, s_flag);
+#ifdef RADNET_NMS_PROFILE
+                if (threadIdx.x == 0 && round == 0) prof[8 + pass] = clock64() * 2 + (moved ? 1 : 0);
+#endif
+                if (moved) {
                     const KeyT *nk = out_k;
                     const IdxT *ni = out_i;
                     out_k = const_cast<KeyT *>(in_k);

@@ -38,6 +38,7 @@ struct RpnTargetParams {
     int32_t *best_anchor;      // [B][Gmax][4]
     int32_t *n_hits;           // [B][Gmax]
     unsigned long long *best_key;  // [B][Gmax] workspace
+    int sm_off_cells;          // shared-memory offset of the per-cell state
 };
 
 // reference utils.py:77-109 with a = GT (x1,y1,x2,y2), b = anchor
@@ -159,87 +160,102 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
             const double xl = (gx1 + mx - aw * 0.5) / p.stride - 0.5, xh = (gx2 - mx + aw * 0.5) / p.stride - 0.5;
             const double yl = (gy1 + my - ah * 0.5) / p.stride - 0.5, yh = (gy2 - my + ah * 0.5) / p.stride - 0.5;
             if (xl <= xh + 2.0 && yl <= yh + 2.0) {
-                r.x = (int)fmax(floor(xl) - 1.0, -1.0);
-                r.y = (int)fmin(ceil(xh) + 1.0, (double)p.W);
-                r.z = (int)fmax(floor(yl) - 1.0, -1.0);
-                r.w = (int)fmin(ceil(yh) + 1.0, (double)p.H);
+                r.x = (int)fmax(floor(xl) - 1.0, 0.0);
+                r.y = (int)fmin(ceil(xh) + 1.0, (double)(p.W - 1));
+                r.z = (int)fmax(floor(yl) - 1.0, 0.0);
+                r.w = (int)fmin(ceil(yh) + 1.0, (double)(p.H - 1));
             }
         }
         s_range[g] = r;
     }
+    // per-cell state of this anchor plane: best IoU above rpn_max_overlap and the figure it came from
+    double *s_lb = reinterpret_cast<double *>(smem + p.sm_off_cells);                    // [HW]
+    short *s_lg = reinterpret_cast<short *>(s_lb + HW);                                  // [HW]
+    for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) {
+        s_lb[cell] = 0.0;
+        s_lg[cell] = -1;
+    }
     __syncthreads();
+
+    // Figures are visited in order (so "first figure wins ties", utils.py:710-713, holds); the CTA
+    // enumerates only the cells of the figure's window, densely over its threads.
 #pragma unroll 1
-    for (int cell = threadIdx.x; cell < ((HW + 31) & ~31); cell += kTgtThreads) {
-        const bool in_map = cell < HW;
-        const int jy = in_map ? cell / p.W : 0, ix = in_map ? cell - jy * p.W : 0;
-        const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
-        // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
-        const bool inside = in_map && !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h);
-        const bool usable = inside && an.x1 < an.x2 && an.y1 < an.y2;
-        const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);     // size->ratio->ix->jy
-        bool pos = false;
-        double loc_best = 0.0;
-        int loc_g = -1;
-        // most anchors cross the image border (77 % for a 600-px panel): such warps only write zeros
-        if (__any_sync(0xffffffffu, usable)) {
-            const float ax1f = (float)an.x1, ay1f = (float)an.y1, ax2f = (float)an.x2, ay2f = (float)an.y2;
-            const float area_bf = (float)((an.x2 - an.x1) * (an.y2 - an.y1));
-            for (int g = 0; g < G; ++g) {
-                const int4 rg = s_range[g];
-                const bool cand = usable && ix >= rg.x && ix <= rg.y && jy >= rg.z && jy <= rg.w;
-                if (!__any_sync(0xffffffffu, cand)) continue;                 // warp-uniform (also bg / degenerate)
-                const uint8_t gflag = s_skip[g];
-                const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
-                // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
-                const bool isect = cand && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
-                // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
-                bool need = false;
-                if (isect) {
-                    const float4 gf = s_gt32[g];
-                    const float w = fminf(gf.z, ax2f) - fmaxf(gf.x, ax1f);
-                    const float h = fminf(gf.w, ay2f) - fmaxf(gf.y, ay1f);
-                    const float it = fmaxf(w, 0.f) * fmaxf(h, 0.f);
-                    const float q = __fdividef(it, s_area32[g] + area_bf - it);
-                    const float lim = fminf(__uint_as_float(s_floor[g]), thr32);
-                    need = (q + kIouMargin >= lim) ||       // could be the best anchor, or exceed rpn_max_overlap
-                           (gflag & 2);                     // estimate not trusted: always exact
-                }
-                if (!__any_sync(0xffffffffu, need)) continue;                 // warp-uniform
-                unsigned bits = 0;
-                bool hit = false;
-                if (need) {
-                    const double iou = ref_iou(gx1, gy1, gx2, gy2, an.x1, an.y1, an.x2, an.y2);
-                    const float iou32 = (float)iou;                           // float32 accumulator (utils.py:603)
-                    if (iou32 > 0.f) bits = __float_as_uint(iou32);
-                    hit = iou > p.max_overlap;                                // utils.py:704
-                    if (hit) {
-                        pos = true;
-                        if (iou > loc_best) { loc_best = iou; loc_g = g; }    // utils.py:710-713
-                    }
-                }
-                // best anchor of this GT: max float32 IoU, then first in loop order.  Two REDUX ops.
-                const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
-                if (wmax) {
-                    const unsigned omin = __reduce_min_sync(0xffffffffu, bits == wmax ? order : 0xFFFFFFFFu);
-                    if (lane == 0) atomicMax(&s_best[g], ((unsigned long long)wmax << 32) | (0xFFFFFFFFu - omin));
-                }
-                const unsigned hm = __ballot_sync(0xffffffffu, hit);
-                if (hm && lane == 0) atomicAdd(&s_hits[g], __popc(hm));
+    for (int g = 0; g < G; ++g) {
+        const int4 rg = s_range[g];
+        if (rg.x > rg.y || rg.z > rg.w) continue;                             // block-uniform (also bg / degenerate)
+        const int ww = rg.y - rg.x + 1, n = ww * (rg.w - rg.z + 1);
+        const uint8_t gflag = s_skip[g];
+        const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
+        const float4 gf = s_gt32[g];
+        const float lim = fminf(__uint_as_float(s_floor[g]), thr32);
+#pragma unroll 1
+        for (int t0 = 0; t0 < n; t0 += kTgtThreads) {
+            const int t = t0 + threadIdx.x;
+            const bool act = t < n;
+            const int dy = act ? t / ww : 0;
+            const int ix = rg.x + (act ? t - dy * ww : 0), jy = rg.z + dy;
+            const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
+            // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
+            const bool usable = act && !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h) &&
+                                an.x1 < an.x2 && an.y1 < an.y2;
+            // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
+            const bool isect = usable && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
+            // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
+            bool need = false;
+            if (isect) {
+                const float ax1f = (float)an.x1, ay1f = (float)an.y1, ax2f = (float)an.x2, ay2f = (float)an.y2;
+                const float area_bf = (float)((an.x2 - an.x1) * (an.y2 - an.y1));
+                const float w = fminf(gf.z, ax2f) - fmaxf(gf.x, ax1f);
+                const float h = fminf(gf.w, ay2f) - fmaxf(gf.y, ay1f);
+                const float it = fmaxf(w, 0.f) * fmaxf(h, 0.f);
+                const float q = __fdividef(it, s_area32[g] + area_bf - it);
+                need = (q + kIouMargin >= lim) ||           // could be the best anchor, or exceed rpn_max_overlap
+                       (gflag & 2);                         // estimate not trusted: always exact
             }
+            if (!__any_sync(0xffffffffu, need)) continue;                     // warp-uniform
+            unsigned bits = 0;
+            bool hit = false;
+            if (need) {
+                const double iou = ref_iou(gx1, gy1, gx2, gy2, an.x1, an.y1, an.x2, an.y2);
+                const float iou32 = (float)iou;                               // float32 accumulator (utils.py:603)
+                if (iou32 > 0.f) bits = __float_as_uint(iou32);
+                hit = iou > p.max_overlap;                                    // utils.py:704
+                if (hit) {
+                    const int cell = jy * p.W + ix;                           // one thread per cell and figure
+                    if (iou > s_lb[cell]) { s_lb[cell] = iou; s_lg[cell] = (short)g; }   // utils.py:710-713
+                }
+            }
+            // best anchor of this GT: max float32 IoU, then first in loop order.  Two REDUX ops.
+            const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);     // size->ratio->ix->jy
+            const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+            if (wmax) {
+                const unsigned omin = __reduce_min_sync(0xffffffffu, bits == wmax ? order : 0xFFFFFFFFu);
+                if (lane == 0) atomicMax(&s_best[g], ((unsigned long long)wmax << 32) | (0xFFFFFFFFu - omin));
+            }
+            const unsigned hm = __ballot_sync(0xffffffffu, hit);
+            if (hm && lane == 0) atomicAdd(&s_hits[g], __popc(hm));
         }
-        if (in_map) {
-            // labels are written inside the GT loop of the reference: no GT, no labels (utils.py:722-738)
-            const double valid = (inside && G > 0) ? 1.0 : 0.0;
-            const double ov = pos ? 1.0 : 0.0;
-            double t[4] = {0.0, 0.0, 0.0, 0.0};
-            if (pos) regr_targets(an, s_gt[4 * loc_g + 0], s_gt[4 * loc_g + 1], s_gt[4 * loc_g + 2], s_gt[4 * loc_g + 3], t);
-            cls_b[(size_t)a * HW + cell] = valid;
-            cls_b[(size_t)(p.A + a) * HW + cell] = ov;
+        __syncthreads();      // the next figure maps other threads onto these cells
+    }
+
+    // write-out: every cell of the anchor plane, 10 float64 planes, coalesced along ix
+#pragma unroll 1
+    for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) {
+        const int jy = cell / p.W, ix = cell - jy * p.W;
+        const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
+        const bool inside = !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h);
+        // labels are written inside the GT loop of the reference: no GT, no labels (utils.py:722-738)
+        const double valid = (inside && G > 0) ? 1.0 : 0.0;
+        const int lg = s_lg[cell];
+        const double ov = lg >= 0 ? 1.0 : 0.0;
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        if (lg >= 0) regr_targets(an, s_gt[4 * lg + 0], s_gt[4 * lg + 1], s_gt[4 * lg + 2], s_gt[4 * lg + 3], t);
+        cls_b[(size_t)a * HW + cell] = valid;
+        cls_b[(size_t)(p.A + a) * HW + cell] = ov;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                regr_b[(size_t)(4 * a + k) * HW + cell] = ov;                       // np.repeat(overlap,4)
-                regr_b[(size_t)(4 * p.A + 4 * a + k) * HW + cell] = t[k];
-            }
+        for (int k = 0; k < 4; ++k) {
+            regr_b[(size_t)(4 * a + k) * HW + cell] = ov;                       // np.repeat(overlap,4)
+            regr_b[(size_t)(4 * p.A + 4 * a + k) * HW + cell] = t[k];
         }
     }
     __syncthreads();
@@ -412,8 +428,17 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
         set_error("rpn_targets: workspace %zu < %zu", ws_bytes, need);
         return RADNET_E_WORKSPACE;
     }
-    size_t smem = (size_t)Gmax * (4 * 8 + 16 + 16 + 8 + 4 + 4 + 4 + 1) + 16;
-    RADNET_CHECK_ARG(smem <= 200 * 1024, "rpn_targets: Gmax=%d too large for shared memory", Gmax);
+    size_t gt_bytes = align_up((size_t)Gmax * (4 * 8 + 16 + 16 + 8 + 4 + 4 + 4 + 1) + 16, 16);
+    size_t smem = gt_bytes + (size_t)H * W * (sizeof(double) + sizeof(short)) + 16;
+    int dev = 0, smem_limit = 0;
+    RADNET_CUDA(cudaGetDevice(&dev));
+    RADNET_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)smem_limit) {
+        set_error("rpn_targets: %d figures on a %dx%d map need %zu B of shared memory (limit %d)", Gmax, H, W, smem,
+                  smem_limit);
+        return RADNET_E_UNSUPPORTED;
+    }
+    RADNET_CHECK_ARG(Gmax < 32768, "rpn_targets: Gmax=%d too large", Gmax);
     RpnTargetParams p{};
     p.gt = gt; p.gt_is_bg = gt_is_bg; p.gt_count = gt_count;
     p.Gmax = Gmax; p.H = H; p.W = W; p.A = A; p.n_ratios = n_ratios;
@@ -424,6 +449,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     p.stride = rpn_stride; p.img_wh = img_wh; p.max_overlap = max_overlap;
     p.y_cls = y_rpn_cls; p.y_regr = y_rpn_regr; p.best_anchor = best_anchor; p.n_hits = n_hits;
     p.best_key = reinterpret_cast<unsigned long long *>(ws);
+    p.sm_off_cells = (int)gt_bytes;
     cudaStream_t st = (cudaStream_t)stream;
     RADNET_CUDA(cudaMemsetAsync(ws, 0, need, st));
     if (Gmax > 0) RADNET_CUDA(cudaMemsetAsync(n_hits, 0, sizeof(int32_t) * (size_t)B * Gmax, st));

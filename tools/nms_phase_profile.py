@@ -39,5 +39,7 @@ for seed in range(3):
             r = rows[w] - t0
             print("  row %2d gathered=%6d matrix=%6d wait_pred=%6d turn=%6d retired=%6d  (turn->retired %5d, prev retired->my turn %5d)" % (
                 w, r[0], r[1], r[2], r[3], r[4], r[4] - r[3], (r[3] - (rows[w - 1, 4] - t0)) if w else 0))
+    ps = ws[off + 8 * 8:off + 16 * 8].view(np.int64)
+    print("   sort passes (cycles since compact, moved):", [(int(v // 2 - st[3]), int(v % 2)) for v in ps[:4]])
     print("seed", seed, " ".join("%s=%d" % (n, v) for n, v in zip(names[1:], d)), "total cycles", st[6] - st[0],
           "n_sorted", pipe.records.to_numpy()[0]["n_sorted"])

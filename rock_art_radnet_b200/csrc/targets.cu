@@ -170,10 +170,26 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     }
     // per-cell state of this anchor plane: best IoU above rpn_max_overlap and the figure it came from
     double *s_lb = reinterpret_cast<double *>(smem + p.sm_off_cells);                    // [HW]
-    short *s_lg = reinterpret_cast<short *>(s_lb + HW);                                  // [HW]
+    double2 *s_ax = reinterpret_cast<double2 *>(s_lb + ((HW + 1) & ~1));                 // [W] anchor x1,x2 of column ix
+    double2 *s_ay = s_ax + p.W;                                                          // [H] anchor y1,y2 of row jy
+    float4 *s_axf = reinterpret_cast<float4 *>(s_ay + p.H);                              // [W] x1,x2,width (f32), in-image flag
+    float4 *s_ayf = s_axf + p.W;                                                         // [H]
+    short *s_lg = reinterpret_cast<short *>(s_ayf + p.H);                                // [HW]
     for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) {
         s_lb[cell] = 0.0;
         s_lg[cell] = -1;
+    }
+    // anchor coordinates per column / row (utils.py:625-626, 635-636) and the per-axis in-image tests
+    // (utils.py:629, 638); an anchor is used when both its column and its row pass
+    for (int i = threadIdx.x; i < p.W + p.H; i += kTgtThreads) {
+        const bool isx = i < p.W;
+        const int k = isx ? i : i - p.W;
+        const double side = isx ? aw : ah, lim_px = isx ? img_w : img_h;
+        const double c = __dmul_rn(p.stride, (double)k + 0.5);
+        const double v1 = __dsub_rn(c, __dmul_rn(side, 0.5)), v2 = __dadd_rn(c, __dmul_rn(side, 0.5));
+        const bool ok = !(v1 < 0.0 || v2 > lim_px) && v1 < v2;
+        (isx ? s_ax : s_ay)[k] = make_double2(v1, v2);
+        (isx ? s_axf : s_ayf)[k] = make_float4((float)v1, (float)v2, (float)(v2 - v1), ok ? 1.f : 0.f);
     }
     __syncthreads();
 
@@ -190,25 +206,26 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
         const float lim = fminf(__uint_as_float(s_floor[g]), thr32);
 #pragma unroll 1
         for (int t0 = 0; t0 < n; t0 += kTgtThreads) {
+            if (t0 + (int)(threadIdx.x & ~31u) >= n) continue;                // this warp has no cell of the window
             const int t = t0 + threadIdx.x;
             const bool act = t < n;
             const int dy = act ? t / ww : 0;
             const int ix = rg.x + (act ? t - dy * ww : 0), jy = rg.z + dy;
-            const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
+            const double2 X = s_ax[ix], Y = s_ay[jy];
+            const float4 XF = s_axf[ix], YF = s_ayf[jy];
+            AnchorPx an;
+            an.x1 = X.x; an.x2 = X.y; an.y1 = Y.x; an.y2 = Y.y;
             // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
-            const bool usable = act && !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h) &&
-                                an.x1 < an.x2 && an.y1 < an.y2;
+            const bool usable = act && XF.w != 0.f && YF.w != 0.f;
             // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
             const bool isect = usable && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
             // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
             bool need = false;
             if (isect) {
-                const float ax1f = (float)an.x1, ay1f = (float)an.y1, ax2f = (float)an.x2, ay2f = (float)an.y2;
-                const float area_bf = (float)((an.x2 - an.x1) * (an.y2 - an.y1));
-                const float w = fminf(gf.z, ax2f) - fmaxf(gf.x, ax1f);
-                const float h = fminf(gf.w, ay2f) - fmaxf(gf.y, ay1f);
+                const float w = fminf(gf.z, XF.y) - fmaxf(gf.x, XF.x);
+                const float h = fminf(gf.w, YF.y) - fmaxf(gf.y, YF.x);
                 const float it = fmaxf(w, 0.f) * fmaxf(h, 0.f);
-                const float q = __fdividef(it, s_area32[g] + area_bf - it);
+                const float q = __fdividef(it, s_area32[g] + XF.z * YF.z - it);
                 need = (q + kIouMargin >= lim) ||           // could be the best anchor, or exceed rpn_max_overlap
                        (gflag & 2);                         // estimate not trusted: always exact
             }
@@ -242,14 +259,19 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
 #pragma unroll 1
     for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) {
         const int jy = cell / p.W, ix = cell - jy * p.W;
-        const AnchorPx an = anchor_px(p.stride, ix, jy, aw, ah);
-        const bool inside = !(an.x1 < 0.0 || an.x2 > img_w) && !(an.y1 < 0.0 || an.y2 > img_h);
+        // `inside` is the per-axis test only; a degenerate anchor (side <= 0) never occurs in-image
+        const bool inside = s_axf[ix].w != 0.f && s_ayf[jy].w != 0.f;
         // labels are written inside the GT loop of the reference: no GT, no labels (utils.py:722-738)
         const double valid = (inside && G > 0) ? 1.0 : 0.0;
         const int lg = s_lg[cell];
         const double ov = lg >= 0 ? 1.0 : 0.0;
         double t[4] = {0.0, 0.0, 0.0, 0.0};
-        if (lg >= 0) regr_targets(an, s_gt[4 * lg + 0], s_gt[4 * lg + 1], s_gt[4 * lg + 2], s_gt[4 * lg + 3], t);
+        if (lg >= 0) {
+            AnchorPx an;
+            const double2 X = s_ax[ix], Y = s_ay[jy];
+            an.x1 = X.x; an.x2 = X.y; an.y1 = Y.x; an.y2 = Y.y;
+            regr_targets(an, s_gt[4 * lg + 0], s_gt[4 * lg + 1], s_gt[4 * lg + 2], s_gt[4 * lg + 3], t);
+        }
         cls_b[(size_t)a * HW + cell] = valid;
         cls_b[(size_t)(p.A + a) * HW + cell] = ov;
 #pragma unroll
@@ -429,7 +451,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
         return RADNET_E_WORKSPACE;
     }
     size_t gt_bytes = align_up((size_t)Gmax * (4 * 8 + 16 + 16 + 8 + 4 + 4 + 4 + 1) + 16, 16);
-    size_t smem = gt_bytes + (size_t)H * W * (sizeof(double) + sizeof(short)) + 16;
+    size_t smem = gt_bytes + (size_t)H * W * (sizeof(double) + sizeof(short)) + (size_t)(H + W) * 32 + 32;
     int dev = 0, smem_limit = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
     RADNET_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

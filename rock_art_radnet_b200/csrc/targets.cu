@@ -18,6 +18,8 @@
 //     serial loop over the GT inside the thread.
 //   * forced positives (utils.py:741-766) are applied by a second tiny kernel in GT order,
 //     with the float32-rounded targets (utils.py:605,766).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace radnet {
@@ -39,6 +41,13 @@ struct RpnTargetParams {
     int32_t *n_hits;           // [B][Gmax]
     unsigned long long *best_key;  // [B][Gmax] workspace
     int sm_off_cells;          // shared-memory offset of the per-cell state
+    int hit_cap;               // capacity of the positive-cell list
+};
+
+struct TargetHit {
+    double iou;
+    int cell;
+    int g;
 };
 
 // reference utils.py:77-109 with a = GT (x1,y1,x2,y2), b = anchor
@@ -174,7 +183,11 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     double2 *s_ay = s_ax + p.W;                                                          // [H] anchor y1,y2 of row jy
     float4 *s_axf = reinterpret_cast<float4 *>(s_ay + p.H);                              // [W] x1,x2,width (f32), in-image flag
     float4 *s_ayf = s_axf + p.W;                                                         // [H]
-    short *s_lg = reinterpret_cast<short *>(s_ayf + p.H);                                // [HW]
+    TargetHit *s_hit = reinterpret_cast<TargetHit *>(s_ayf + p.H);                       // [hit_cap]
+    const int hit_cap = p.hit_cap;
+    int *s_nhit = reinterpret_cast<int *>(s_hit + hit_cap);                              // 4 ints
+    short *s_lg = reinterpret_cast<short *>(s_nhit + 4);                                 // [HW]
+    if (threadIdx.x == 0) *s_nhit = 0;
     for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) {
         s_lb[cell] = 0.0;
         s_lg[cell] = -1;
@@ -193,38 +206,42 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     }
     __syncthreads();
 
-    // Figures are visited in order (so "first figure wins ties", utils.py:710-713, holds); the CTA
-    // enumerates only the cells of the figure's window, densely over its threads.
+    // Phase 1 - one WARP per figure (8 figures in flight per CTA; a CTA-wide pass per figure was
+    // latency-bound on the float64 divide and the block barrier).  The warp enumerates the cells
+    // of the figure's window 32 at a time.  Cells whose IoU exceeds rpn_max_overlap go to a hit
+    // list; which figure wins a cell is settled in phase 2, so the figure order of the reference
+    // ("first figure wins ties", utils.py:710-713) does not serialise the warps.
+    constexpr int kWarps = kTgtThreads / 32;
+    const int w = threadIdx.x >> 5;
 #pragma unroll 1
-    for (int g = 0; g < G; ++g) {
+    for (int g = w; g < G; g += kWarps) {
         const int4 rg = s_range[g];
-        if (rg.x > rg.y || rg.z > rg.w) continue;                             // block-uniform (also bg / degenerate)
+        if (rg.x > rg.y || rg.z > rg.w) continue;                             // warp-uniform (also bg / degenerate)
         const int ww = rg.y - rg.x + 1, n = ww * (rg.w - rg.z + 1);
         const uint8_t gflag = s_skip[g];
         const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
         const float4 gf = s_gt32[g];
         const float lim = fminf(__uint_as_float(s_floor[g]), thr32);
+        unsigned long long best = 0ull;
+        int nhit = 0;
 #pragma unroll 1
-        for (int t0 = 0; t0 < n; t0 += kTgtThreads) {
-            if (t0 + (int)(threadIdx.x & ~31u) >= n) continue;                // this warp has no cell of the window
-            const int t = t0 + threadIdx.x;
+        for (int t0 = 0; t0 < n; t0 += 32) {
+            const int t = t0 + lane;
             const bool act = t < n;
             const int dy = act ? t / ww : 0;
             const int ix = rg.x + (act ? t - dy * ww : 0), jy = rg.z + dy;
             const double2 X = s_ax[ix], Y = s_ay[jy];
             const float4 XF = s_axf[ix], YF = s_ayf[jy];
-            AnchorPx an;
-            an.x1 = X.x; an.x2 = X.y; an.y1 = Y.x; an.y2 = Y.y;
             // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
             const bool usable = act && XF.w != 0.f && YF.w != 0.f;
             // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
-            const bool isect = usable && gx2 > an.x1 && an.x2 > gx1 && gy2 > an.y1 && an.y2 > gy1;
+            const bool isect = usable && gx2 > X.x && X.y > gx1 && gy2 > Y.x && Y.y > gy1;
             // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
             bool need = false;
             if (isect) {
-                const float w = fminf(gf.z, XF.y) - fmaxf(gf.x, XF.x);
-                const float h = fminf(gf.w, YF.y) - fmaxf(gf.y, YF.x);
-                const float it = fmaxf(w, 0.f) * fmaxf(h, 0.f);
+                const float wi = fminf(gf.z, XF.y) - fmaxf(gf.x, XF.x);
+                const float hi = fminf(gf.w, YF.y) - fmaxf(gf.y, YF.x);
+                const float it = fmaxf(wi, 0.f) * fmaxf(hi, 0.f);
                 const float q = __fdividef(it, s_area32[g] + XF.z * YF.z - it);
                 need = (q + kIouMargin >= lim) ||           // could be the best anchor, or exceed rpn_max_overlap
                        (gflag & 2);                         // estimate not trusted: always exact
@@ -232,28 +249,74 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
             if (!__any_sync(0xffffffffu, need)) continue;                     // warp-uniform
             unsigned bits = 0;
             bool hit = false;
+            double iou = 0.0;
             if (need) {
-                const double iou = ref_iou(gx1, gy1, gx2, gy2, an.x1, an.y1, an.x2, an.y2);
+                iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
                 const float iou32 = (float)iou;                               // float32 accumulator (utils.py:603)
                 if (iou32 > 0.f) bits = __float_as_uint(iou32);
                 hit = iou > p.max_overlap;                                    // utils.py:704
-                if (hit) {
-                    const int cell = jy * p.W + ix;                           // one thread per cell and figure
-                    if (iou > s_lb[cell]) { s_lb[cell] = iou; s_lg[cell] = (short)g; }   // utils.py:710-713
-                }
             }
-            // best anchor of this GT: max float32 IoU, then first in loop order.  Two REDUX ops.
+            // best anchor of this figure: max float32 IoU, then first in loop order.  Two REDUX ops.
             const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);     // size->ratio->ix->jy
             const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
             if (wmax) {
                 const unsigned omin = __reduce_min_sync(0xffffffffu, bits == wmax ? order : 0xFFFFFFFFu);
-                if (lane == 0) atomicMax(&s_best[g], ((unsigned long long)wmax << 32) | (0xFFFFFFFFu - omin));
+                const unsigned long long key = ((unsigned long long)wmax << 32) | (0xFFFFFFFFu - omin);
+                best = key > best ? key : best;
             }
             const unsigned hm = __ballot_sync(0xffffffffu, hit);
-            if (hm && lane == 0) atomicAdd(&s_hits[g], __popc(hm));
+            if (hm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(s_nhit, __popc(hm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) {
+                    const int pos = base + __popc(hm & lanemask_lt());
+                    if (pos < hit_cap) s_hit[pos] = TargetHit{iou, jy * p.W + ix, g};
+                }
+                nhit += __popc(hm);
+            }
         }
-        __syncthreads();      // the next figure maps other threads onto these cells
+        if (lane == 0) {              // this warp is the only writer of figure g in this CTA
+            s_best[g] = best;
+            s_hits[g] = nhit;
+        }
     }
+    __syncthreads();
+
+    // Phase 2 - settle every hit cell: highest IoU wins, equal IoU -> the earlier figure (strict '>'
+    // in figure order, utils.py:710-713).
+    const int n_hit = *s_nhit;
+    if (n_hit <= hit_cap) {
+        for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
+            const TargetHit h = s_hit[e];
+            bool win = true;
+            for (int j = 0; j < n_hit; ++j) {
+                const TargetHit o = s_hit[j];
+                if (o.cell == h.cell && (o.iou > h.iou || (o.iou == h.iou && o.g < h.g))) win = false;
+            }
+            if (win) s_lg[h.cell] = (short)h.g;
+        }
+    } else {
+        // more positives than the list holds (never seen in practice): replay figure by figure with
+        // in-place per-cell state, the whole CTA on one figure at a time
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            const int4 rg = s_range[g];
+            if (rg.x > rg.y || rg.z > rg.w) continue;                         // block-uniform
+            const int ww = rg.y - rg.x + 1, n = ww * (rg.w - rg.z + 1);
+            const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
+            for (int t = threadIdx.x; t < n; t += kTgtThreads) {
+                const int dy = t / ww, ix = rg.x + t - dy * ww, jy = rg.z + dy;
+                if (s_axf[ix].w == 0.f || s_ayf[jy].w == 0.f) continue;
+                const double2 X = s_ax[ix], Y = s_ay[jy];
+                const double iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
+                const int cell = jy * p.W + ix;
+                if (iou > p.max_overlap && iou > s_lb[cell]) { s_lb[cell] = iou; s_lg[cell] = (short)g; }
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
 
     // write-out: every cell of the anchor plane, 10 float64 planes, coalesced along ix
 #pragma unroll 1
@@ -451,7 +514,13 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
         return RADNET_E_WORKSPACE;
     }
     size_t gt_bytes = align_up((size_t)Gmax * (4 * 8 + 16 + 16 + 8 + 4 + 4 + 4 + 1) + 16, 16);
-    size_t smem = gt_bytes + (size_t)H * W * (sizeof(double) + sizeof(short)) + (size_t)(H + W) * 32 + 32;
+    int hit_cap = H * W < 4096 ? H * W : 4096;
+    if (const char *e = getenv("RADNET_TARGETS_HIT_CAP")) {      // tests shrink the list to exercise the replay path
+        int v = atoi(e);
+        if (v >= 1 && v < hit_cap) hit_cap = v;
+    }
+    size_t smem = gt_bytes + (size_t)H * W * (sizeof(double) + sizeof(short)) + (size_t)(H + W) * 32 +
+                  (size_t)hit_cap * sizeof(TargetHit) + 64;
     int dev = 0, smem_limit = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
     RADNET_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -472,6 +541,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     p.y_cls = y_rpn_cls; p.y_regr = y_rpn_regr; p.best_anchor = best_anchor; p.n_hits = n_hits;
     p.best_key = reinterpret_cast<unsigned long long *>(ws);
     p.sm_off_cells = (int)gt_bytes;
+    p.hit_cap = hit_cap;
     cudaStream_t st = (cudaStream_t)stream;
     RADNET_CUDA(cudaMemsetAsync(ws, 0, need, st));
     if (Gmax > 0) RADNET_CUDA(cudaMemsetAsync(n_hits, 0, sizeof(int32_t) * (size_t)B * Gmax, st));

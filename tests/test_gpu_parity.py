@@ -228,6 +228,20 @@ def test_rpn_targets_batched_presample_vs_oracle(pkg):
         assert np.array_equal(hits[b, :g], nh)
 
 
+def test_rpn_targets_hit_list_overflow_replay(pkg, monkeypatch):
+    """With a 3-entry positive-cell list the kernel must fall back to the figure-by-figure replay."""
+    monkeypatch.setenv("RADNET_TARGETS_HIT_CAP", "3")
+    C = S.HotPathConfig()
+    img = S.gt_figures(6, 30, 1000, 700, classes=("boat", "human"))
+    wr, hr = O.get_new_img_size(1000, 700, C.img_size)
+    np.random.seed(6)
+    got = pkg.calc_region_props(C, img, 1000, 700, wr, hr, S.resnet50_map_size)
+    np.random.seed(6)
+    ref = O.calc_region_props(C, img, 1000, 700, wr, hr, S.resnet50_map_size)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2]) and got[3] == ref[3]
+    np.testing.assert_allclose(got[1], ref[1], rtol=REGR_RTOL, atol=0)
+
+
 def test_rpn_targets_many_seeds_best_anchor_and_hits(pkg):
     """Stresses the float32 pre-filter of the IoU kernel: tiny / huge / touching / duplicate figures."""
     from rock_art_radnet_b200.utils import rpn_targets_device

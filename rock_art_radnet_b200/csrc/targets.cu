@@ -152,31 +152,6 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     __syncthreads();
 
     const float thr32 = (float)p.max_overlap;
-    // Cell window of this anchor shape that can matter for each figure.  IoU >= L needs, on each
-    // axis, an overlap of at least L*max(figure side, anchor side) (because union >= the larger
-    // area and the other overlap <= the smaller side); with L = min(floor, thr) - margin this is
-    // a handful of cells around the figure, and empty when the shapes cannot reach L at all.
-    // One cell of padding on every side absorbs the rounding of this float64 arithmetic.
-    for (int g = threadIdx.x; g < G; g += kTgtThreads) {
-        int4 r = make_int4(0, -1, 0, -1);                                    // empty
-        const uint8_t f = s_skip[g];
-        if (!(f & 1)) {
-            const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
-            double L = (double)fminf(__uint_as_float(s_floor[g]), thr32) - 2.0 * (double)kIouMargin;
-            if ((f & 2) || !(L > 0.0)) L = 0.0;
-            const double mx = L * fmax(gx2 - gx1, aw), my = L * fmax(gy2 - gy1, ah);
-            // centre c = stride*(i+0.5) must satisfy  g1 + m - side/2 <= c <= g2 - m + side/2
-            const double xl = (gx1 + mx - aw * 0.5) / p.stride - 0.5, xh = (gx2 - mx + aw * 0.5) / p.stride - 0.5;
-            const double yl = (gy1 + my - ah * 0.5) / p.stride - 0.5, yh = (gy2 - my + ah * 0.5) / p.stride - 0.5;
-            if (xl <= xh + 2.0 && yl <= yh + 2.0) {
-                r.x = (int)fmax(floor(xl) - 1.0, 0.0);
-                r.y = (int)fmin(ceil(xh) + 1.0, (double)(p.W - 1));
-                r.z = (int)fmax(floor(yl) - 1.0, 0.0);
-                r.w = (int)fmin(ceil(yh) + 1.0, (double)(p.H - 1));
-            }
-        }
-        s_range[g] = r;
-    }
     // per-cell state of this anchor plane: best IoU above rpn_max_overlap and the figure it came from
     double *s_lb = reinterpret_cast<double *>(smem + p.sm_off_cells);                    // [HW]
     double2 *s_ax = reinterpret_cast<double2 *>(s_lb + ((HW + 1) & ~1));                 // [W] anchor x1,x2 of column ix
@@ -186,8 +161,13 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     TargetHit *s_hit = reinterpret_cast<TargetHit *>(s_ayf + p.H);                       // [hit_cap]
     const int hit_cap = p.hit_cap;
     int *s_nhit = reinterpret_cast<int *>(s_hit + hit_cap);                              // 4 ints
-    short *s_lg = reinterpret_cast<short *>(s_nhit + 4);                                 // [HW]
-    if (threadIdx.x == 0) *s_nhit = 0;
+    short *s_lg = reinterpret_cast<short *>(s_nhit + 8);                                 // [HW]
+    int *s_use = s_nhit + 4;                                                             // ix_lo, ix_hi, jy_lo, jy_hi in-image
+    if (threadIdx.x == 0) {
+        *s_nhit = 0;
+        s_use[0] = p.W; s_use[1] = -1; s_use[2] = p.H; s_use[3] = -1;
+    }
+    __syncthreads();
     for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) {
         s_lb[cell] = 0.0;
         s_lg[cell] = -1;
@@ -203,6 +183,41 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
         const bool ok = !(v1 < 0.0 || v2 > lim_px) && v1 < v2;
         (isx ? s_ax : s_ay)[k] = make_double2(v1, v2);
         (isx ? s_axf : s_ayf)[k] = make_float4((float)v1, (float)v2, (float)(v2 - v1), ok ? 1.f : 0.f);
+        if (ok) {
+            atomicMin(&s_use[isx ? 0 : 2], k);
+            atomicMax(&s_use[isx ? 1 : 3], k);
+        }
+    }
+    __syncthreads();
+
+    // Cell window of this anchor shape that can matter for each figure.  IoU >= L needs, on each
+    // axis, an overlap of at least L*max(figure side, anchor side) (because union >= the larger
+    // area and the other overlap <= the smaller side); with L = min(floor, thr) - margin this is
+    // a handful of cells around the figure.  The window is empty when the two shapes cannot reach
+    // L at all (IoU <= smaller-overlap-box / union), and it is clipped to the in-image rectangle
+    // of this anchor shape.  One cell of padding absorbs the rounding of this float64 arithmetic.
+    for (int g = threadIdx.x; g < G; g += kTgtThreads) {
+        int4 r = make_int4(0, -1, 0, -1);                                    // empty
+        const uint8_t f = s_skip[g];
+        if (!(f & 1) && s_use[0] <= s_use[1] && s_use[2] <= s_use[3]) {
+            const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
+            double L = (double)fminf(__uint_as_float(s_floor[g]), thr32) - 2.0 * (double)kIouMargin;
+            if ((f & 2) || !(L > 0.0)) L = 0.0;
+            const double wg = gx2 - gx1, hg = gy2 - gy1;
+            const double imax = fmin(wg, aw) * fmin(hg, ah);                  // largest possible intersection
+            const bool feasible = imax >= (L - 1e-9) * (wg * hg + aw * ah - imax);
+            const double mx = L * fmax(wg, aw), my = L * fmax(hg, ah);
+            // centre c = stride*(i+0.5) must satisfy  g1 + m - side/2 <= c <= g2 - m + side/2
+            const double xl = (gx1 + mx - aw * 0.5) / p.stride - 0.5, xh = (gx2 - mx + aw * 0.5) / p.stride - 0.5;
+            const double yl = (gy1 + my - ah * 0.5) / p.stride - 0.5, yh = (gy2 - my + ah * 0.5) / p.stride - 0.5;
+            if (feasible && xl <= xh + 2.0 && yl <= yh + 2.0) {
+                r.x = max((int)fmax(floor(xl) - 1.0, 0.0), s_use[0]);
+                r.y = min((int)fmin(ceil(xh) + 1.0, (double)(p.W - 1)), s_use[1]);
+                r.z = max((int)fmax(floor(yl) - 1.0, 0.0), s_use[2]);
+                r.w = min((int)fmin(ceil(yh) + 1.0, (double)(p.H - 1)), s_use[3]);
+            }
+        }
+        s_range[g] = r;
     }
     __syncthreads();
 

@@ -330,6 +330,14 @@ def run_b200_arm(args):
         pool_bytes = B * (H * W * CH * 4) + kept * 16 + kept * POOL * POOL * CH * 4
         peak, peak_src = measured_hbm_peak()
         achieved = pool_bytes / (pool_ms * 1e-3) / 1e9
+        traffic = None          # DRAM bytes of one launch from the committed ncu capture (same launch shape only)
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("panels_per_launch") == B:
+                traffic = tj["traffic_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": "panels_per_sec", "value": value, "unit": "panels/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / K, "higher_is_better": True,
@@ -346,7 +354,7 @@ def run_b200_arm(args):
             "nms_latency_us": {"p50": lat[len(lat) // 2], "p95": lat[int(len(lat) * 0.95) - 1], "n": len(lat),
                                "what": "radnet_sort_nms_i32, one 600-px panel (12,996 candidates) per launch"},
             "roofline": {"kernel": "roi_pool_slice_kernel<8>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pool_bytes, "avg_launch_ms": pool_ms},
             "kept_boxes_per_step": kept,
         }

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
     float4 *s_map = reinterpret_cast<float4 *>(smem);                                   // [HW+1][LANES]
     YEntry *s_ytab = reinterpret_cast<YEntry *>(smem + (size_t)(HW + 1) * kPixBytes);   // [chunk][pool]
     int2 *s_roi = reinterpret_cast<int2 *>(s_ytab + (size_t)p.roi_chunk * pool);        // [chunk] {x, cw}
+    float *s_scale = reinterpret_cast<float *>(s_roi + p.roi_chunk);                    // [W+1] cw / pool (float32 divide)
 
     const int b = blockIdx.x / p.n_slices;
     const int s = blockIdx.x - b * p.n_slices;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
         const float4 *src = reinterpret_cast<const float4 *>(p.feat) + (size_t)b * HW * C4 + (size_t)s * LANES + q;
         for (int pix = g; pix < HW; pix += G) cp_async16(&s_map[pix * LANES + q], src + (size_t)pix * C4);
         if (g == 0) s_map[HW * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);      // the "zero pixel"
+        for (int i = threadIdx.x; i <= p.W; i += kPoolThreads) s_scale[i] = __fdiv_rn((float)i, (float)p.pool);
         cp_async_wait_all();
     }
     const unsigned char *mapb = reinterpret_cast<const unsigned char *>(s_map) + q * 16;
@@ -194,14 +196,20 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
         __syncthreads();
 
         const int ncol = nr * pool;
-        for (int col = g; col < ncol; col += G) {
-            const int rl = col / pool, px = col - rl * pool;
+        // (rl, px) advance incrementally by G columns: no integer division in the column loop
+        int rl = g / pool, px = g - rl * pool;
+        const int d_rl = G / pool, d_px = G - d_rl * pool;
+        for (int col = g; col < ncol; col += G, rl += d_rl, px += d_px) {
+            if (px >= pool) { px -= pool; ++rl; }
             const int2 rx = s_roi[rl];
             int xo0, xo1;
             float lx;
             if (rx.y > 0) {
-                int lo, hi;
-                legacy_axis(px, rx.y, pool, lo, hi, lx);
+                // TF-1 legacy weights with the float32 scale cw/pool taken from a table
+                const float src = __fmul_rn((float)px, s_scale[rx.y]);
+                const float fl = floorf(src);
+                const int lo = max((int)fl, 0), hi = min((int)ceilf(src), rx.y - 1);
+                lx = __fsub_rn(src, fl);
                 xo0 = (rx.x + lo) * kPixBytes;
                 xo1 = (rx.x + hi) * kPixBytes;
             } else {
@@ -322,10 +330,11 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
         for (int li = 0; li < 4; ++li) {
             int L = lanes_opts[li];
             size_t map_bytes = (HW + 1) * L * 16;
-            if (C4 % L != 0 || map_bytes + 8 * per_roi > (size_t)smem_limit) continue;
-            size_t chunk = ((size_t)smem_limit - map_bytes) / per_roi;
+            const size_t scale_bytes = ((size_t)W + 1) * sizeof(float) + 16;
+            if (C4 % L != 0 || map_bytes + scale_bytes + 8 * per_roi > (size_t)smem_limit) continue;
+            size_t chunk = ((size_t)smem_limit - map_bytes - scale_bytes) / per_roi;
             if (chunk > (size_t)rois_per_panel) chunk = rois_per_panel;
-            size_t smem = map_bytes + chunk * per_roi;
+            size_t smem = map_bytes + chunk * per_roi + scale_bytes;
             p.n_slices = C4 / L;
             p.roi_chunk = (int)chunk;
             if ((long long)B * p.n_slices >= 0x7fffffffLL) continue;

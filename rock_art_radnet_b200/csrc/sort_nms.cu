@@ -31,6 +31,8 @@
 // are packed 2 x int16 and compared with VIMNMX.S16x2 / VIADDMNMX.S16x2.RELU.  The f64 path
 // performs the float64 arithmetic in the reference's association order.  Both decide
 // bit-exactly like NumPy.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace radnet {
@@ -129,6 +131,7 @@ struct SortNmsParams {
     double thr;
     int table_entries;        // i32 only: umax + 1
     int sel_target;           // candidates the first (selective) sort round aims for
+    int look_ahead;           // rows that may run ahead of the retiring row in the NMS hand-off
     // outputs
     unsigned char *det;       // i32: detection records
     size_t det_stride;
@@ -652,7 +655,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             int seen = k0;
             int kc = k0;
             NMS_ROW_STAMP(1);    // intra-row matrix done
-            for (int pw = max(0, w - kLookAhead); pw < w; ++pw) {
+            for (int pw = max(0, w - p.look_ahead); pw < w; ++pw) {
                 if (pw == w - 1) NMS_ROW_STAMP(2);    // about to wait for the immediate predecessor
                 if (!mbar_wait_bounded(&s_turn[pw], parity)) { *s_fault = 1; break; }
                 kc = s_kafter[pw];            // published by exactly the row just acquired
@@ -773,6 +776,15 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     if (pl.kept_smem) off += align_up((size_t)K * sizeof(Cand) + 64, 128);
     // first sort round: about this many top-scoring candidates (see the kernel)
     p.sel_target = (4 * K > 2048) ? 4 * K : 2048;
+    p.look_ahead = kLookAhead;
+    if (const char *e = getenv("RADNET_NMS_LOOKAHEAD")) {     // tuning knob (any value is correct)
+        int v = atoi(e);
+        if (v >= 1 && v <= 32) p.look_ahead = v;
+    }
+    if (const char *e = getenv("RADNET_NMS_SEL_TARGET")) {
+        int v = atoi(e);
+        if (v >= 32) p.sel_target = v;
+    }
     // shared-memory sort: keys ping-pong + uint16 index ping-pong
     size_t cap = align_up((size_t)N, 64);
     size_t sort_bytes = 2 * cap * sizeof(KeyT) + 2 * cap * sizeof(uint16_t);

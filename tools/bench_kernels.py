@@ -98,6 +98,20 @@ def main():
     res["sort_nms_90k_candidates"] = time_ms(lambda: pipe.sort_nms(), iters=20, flush=False)
     del pipe
 
+    # secondary shapes: the reference's DEFAULT 12-anchor config and a 600x800 panel (38x50 map)
+    for tag, (Hh, Ww, scales) in {"12anchors_38x38": (38, 38, (64, 128, 256, 512)),
+                                  "9anchors_38x50": (38, 50, (128, 256, 512))}.items():
+        C2 = S.HotPathConfig(scales)
+        cls, regr = tile_maps(64, Hh, Ww, C2.num_anchors)
+        pipe = ProposalPipeline(C2, 64, Hh, Ww, alloc_pooled=False)
+        pipe.decode(cls, regr)
+        res["sort_nms_B64_" + tag] = time_ms(lambda: pipe.sort_nms())
+        cls1, regr1 = tile_maps(1, Hh, Ww, C2.num_anchors)
+        pipe1 = ProposalPipeline(C2, 1, Hh, Ww, alloc_pooled=False)
+        pipe1.decode(cls1, regr1)
+        res["sort_nms_single_" + tag] = time_ms(lambda: pipe1.sort_nms(), iters=30, flush=False)
+        del pipe, pipe1
+
     # ---- K3 ----------------------------------------------------------------------------
     G = 20
     for B in (64, 512):
@@ -140,15 +154,16 @@ def main():
     res["calc_region_props_dropin_wall_ms"] = (time.perf_counter() - t0) / 10 * 1e3
 
     # ---- K4 ----------------------------------------------------------------------------
-    for (B, Cn, pool, tag) in ((64, 1024, 14, "resnet50"), (64, 512, 7, "vgg16")):
-        cls, regr = tile_maps(B)
-        feat = torch.randn((B, 38, 38, Cn), dtype=torch.float32, device="cuda")
-        pipe = ProposalPipeline(C, B, 38, 38, channels=Cn, pool_size=pool)
+    for (B, Cn, pool, tag, Hh, Ww) in ((64, 1024, 14, "resnet50", 38, 38), (64, 512, 7, "vgg16", 38, 38),
+                                       (32, 1024, 14, "resnet50_38x50", 38, 50)):
+        cls, regr = tile_maps(B, Hh, Ww)
+        feat = torch.randn((B, Hh, Ww, Cn), dtype=torch.float32, device="cuda")
+        pipe = ProposalPipeline(C, B, Hh, Ww, channels=Cn, pool_size=pool)
         pipe.decode(cls, regr)
         pipe.sort_nms()
         kept = int(pipe.records.counts.sum().item())
         t = time_ms(lambda: pipe.pool(feat), iters=10)
-        nbytes = B * 38 * 38 * Cn * 4 + kept * 16 + kept * pool * pool * Cn * 4
+        nbytes = B * Hh * Ww * Cn * 4 + kept * 16 + kept * pool * pool * Cn * 4
         res["roi_pool_%s_B%d" % (tag, B)] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
                                                   frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk)
         del pipe, feat

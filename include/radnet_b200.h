@@ -179,6 +179,73 @@ int radnet_roi_targets(const int32_t *rois, int R, const double *gt, const int32
                        const double *h_regr_std4, int32_t *x_roi, int32_t *y_class,
                        double *y_regr, double *ious, int32_t *count, void *stream);
 
+/* ------------------------------------------------ f1/f2: detection post-processing
+ * Labelled detection record, the unit exchanged between these entry points and between ranks
+ * (stride = radnet_cls_record_bytes(max_det)):
+ *   int32 header[8] = {n_det (-1 = an input record carried a fault, -2 = capacity exceeded),
+ *                      n_in (RoIs examined / entries concatenated), n_degenerate (boxes with
+ *                      x1>=x2 or y1>=y2: the reference's NMS asserts, rpn.py:400-401),
+ *                      n_score_ties, n_classes_present,
+ *                      n_regr_fallback (classify_*) or n_empty_clusters (final_nms),
+ *                      n_round_near_ties, n_out_of_range (|coordinate| > 2^25)}
+ *   int32 class_order[32]  class ids in first-appearance order (the insertion order of the
+ *                          reference's per-class dicts), -1 padded
+ *   int32 class_count[32]  entries per class id
+ *   entry[max_det]         {int32 cls; float prob; int32 x1,y1,x2,y2; int32 src; int32 aux}
+ * Entries of radnet_classify_decode are in RoI order; those of the NMS entry points are grouped by
+ * class (class_order) and, inside a class, in pick order (descending score). */
+size_t radnet_cls_record_bytes(int max_det);
+
+/* Per-RoI class decision and box decode of RADNet.apply_spatial_pyramid_pooling (reference
+ * faster_rcnn/RADNet.py:123-150) with the scalar apply_regr (rpn.py:346-378), B tiles at once.
+ *   p_cls  [B][R][n_cls] float32, p_regr [B][R][4*(n_cls-1)] float32: classifier-head outputs
+ *   RoIs (x,y,w,h in feature cells), two addressing modes as in radnet_roi_pool:
+ *     det != NULL : the kept boxes of the B detection records (x2-x1, y2-y1; RADNet.py:564-565)
+ *     det == NULL : rois [B][R][4] int32, roi_count [B] or NULL (= R); the caller has already
+ *                   padded the last chunk as RADNet.py:106-118 does
+ *   bbox_threshold   compared in float32 (RADNet.py:126, NumPy >= 2 scalar rule)
+ *   h_regr_std4      classifier_regr_std; the division is float32 (RADNet.py:140-143)
+ *   rpn_stride       integer stride (RADNet.py:149); R <= 1024, n_cls <= 32 ('bg' is the last class)
+ * Output: B records, entries in RoI order, src = RoI index. */
+int radnet_classify_decode(const float *p_cls, const float *p_regr, int B, int R, int n_cls,
+                           const void *det, int det_max_boxes, const int32_t *rois,
+                           const int32_t *roi_count, double bbox_threshold,
+                           const double *h_regr_std4, int rpn_stride, void *rec_out,
+                           int rec_max_det, void *stream);
+
+/* The same decode fused with the per-class NMS of RADNet.predict (rpn.non_max_suppression_fast at
+ * RADNet.py:574, threshold nms_thr, stop at max_boxes per class), get_real_coordinates
+ * (RADNet.py:44-51: Python floor division by ratio[b]) and the tile offset origin[b] = {x0,y0}
+ * (RADNet.py:582-600).  ratio / origin may be NULL (no scaling / no offset). */
+int radnet_classify_nms(const float *p_cls, const float *p_regr, int B, int R, int n_cls,
+                        const void *det, int det_max_boxes, const int32_t *rois,
+                        const int32_t *roi_count, double bbox_threshold,
+                        const double *h_regr_std4, int rpn_stride, double nms_thr, int max_boxes,
+                        const double *ratio, const int32_t *origin, void *rec_out,
+                        int rec_max_det, void *stream);
+
+/* Per-class greedy NMS over the concatenation of n_in records per segment (the cross-image NMS of
+ * RADNet.py:695-716, or the NMS half of radnet_classify_nms on records).  rec_in is
+ * [S][n_in] records of capacity in_max_det; in_count [S] (NULL = n_in) limits the records used.
+ * Optional ratio [S] / origin [S][2] as above. */
+size_t radnet_class_nms_workspace_bytes(int S, int n_in, int in_max_det, int n_cls);
+int radnet_class_nms(const void *rec_in, int in_max_det, int S, int n_in, const int32_t *in_count,
+                     int n_cls, double thr, int max_boxes, const double *ratio,
+                     const int32_t *origin, void *rec_out, int out_max_det, void *ws,
+                     size_t ws_bytes, void *stream);
+
+/* RADNet.final_nms (RADNet.py:156-240): cluster-and-average merge, per class, of the n_in tile
+ * records of each of S images.  A cluster = the best remaining box and every remaining box with
+ * inter/(union+1e-6) > avg_thr; it is represented by the members scoring above conf_thr (float32
+ * comparison) or, if even its best score is below conf_thr, by its n_obj_avg best members:
+ * box = rint(mean), prob = float32 mean in NumPy's pairwise order.  Entry.src = input index of the
+ * cluster's best box, entry.aux = number of members averaged.  At most 4096 boxes per (image,
+ * class); beyond that header[0] = -2. */
+size_t radnet_final_nms_workspace_bytes(int S, int n_in, int in_max_det, int n_cls);
+int radnet_final_nms(const void *rec_in, int in_max_det, int S, int n_in, const int32_t *in_count,
+                     int n_cls, double avg_thr, double conf_thr, int n_obj_avg, void *rec_out,
+                     int out_max_det, void *ws, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,3 +54,16 @@ def load_reference():
     utils = importlib.import_module("faster_rcnn.utils")
     config = importlib.import_module("faster_rcnn.config")
     return rpn, utils, config
+
+
+def load_radnet():
+    """Return the reference module `faster_rcnn.RADNet` (class RADNet), imported unmodified.
+    RADNet.py:14-15 imports `keras.layers.Input` and `keras.models.Model`, stubbed here; cv2,
+    pandas and tqdm are present in the build container."""
+    load_reference()
+    layers = sys.modules["keras.layers"]
+    if not hasattr(layers, "Input"):
+        layers.Input = object
+    models = _stub("keras.models", Model=object)
+    sys.modules["keras"].models = models
+    return importlib.import_module("faster_rcnn.RADNet")

@@ -44,6 +44,18 @@ SIGNATURES = {
     "radnet_roi_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_double,
                                    c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
+    "radnet_cls_record_bytes": (c_size_t, [c_int]),
+    "radnet_classify_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                       c_void_p, c_double, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "radnet_classify_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_double, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_int, c_void_p]),
+    "radnet_class_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "radnet_class_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_double, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "radnet_final_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "radnet_final_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_double, c_double, c_int,
+                                 c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
 }
 
 

@@ -92,3 +92,203 @@ def resnet50_map_size(width, height):
         return n
 
     return one(width), one(height)
+
+
+# ----------------------------------------------------------------------------------------
+# Deterministic stand-ins for the two Keras models around the hot path (tests, goldens, bench).
+# The reference calls `model_rpn.predict(X) -> [Y1, Y2, F]` and
+# `model_detector.predict([F, ROIs]) -> [P_cls, P_regr]` (RADNet.py:560, 120); both networks are
+# out of scope here, so these fakes produce maps / head outputs that are pure functions of
+# their inputs and lead to overlapping detections across tiles (so that the tile merge has
+# real clusters to average).
+# ----------------------------------------------------------------------------------------
+def coordinate_image(width, height):
+    """uint8 BGR image whose pixel values encode their own coordinates, so that a fake RPN
+    can recover the tile origin from a crop: ch0 = x % 256, ch1 = y % 256,
+    ch2 = 16*(x // 256) + (y // 256)."""
+    xs = np.arange(width)[None, :].repeat(height, 0)
+    ys = np.arange(height)[:, None].repeat(width, 1)
+    return np.stack([xs % 256, ys % 256, 16 * (xs // 256) + (ys // 256)], axis=-1).astype(np.uint8)
+
+
+def scene_objects(seed, width, height, n_obj=12, n_cls=6, lo=60, hi=260):
+    """Synthetic 'true' figures of a scene: (n_obj, 5) int64 [x1, y1, x2, y2, class]."""
+    rng = np.random.default_rng(4_000_003 + seed)
+    out = []
+    for _ in range(n_obj):
+        w = int(rng.integers(lo, min(hi, width) + 1))
+        h = int(rng.integers(lo, min(hi, height) + 1))
+        x1 = int(rng.integers(0, width - w + 1))
+        y1 = int(rng.integers(0, height - h + 1))
+        out.append([x1, y1, x1 + w, y1 + h, int(rng.integers(0, n_cls))])
+    return np.asarray(out, dtype=np.int64)
+
+
+class FakeRpnModel:
+    """`predict(X)`: X (1,h,w,3) float32 RGB view of a `coordinate_image` crop at scale `ratio`
+    -> [Y1 (1,H,W,A), Y2 (1,H,W,4A), F (1,H,W,4)].  The maps are `rpn_maps(seed)` with the seed
+    derived from the crop origin; F[0,0,0,:3] carries (origin x, origin y, resized width) for
+    the fake detector."""
+
+    def __init__(self, num_anchors=9, map_size=resnet50_map_size, seed=0):
+        self.num_anchors = num_anchors
+        self.map_size = map_size
+        self.seed = seed
+        self.calls = 0
+
+    def predict(self, X):
+        self.calls += 1
+        _, h, w, _ = X.shape
+        Wm, Hm = self.map_size(w, h)
+        r0, g0, b0 = (int(round(float(v))) for v in X[0, 0, 0, :3])      # RGB = ch2, ch1, ch0
+        ox = b0 + 256 * (r0 // 16)
+        oy = g0 + 256 * (r0 % 16)
+        salt = 0
+        if h > 1 and w > 1:     # differs between the image types of `predict_case` (odd pixels are flipped)
+            salt = (int(round(float(X[0, 1, 1, 1]))) ^ ((oy + 1) % 256)) & 1
+        cls, regr = rpn_maps(self.seed * 7919 + ox * 31 + oy + 104729 * salt, Hm, Wm, self.num_anchors)
+        F = np.zeros((1, Hm, Wm, 4), dtype=np.float32)
+        F[0, 0, 0, :3] = (ox, oy, w)
+        return [cls, regr, F]
+
+
+class FakeDetectorModel:
+    """`predict([F, ROIs])`: ROIs (1,n,4) xywh in feature cells -> [P_cls (1,n,n_cls) float32,
+    P_regr (1,n,4(n_cls-1)) float32].  Each RoI is scored by its IoU with the scene objects
+    (in original-image pixels): the best object's class gets 0.40 + 0.58*iou (+ a hash jitter), 'bg' the
+    rest; the regression targets point at the object, scaled by classifier_regr_std and
+    perturbed by a hash of the RoI, so equal RoIs give equal outputs."""
+
+    def __init__(self, objects, C, ratio=1.0, n_cls=7):
+        self.objects = np.asarray(objects, dtype=np.float64)
+        self.C = C
+        self.ratio = float(ratio)
+        self.n_cls = n_cls
+        self.calls = 0
+
+    def predict(self, inputs):
+        self.calls += 1
+        F, rois = inputs
+        ox, oy = float(F[0, 0, 0, 0]), float(F[0, 0, 0, 1])
+        n = rois.shape[1]
+        P_cls = np.zeros((1, n, self.n_cls), dtype=np.float32)
+        P_regr = np.zeros((1, n, 4 * (self.n_cls - 1)), dtype=np.float32)
+        s = float(self.C.rpn_stride)
+        std = self.C.classifier_regr_std
+        ob = self.objects
+        for i in range(n):
+            x, y, w, h = (float(v) for v in rois[0, i])
+            gx1, gy1 = ox + s * x / self.ratio, oy + s * y / self.ratio
+            gx2, gy2 = gx1 + s * w / self.ratio, gy1 + s * h / self.ratio
+            iw = np.maximum(0.0, np.minimum(gx2, ob[:, 2]) - np.maximum(gx1, ob[:, 0]))
+            ih = np.maximum(0.0, np.minimum(gy2, ob[:, 3]) - np.maximum(gy1, ob[:, 1]))
+            inter = iw * ih
+            iou = inter / ((gx2 - gx1) * (gy2 - gy1) + (ob[:, 2] - ob[:, 0]) * (ob[:, 3] - ob[:, 1]) - inter)
+            k = int(np.argmax(iou))
+            hsh = (int(x) * 73856093 ^ int(y) * 19349663 ^ int(w) * 83492791 ^ int(h) * 2654435761) & 0xFFFF
+            p = 0.40 + 0.58 * float(iou[k]) + 1e-4 * (hsh % 97)          # < 1, never saturates (no planted ties)
+            c = int(ob[k, 4])
+            P_cls[0, i, c] = p
+            P_cls[0, i, self.n_cls - 1] = 1.0 - p
+            # regression towards the object, in feature cells of this view
+            fx1, fy1 = (ob[k, 0] - ox) * self.ratio / s, (ob[k, 1] - oy) * self.ratio / s
+            fw, fh = (ob[k, 2] - ob[k, 0]) * self.ratio / s, (ob[k, 3] - ob[k, 1]) * self.ratio / s
+            w_, h_ = max(w, 1.0), max(h, 1.0)
+            noise = ((hsh % 13) - 6) * 0.01
+            t = [((fx1 + fw / 2) - (x + w / 2)) / w_ + noise, ((fy1 + fh / 2) - (y + h / 2)) / h_ - noise,
+                 np.log(max(fw, 0.25) / w_) * 0.8, np.log(max(fh, 0.25) / h_) * 0.8]
+            P_regr[0, i, 4 * c:4 * c + 4] = [t[j] * std[j] for j in range(4)]
+        return [P_cls, P_regr]
+
+
+class RandomHeadModel:
+    """`predict([F, ROIs])` with head outputs that are a hash-seeded random function of each RoI:
+    softmax-like P_cls rows (so every class, 'bg' included, wins somewhere) and N(0,1) regression
+    deltas.  `extremes=True` plants what the reference's apply_regr handles through its `except`
+    branches (exp overflow, inf, NaN deltas) and, when `nan_cls` is set, NaN class scores."""
+
+    def __init__(self, seed, C, n_cls=7, extremes=False, nan_cls=False, sharp=4.0):
+        self.seed, self.C, self.n_cls = seed, C, n_cls
+        self.extremes, self.nan_cls, self.sharp = extremes, nan_cls, sharp
+        self.calls = 0
+
+    def predict(self, inputs):
+        self.calls += 1
+        _, rois = inputs
+        n = rois.shape[1]
+        P_cls = np.zeros((1, n, self.n_cls), dtype=np.float32)
+        P_regr = np.zeros((1, n, 4 * (self.n_cls - 1)), dtype=np.float32)
+        std = np.tile(np.asarray(self.C.classifier_regr_std, dtype=np.float64), self.n_cls - 1)
+        for i in range(n):
+            x, y, w, h = (int(v) for v in rois[0, i])
+            hsh = (x * 73856093 ^ y * 19349663 ^ w * 83492791 ^ h * 2654435761 ^ self.seed * 40503) & 0x7FFFFFFF
+            rng = np.random.default_rng(hsh)
+            z = rng.standard_normal(self.n_cls) * self.sharp
+            e = np.exp(z - z.max())
+            P_cls[0, i] = (e / e.sum()).astype(np.float32)
+            t = rng.standard_normal(4 * (self.n_cls - 1)) * 0.4
+            if self.extremes:
+                k = hsh % 11
+                if k == 0:
+                    t[2::4] = 800.0          # exp overflow -> OverflowError branch
+                elif k == 1:
+                    t[0::4] = np.inf         # inf centre -> OverflowError in round()
+                elif k == 2:
+                    t[3::4] = np.nan         # NaN -> ValueError in round()
+                elif k == 3:
+                    t[2::4] = -30.0          # width rounds to 0 -> degenerate box
+                if self.nan_cls and hsh % 17 == 0:
+                    P_cls[0, i, hsh % self.n_cls] = np.nan
+            P_regr[0, i] = (t * std).astype(np.float32)
+        return [P_cls, P_regr]
+
+
+def clustered_boxes(seed, n_clusters, per_cluster, score_lo=0.7, score_hi=1.0, extent=1500, ties=False):
+    """Integer boxes in `n_clusters` jittered groups with float32 scores - input of the tile merge
+    (final_nms).  Returns (boxes (M,4) int64, probs (M,) float32)."""
+    rng = np.random.default_rng(5_000_003 + seed)
+    b, p = [], []
+    for _ in range(n_clusters):
+        cx, cy = (int(v) for v in rng.integers(0, extent, 2))
+        w, h = (int(v) for v in rng.integers(80, 320, 2))
+        for _ in range(per_cluster):
+            j = rng.integers(-30, 31, 4)
+            b.append([cx + j[0], cy + j[1], cx + w + j[2], cy + h + j[3]])
+            p.append(rng.uniform(score_lo, score_hi))
+    b = np.asarray(b, dtype=np.int64).reshape(-1, 4)
+    p = np.asarray(p, dtype=np.float32)
+    if ties and len(p) > 3:
+        idx = rng.integers(0, len(p), len(p) // 3)
+        p[idx] = p[idx[0]]
+    return b, p
+
+
+# name -> (seed, image width, height, tile_size, step, include_full_img, number of image types)
+PREDICT_CASES = {
+    "w1000_h800_tiles": (0, 1000, 800, 600, 200, False, 1),
+    "w1000_h800_tiles_full": (1, 1000, 800, 600, 200, True, 1),
+    "w700_h600_two_types": (2, 700, 600, 600, 200, False, 2),
+    "w640_h600_fullonly": (3, 640, 600, 600, 200, True, 1),
+}
+
+
+def predict_case(name, config_cls=HotPathConfig):
+    """(C, images, make_models) of one end-to-end post-processing case; `make_models()` returns a
+    fresh (model_rpn, model_detector) pair so that the reference, the oracle and the device path
+    all see the same call sequence."""
+    seed, width, height, tile, step, full, n_types = PREDICT_CASES[name]
+    C = config_cls()
+    C.anchor_box_scales = [128, 256, 512]
+    C.tile_size, C.tile_overlap = tile, step
+    C.include_full_img = full
+    C.max_n_tiles_train = 0 if name.endswith("fullonly") else 1
+    objs = scene_objects(seed, width, height, n_obj=14)
+    images = [coordinate_image(width, height) for _ in range(n_types)]
+    if n_types > 1:
+        images[1] = images[1].copy()
+        images[1][1::2, 1::2, :] ^= 1          # a second image type: same geometry, different pixels
+
+    def make_models():
+        return FakeRpnModel(seed=seed), FakeDetectorModel(objs, C)
+
+    return C, images, make_models

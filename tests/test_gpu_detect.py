@@ -1,0 +1,217 @@
+"""GPU parity of the detection post-processing through the C ABI:
+radnet_classify_decode / radnet_classify_nms / radnet_class_nms / radnet_final_nms and the
+`RADNet` mirror class, against the reference-generated goldens and the CPU oracle.
+Bar: bit-exact (classes, int boxes, float32 scores, order)."""
+import numpy as np
+import pytest
+
+from conftest import _load_npz
+from oracle import detect_oracle as DO
+from oracle import radnet_oracle as O
+from oracle.make_golden_detect import F1_CASES, F2_CASES, dicts_to_arrays, f1_inputs, f2_inputs
+from rock_art_radnet_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device; there is no CPU fallback"
+    from rock_art_radnet_b200 import RADNet as RN
+    from rock_art_radnet_b200 import detect as DT
+    return RN, DT, torch
+
+
+def _config():
+    C = S.HotPathConfig()
+    C.tile_size, C.tile_overlap, C.include_full_img, C.max_n_tiles_train = 600, 200, False, 1
+    return C
+
+
+NAMES = {v: k for k, v in S.HotPathConfig().class_mapping.items()}
+
+
+@pytest.mark.parametrize("name", sorted(F1_CASES))
+def test_apply_spatial_pyramid_pooling_matches_reference_golden(mods, name):
+    RN, DT, _ = mods
+    g = _load_npz("f1_classify.npz")
+    C = _config()
+    R, model, F = f1_inputs(name, C)
+    net = RN.RADNet(C, None, model, lambda x: x)
+    bboxes, probs = net.apply_spatial_pyramid_pooling(R, F)
+    order, cls, box, pr = dicts_to_arrays(bboxes, probs, C.class_mapping)
+    assert np.array_equal(order, g[name + "/order"])
+    assert np.array_equal(cls, g[name + "/cls"])
+    assert np.array_equal(box, g[name + "/box"])
+    assert np.array_equal(pr, g[name + "/prob"], equal_nan=True)
+    assert all(isinstance(v, np.float32) for k in probs for v in probs[k])
+
+
+def test_classify_decode_counters(mods):
+    RN, DT, _ = mods
+    C = _config()
+    R, model, F = f1_inputs("random_55_extremes", C)
+    rois = DO.pad_rois(R, C.n_rois)
+    pc, pr = [], []
+    for k in range(0, len(rois), C.n_rois):
+        a, b = model.predict([F, rois[None, k:k + C.n_rois]])
+        pc.append(a[0]); pr.append(b[0])
+    pc, pr = np.concatenate(pc), np.concatenate(pr)
+    rec = DT.classify_decode(pc[None], pr[None], C, rois=rois[None].astype(np.int32)).to_numpy()[0]
+    cls, prob, box, n_fallback = DO.classify_decode(rois, pc, pr, C)
+    keep = cls >= 0
+    n = int(rec["header"][DT.H_NDET])
+    assert n == keep.sum() and rec["header"][DT.H_NIN] == len(rois)
+    assert np.array_equal(rec["entry"]["cls"][:n], cls[keep])
+    assert np.array_equal(rec["entry"]["box"][:n], box[keep])
+    assert np.array_equal(rec["entry"]["prob"][:n], prob[keep])
+    assert np.array_equal(rec["entry"]["src"][:n], np.flatnonzero(keep))
+    assert rec["header"][DT.H_NFALLBACK] == n_fallback and n_fallback > 0
+    assert rec["header"][DT.H_NNEARTIE] == 0 and rec["header"][DT.H_NRANGE] == 0
+
+
+@pytest.mark.parametrize("seed,n,ratio,origin", [(0, 300, 1.0, (0, 0)), (1, 290, 0.75, (400, 200)),
+                                                 (2, 64, 600 / 799.0, (1234, 77)), (3, 300, 2.0, (0, 16))])
+def test_classify_nms_matches_oracle(mods, seed, n, ratio, origin):
+    """Fused decode + per-class NMS (0.2) + get_real_coordinates + tile offset, B = 3 tiles at once."""
+    RN, DT, _ = mods
+    C = _config()
+    B = 3
+    rois, pcs, prs = [], [], []
+    for b in range(B):
+        R = S.random_rois(10 * seed + b, n)[0]
+        model = S.RandomHeadModel(seed + 100 * b, C, sharp=2.0 + b) if b else \
+            S.FakeDetectorModel(S.scene_objects(seed, 600, 600, n_obj=25, lo=40, hi=200), C)
+        a, r = model.predict([np.zeros((1, 1, 1, 4), np.float32), R[None]])
+        rois.append(R); pcs.append(a[0]); prs.append(r[0])
+    rec = DT.classify_nms(np.stack(pcs), np.stack(prs), C, rois=np.stack(rois).astype(np.int32),
+                          ratio=[ratio] * B, origin=[origin] * B).to_numpy()
+    DT.check_records(rec, "test")
+    total = 0
+    for b in range(B):
+        want = DO.tile_detections(rois[b], pcs[b], prs[b], C, ratio, origin, NAMES)
+        got_b, got_p = DT.record_to_dicts(rec[b], NAMES)
+        assert list(got_b) == list(want)
+        for k in want:
+            assert np.array_equal(got_b[k], want[k][0]) and np.array_equal(got_p[k], want[k][1])
+            total += len(got_p[k])
+    assert total > 0
+
+
+def test_classify_nms_from_detection_records(mods):
+    """RoIs taken straight from the K2 detection records (xyxy -> xywh), as in the batched pipeline."""
+    RN, DT, torch = mods
+    from rock_art_radnet_b200.pipeline import ProposalPipeline
+    C = _config()
+    B = 2
+    pipe = ProposalPipeline(C, B, 38, 38, alloc_pooled=False)
+    maps = [S.rpn_maps(40 + b) for b in range(B)]
+    cls = torch.from_numpy(np.concatenate([m[0] for m in maps])).cuda()
+    regr = torch.from_numpy(np.concatenate([m[1] for m in maps])).cuda()
+    pipe.decode(cls, regr)
+    pipe.sort_nms()
+    dets = pipe.records.to_numpy()
+    pcs, prs, rois = [], [], []
+    for b in range(B):
+        R = dets[b]["boxes"].copy()
+        R[:, 2] -= R[:, 0]
+        R[:, 3] -= R[:, 1]
+        a, r = S.RandomHeadModel(b, C, sharp=3.0).predict([None, R[None]])
+        pc = np.zeros((300, 7), np.float32); pr = np.zeros((300, 24), np.float32)
+        pc[:len(R)] = a[0]; pr[:len(R)] = r[0]
+        pcs.append(pc); prs.append(pr); rois.append(R)
+    rec = DT.classify_nms(np.stack(pcs), np.stack(prs), C, det=pipe.records).to_numpy()
+    for b in range(B):
+        n = len(rois[b])
+        want = DO.tile_detections(rois[b], pcs[b][:n], prs[b][:n], C, 1.0, (0, 0), NAMES)
+        got_b, got_p = DT.record_to_dicts(rec[b], NAMES)
+        assert list(got_b) == list(want)
+        for k in want:
+            assert np.array_equal(got_b[k], want[k][0]) and np.array_equal(got_p[k], want[k][1])
+
+
+@pytest.mark.parametrize("name", sorted(F2_CASES))
+def test_final_nms_matches_reference_golden(mods, name):
+    RN, DT, _ = mods
+    g = _load_npz("f2_final_nms.npz")
+    b, p = f2_inputs(name)
+    net = RN.RADNet(_config(), None, None, lambda x: x)
+    nb, npb = net.final_nms(b, p)
+    assert nb.dtype == g[name + "/box"].dtype and np.array_equal(nb, g[name + "/box"])
+    assert npb.dtype == np.float32 and np.array_equal(npb, g[name + "/prob"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_final_nms_random_and_ties_vs_oracle(mods, seed):
+    RN, DT, _ = mods
+    rng = np.random.default_rng(seed)
+    ncl, per = int(rng.integers(1, 30)), int(rng.integers(1, 60))
+    b, p = S.clustered_boxes(100 + seed, ncl, per, 0.6, 1.0, ties=bool(seed % 2))
+    thr, conf, navg = [(0.2, 0.8, 5), (0.5, 0.9, 3), (0.05, 0.7, 1)][seed % 3]
+    net = RN.RADNet(_config(), None, None, lambda x: x)
+    nb, npb = net.final_nms(b, p, obj_avg_threshold=thr, obj_confidence_threshold=conf, n_obj_avg=navg)
+    ob, op = DO.final_nms(b, p, obj_avg_threshold=thr, obj_confidence_threshold=conf, n_obj_avg=navg)
+    assert np.array_equal(nb, ob) and np.array_equal(npb, op)
+    assert net.final_nms(np.zeros((0, 4)), np.zeros((0,))) == []
+    with pytest.raises(AssertionError):
+        net.final_nms(np.array([[5, 5, 5, 9]]), np.array([0.9], dtype=np.float32))
+
+
+@pytest.mark.parametrize("n_in,per", [(3, 100), (5, 400)])
+def test_class_nms_over_concatenated_records(mods, n_in, per):
+    """Cross-image NMS at 0.4 over several records (RADNet.py:695-716): the bit-matrix kernel up to
+    1024 boxes, the cluster kernel in plain-NMS mode beyond."""
+    RN, DT, torch = mods
+    rng = np.random.default_rng(n_in)
+    groups, all_c, all_p, all_b = [], [], [], []
+    for j in range(n_in):
+        b, p = S.clustered_boxes(200 + j, 10, per // 10, 0.5, 1.0)
+        c = rng.integers(0, 6, len(p)).astype(np.int32)
+        c = np.sort(c) if j % 2 else c            # grouped and ungrouped inputs
+        groups.append((c, p, b))
+        all_c.append(c); all_p.append(p); all_b.append(b)
+    rec_in = DT.ClassRecords.from_arrays(groups, per, torch.device("cuda"))
+    out = DT.class_nms(rec_in, 1, n_in, 7, 0.4, max_boxes=50).to_numpy()
+    DT.check_records(out, "test")
+    c, p, b = np.concatenate(all_c), np.concatenate(all_p), np.concatenate(all_b)
+    got_b, got_p = DT.record_to_dicts(out[0], NAMES)
+    first = []
+    for v in c:
+        if v not in first:
+            first.append(int(v))
+    assert [NAMES[v] for v in first] == list(got_b)
+    for v in first:
+        wb, wp = O.non_max_suppression_fast(b[c == v], p[c == v], overlap_thresh=0.4, max_boxes=50)
+        assert np.array_equal(got_b[NAMES[v]], wb) and np.array_equal(got_p[NAMES[v]], wp)
+
+
+@pytest.mark.parametrize("name", sorted(S.PREDICT_CASES))
+def test_predict_matches_reference_golden(mods, name):
+    pytest.importorskip("cv2")
+    RN, DT, _ = mods
+    g = _load_npz("f2_predict.npz")
+    C, images, make_models = S.predict_case(name)
+    m_rpn, m_det = make_models()
+    dets = RN.RADNet(C, m_rpn, m_det, lambda x: x).predict(images)
+    cls = np.asarray([C.class_mapping[d['class']] for d in dets], dtype=np.int64)
+    prob = np.asarray([d['prob'] for d in dets], dtype=np.float32)
+    box = np.asarray([[d['x1'], d['y1'], d['x2'], d['y2']] for d in dets], dtype=np.int64).reshape(-1, 4)
+    assert np.array_equal(cls, g[name + "/cls"])
+    assert np.array_equal(prob, g[name + "/prob"])
+    assert np.array_equal(box, g[name + "/box"])
+    assert [m_rpn.calls, m_det.calls] == list(g[name + "/calls"])
+    assert all(isinstance(d['prob'], np.float32) and isinstance(d['x1'], np.int64) for d in dets)
+
+
+def test_predict_degenerate_box_raises_like_the_reference(mods):
+    """A head that shrinks boxes to zero width makes the reference's NMS assert (rpn.py:400-401)."""
+    RN, DT, _ = mods
+    C = _config()
+    R = S.random_rois(0, 40)[0]
+    pc = np.zeros((1, 40, 7), np.float32); pc[..., 0] = 0.9; pc[..., 6] = 0.1
+    pr = np.zeros((1, 40, 24), np.float32); pr[..., 2] = -30.0 * 4.0          # tw = -30 -> w rounds to 0
+    rec = DT.classify_nms(pc, pr, C, rois=R[None].astype(np.int32)).to_numpy()
+    assert rec["header"][0, DT.H_NDEGEN] == 40
+    with pytest.raises(AssertionError):
+        DT.check_records(rec, "test")

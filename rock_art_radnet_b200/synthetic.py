@@ -207,9 +207,9 @@ class RandomHeadModel:
     deltas.  `extremes=True` plants what the reference's apply_regr handles through its `except`
     branches (exp overflow, inf, NaN deltas) and, when `nan_cls` is set, NaN class scores."""
 
-    def __init__(self, seed, C, n_cls=7, extremes=False, nan_cls=False, sharp=4.0):
+    def __init__(self, seed, C, n_cls=7, extremes=False, nan_cls=False, sharp=4.0, regr_scale=0.4):
         self.seed, self.C, self.n_cls = seed, C, n_cls
-        self.extremes, self.nan_cls, self.sharp = extremes, nan_cls, sharp
+        self.extremes, self.nan_cls, self.sharp, self.regr_scale = extremes, nan_cls, sharp, regr_scale
         self.calls = 0
 
     def predict(self, inputs):
@@ -226,7 +226,7 @@ class RandomHeadModel:
             z = rng.standard_normal(self.n_cls) * self.sharp
             e = np.exp(z - z.max())
             P_cls[0, i] = (e / e.sum()).astype(np.float32)
-            t = rng.standard_normal(4 * (self.n_cls - 1)) * 0.4
+            t = rng.standard_normal(4 * (self.n_cls - 1)) * self.regr_scale
             if self.extremes:
                 k = hsh % 11
                 if k == 0:

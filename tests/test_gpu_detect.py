@@ -81,7 +81,8 @@ def test_classify_nms_matches_oracle(mods, seed, n, ratio, origin):
     rois, pcs, prs = [], [], []
     for b in range(B):
         R = S.random_rois(10 * seed + b, n)[0]
-        model = S.RandomHeadModel(seed + 100 * b, C, sharp=2.0 + b) if b else \
+        R[:, 2:] = np.maximum(R[:, 2:], 3)            # with regr_scale 0.2 no box can shrink to zero width
+        model = S.RandomHeadModel(seed + 100 * b, C, sharp=2.0 + b, regr_scale=0.2) if b else \
             S.FakeDetectorModel(S.scene_objects(seed, 600, 600, n_obj=25, lo=40, hi=200), C)
         a, r = model.predict([np.zeros((1, 1, 1, 4), np.float32), R[None]])
         rois.append(R); pcs.append(a[0]); prs.append(r[0])
@@ -117,7 +118,7 @@ def test_classify_nms_from_detection_records(mods):
         R = dets[b]["boxes"].copy()
         R[:, 2] -= R[:, 0]
         R[:, 3] -= R[:, 1]
-        a, r = S.RandomHeadModel(b, C, sharp=3.0).predict([None, R[None]])
+        a, r = S.RandomHeadModel(b, C, sharp=3.0, regr_scale=0.1).predict([None, R[None]])
         pc = np.zeros((300, 7), np.float32); pr = np.zeros((300, 24), np.float32)
         pc[:len(R)] = a[0]; pr[:len(R)] = r[0]
         pcs.append(pc); prs.append(pr); rois.append(R)

@@ -216,3 +216,25 @@ def test_predict_degenerate_box_raises_like_the_reference(mods):
     assert rec["header"][0, DT.H_NDEGEN] == 40
     with pytest.raises(AssertionError):
         DT.check_records(rec, "test")
+
+
+def test_repeated_launches_are_bitwise_identical(mods):
+    """The cluster kernel pipelines a finaliser warp against the search warps and packs through a
+    last-CTA-done counter; any race there would show up as run-to-run differences."""
+    RN, DT, torch = mods
+    dev = torch.device("cuda")
+    groups = []
+    rng = np.random.default_rng(7)
+    for j in range(12):
+        b, p = S.clustered_boxes(300 + j, 25, 8, 0.6, 1.0)
+        groups.append((rng.integers(0, 6, len(p)).astype(np.int32), p, b))
+    rec_in = DT.ClassRecords.from_arrays(groups, 200, dev)
+    first_a = first_b = first_c = None
+    for _ in range(25):
+        a = DT.final_nms_records(rec_in, 3, 4, 7).raw.cpu().numpy()
+        b = DT.class_nms(rec_in, 2, 6, 7, 0.4).raw.cpu().numpy()            # 1200 boxes: cluster kernel, NMS mode
+        c = DT.class_nms(rec_in, 3, 4, 7, 0.3).raw.cpu().numpy()            # 800 boxes: bit-matrix kernel
+        if first_a is None:
+            first_a, first_b, first_c = a, b, c
+        assert np.array_equal(a, first_a) and np.array_equal(b, first_b) and np.array_equal(c, first_c)
+    assert (first_a.view(np.int32)[:, 0] > 0).all()

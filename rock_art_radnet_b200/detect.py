@@ -147,6 +147,8 @@ def classify_nms(P_cls, P_regr, C, rois=None, roi_count=None, det=None, bbox_thr
     ratio_d = _ratio_tensor(ratio, B, dev)
     origin_d = D.to_device(origin, np.int32, dev).reshape(B, 2) if origin is not None else None
     out = out if out is not None else ClassRecords(B, R, dev)
+    if out.n != B or out.max_det < 1:
+        raise ValueError("output records: %d records for %d tiles" % (out.n, B))
     _lib.call("radnet_classify_nms", D.ptr(P_cls), D.ptr(P_regr), B, R, n_cls, D.ptr(det_raw), det_k,
               D.ptr(rois), D.ptr(roi_count), float(bbox_threshold), D.ptr(std), stride, float(nms_thresh),
               int(max_boxes), D.ptr(ratio_d), D.ptr(origin_d), D.ptr(out.raw), out.max_det, D.stream_ptr(dev))
@@ -156,6 +158,9 @@ def classify_nms(P_cls, P_regr, C, rois=None, roi_count=None, det=None, bbox_thr
 def _ratio_tensor(ratio, n, dev):
     if ratio is None:
         return None
+    if D.is_cuda_tensor(ratio):          # resident (batched pipeline): the caller vouches for positive finite values
+        assert ratio.dtype == torch.float64 and ratio.numel() == n
+        return ratio.contiguous()
     r = np.asarray(ratio, dtype=np.float64).reshape(n)
     if not (np.isfinite(r).all() and (r > 0).all()):
         raise ZeroDivisionError("resize ratio must be finite and positive")
@@ -163,16 +168,17 @@ def _ratio_tensor(ratio, n, dev):
 
 
 def class_nms(records, n_segments, n_in, n_cls, thresh, max_boxes=300, ratio=None, origin=None, in_count=None,
-              out_max_det=None):
+              out_max_det=None, out=None, ws=None):
     """Per-class greedy NMS over the concatenation of `n_in` consecutive records per segment
     (rpn.py:380-456 applied per class: RADNet.py:574, 639, 698).  Returns ClassRecords (n_segments,)."""
     dev = records.raw.device
     assert records.n == n_segments * n_in
     cap = int(out_max_det) if out_max_det is not None else n_in * records.max_det
-    out = ClassRecords(n_segments, cap, dev)
+    out = out if out is not None else ClassRecords(n_segments, cap, dev)
     lib = _lib.load()
     ws_bytes = int(lib.radnet_class_nms_workspace_bytes(n_segments, n_in, records.max_det, n_cls))
-    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
     ratio_d = _ratio_tensor(ratio, n_segments, dev)
     origin_d = D.to_device(origin, np.int32, dev).reshape(n_segments, 2) if origin is not None else None
     cnt_d = D.to_device(in_count, np.int32, dev) if in_count is not None else None
@@ -183,16 +189,17 @@ def class_nms(records, n_segments, n_in, n_cls, thresh, max_boxes=300, ratio=Non
 
 
 def final_nms_records(records, n_segments, n_in, n_cls, obj_avg_threshold=0.2, obj_confidence_threshold=0.8,
-                      n_obj_avg=5, in_count=None, out_max_det=None):
+                      n_obj_avg=5, in_count=None, out_max_det=None, out=None, ws=None):
     """Cluster-and-average merge (RADNet.final_nms, RADNet.py:156-240) of `n_in` consecutive tile
     records per image, every class at once.  Returns ClassRecords (n_segments,)."""
     dev = records.raw.device
     assert records.n == n_segments * n_in
     cap = int(out_max_det) if out_max_det is not None else n_in * records.max_det
-    out = ClassRecords(n_segments, cap, dev)
+    out = out if out is not None else ClassRecords(n_segments, cap, dev)
     lib = _lib.load()
     ws_bytes = int(lib.radnet_final_nms_workspace_bytes(n_segments, n_in, records.max_det, n_cls))
-    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
     cnt_d = D.to_device(in_count, np.int32, dev) if in_count is not None else None
     _lib.call("radnet_final_nms", D.ptr(records.raw), records.max_det, n_segments, n_in, D.ptr(cnt_d), int(n_cls),
               float(obj_avg_threshold), float(obj_confidence_threshold), int(n_obj_avg), D.ptr(out.raw),

@@ -203,3 +203,38 @@ class HostPanelStream:
         s = self._pending.pop(0)
         self.done[s].synchronize()
         return self.rec_host[s]
+
+
+class DetectionPipeline(ProposalPipeline):
+    """ProposalPipeline plus the stages that follow the classifier head:
+
+        K1 -> K2 -> K4 -> [classifier head, user code on the same stream] -> K5+K6 fused
+        (radnet_classify_nms: head decode, per-class NMS at 0.2, real coordinates, tile offset)
+
+    and, once the records of all tiles of a panel are on one GPU (`sharding.gather_detections`
+    works on any fixed-size record), `merge`: K7 radnet_final_nms per image followed by the
+    cross-image per-class NMS at 0.4 (reference RADNet.py:566-716).  Every buffer is resident; nothing
+    synchronises."""
+
+    def __init__(self, C, batch, H, W, n_cls=None, bbox_threshold=0.7, **kw):
+        super().__init__(C, batch, H, W, **kw)
+        from . import detect as DT
+        self._DT = DT
+        self.n_cls = int(n_cls if n_cls is not None else len(C.class_mapping))
+        self.bbox_threshold = float(bbox_threshold)
+        self.class_records = DT.ClassRecords(self.batch, self.max_boxes, self.device)
+
+    def classify(self, P_cls, P_regr, ratio=None, origin=None, nms_thresh=0.2):
+        """P_cls (B,max_boxes,n_cls), P_regr (B,max_boxes,4(n_cls-1)) float32 CUDA tensors for the kept
+        boxes of `self.records` (rows >= count are ignored); ratio (B,) / origin (B,2) optional."""
+        return self._DT.classify_nms(P_cls, P_regr, self.C, det=self.records, bbox_threshold=self.bbox_threshold,
+                                     nms_thresh=nms_thresh, max_boxes=300, ratio=ratio, origin=origin,
+                                     out=self.class_records)
+
+    def merge(self, tile_records, n_images, tiles_per_image, final_thresh=0.4):
+        """tile_records: ClassRecords of n_images * tiles_per_image tiles in (image, tile) order.
+        Returns (per-image merged ClassRecords, final ClassRecords(1)) - RADNet.py:672, 698."""
+        DT = self._DT
+        merged = DT.final_nms_records(tile_records, n_images, tiles_per_image, self.n_cls)
+        final = DT.class_nms(merged, 1, n_images, self.n_cls, final_thresh, max_boxes=300)
+        return merged, final

@@ -60,6 +60,32 @@ def time_ms(fn, iters=20, warmup=3, flush=True):
     return {"p50_ms": ts[len(ts) // 2], "min_ms": ts[0], "p95_ms": ts[max(0, int(len(ts) * 0.95) - 1)]}
 
 
+def time_graph_ms(fn, reps=20, iters=10, warmup=2):
+    """GPU time of one call for kernels shorter than the Python launch path: `reps` calls are captured
+    into a CUDA graph on a side stream and the graph is replayed; returns per-call figures."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        fn()
+        st.synchronize()
+        with torch.cuda.graph(graph, stream=st):
+            for _ in range(reps):
+                fn()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) / reps)
+    ts.sort()
+    return {"p50_ms": ts[len(ts) // 2], "min_ms": ts[0], "how": "CUDA graph of %d back-to-back calls (L2 warm)" % reps}
+
+
 def tile_maps(B, H=38, W=38, A=9):
     base = [S.rpn_maps(s, H, W, A) for s in range(8)]
     cls = np.concatenate([base[i % 8][0] for i in range(B)])
@@ -152,6 +178,60 @@ def main():
     for _ in range(10):
         R.calc_region_props(C, img, 600, 600, 600, 600, S.resnet50_map_size)
     res["calc_region_props_dropin_wall_ms"] = (time.perf_counter() - t0) / 10 * 1e3
+
+    # ---- f1/f2: detection post-processing (K5+K6 fused, K7, cross-image NMS) -------------------
+    from rock_art_radnet_b200 import detect as DT
+    from rock_art_radnet_b200.pipeline import DetectionPipeline
+
+    def head_outputs(B, R, seed, frac_fg=0.25):
+        """Random classifier-head outputs: about frac_fg of the RoIs clear the 0.7 threshold."""
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        logits = torch.randn((B, R, 7), device="cuda", generator=g) * 1.5
+        logits[..., 6] += 1.0
+        boost = torch.rand((B, R, 1), device="cuda", generator=g) < frac_fg
+        pick = torch.randint(0, 6, (B, R, 1), device="cuda", generator=g)
+        logits.scatter_add_(2, pick, boost.float() * 6.0)
+        return torch.softmax(logits, dim=-1).contiguous(), (torch.randn((B, R, 24), device="cuda", generator=g) * 0.8).contiguous()
+
+    for B in (1, 64, 512):
+        cls, regr = tile_maps(B)
+        dp = DetectionPipeline(C, B, 38, 38, alloc_pooled=False)
+        dp.decode(cls, regr)
+        dp.sort_nms()
+        P_cls, P_regr = head_outputs(B, 300, B)
+        ratio = torch.ones((B,), dtype=torch.float64, device="cuda")
+        origin = torch.zeros((B, 2), dtype=torch.int32, device="cuda")
+        t = time_graph_ms(lambda: dp.classify(P_cls, P_regr, ratio=ratio, origin=origin))
+        hdr = dp.class_records.header.cpu().numpy()
+        res["classify_nms_B%d" % B] = dict(t, kept_per_tile=float(hdr[:, 0].mean()), candidates_per_tile=300,
+                                            degenerate=int(hdr[:, 2].sum()))
+        dec_out = DT.ClassRecords(B, 300, "cuda")
+        t = time_graph_ms(lambda: DT.classify_decode(P_cls, P_regr, C, det=dp.records, out=dec_out))
+        res["classify_decode_B%d" % B] = t
+        if B == 64:
+            # BASELINE configs[3]: 36 tiles per 1600-px panel -> one merge per panel; here 1 panel of 36 and 16 of 4
+            tiles36 = DT.ClassRecords(36, 300, "cuda", raw=dp.class_records.raw[:36].clone())
+            ws = torch.empty((64 << 20,), dtype=torch.uint8, device="cuda")
+
+            def bench_merge(tag, fn_make):
+                out_holder = {}
+
+                def fn():
+                    out_holder["o"] = fn_make(out_holder.get("o"))
+                fn()
+                res[tag] = time_graph_ms(fn, reps=10)
+                return out_holder["o"]
+
+            o = bench_merge("final_nms_1x36_tiles", lambda o: DT.final_nms_records(tiles36, 1, 36, 7, out=o, ws=ws))
+            res["final_nms_1x36_tiles"].update(boxes_in=int(hdr[:36, 0].sum()), clusters_out=int(o.header[0, 0].item()))
+            merged = bench_merge("final_nms_16x4_tiles", lambda o: DT.final_nms_records(dp.class_records, 16, 4, 7, out=o, ws=ws))
+            res["final_nms_16x4_tiles"].update(boxes_in=int(hdr[:, 0].sum()), clusters_out=int(merged.header[:, 0].sum().item()))
+            o = bench_merge("class_nms_cross_image_16", lambda o: DT.class_nms(merged, 1, 16, 7, 0.4, out=o, ws=ws))
+            res["class_nms_cross_image_16"].update(kept=int(o.header[0, 0].item()), capacity=16 * merged.max_det)
+            small = DT.ClassRecords(3, 300, "cuda", raw=dp.class_records.raw[:3].clone())
+            o = bench_merge("class_nms_matrix_3x300", lambda o: DT.class_nms(small, 1, 3, 7, 0.4, out=o, ws=ws))
+            res["class_nms_matrix_3x300"].update(kept=int(o.header[0, 0].item()))
+        del dp
 
     # ---- K4 ----------------------------------------------------------------------------
     for (B, Cn, pool, tag, Hh, Ww) in ((64, 1024, 14, "resnet50", 38, 38), (64, 512, 7, "vgg16", 38, 38),

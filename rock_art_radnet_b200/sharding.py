@@ -67,3 +67,52 @@ def split_gathered(gathered, n_panels, max_boxes):
     dets = rec.to_numpy()
     order = global_order(n_panels, world, per_rank)
     return [dets[int(j)] for j in order]
+
+
+def gathered_to_global(gathered, n_items):
+    """(world, per_rank, stride) gathered records -> (n_items, stride) in GLOBAL item order
+    (item i lives on rank i % world, slot i // world); padded slots are dropped.  Stays on the
+    device of `gathered` (one index_select), so the merge kernels can consume it directly."""
+    world, per_rank = int(gathered.shape[0]), int(gathered.shape[1])
+    order = torch.from_numpy(global_order(n_items, world, per_rank)).to(gathered.device)
+    return gathered.reshape(world * per_rank, -1).index_select(0, order).contiguous()
+
+
+class TiledPanelSharder:
+    """Tiles of tiled panels (reference RADNet.py:511-604: every tile is an independent 600-px
+    image until `final_nms`) spread over the ranks, tile i -> rank i % world.
+
+    Each rank runs decode -> NMS -> RoI pool -> [head] -> head decode + per-class NMS on its own
+    tiles (`DetectionPipeline`), the fixed-size labelled detection records are all-gathered over
+    NCCL (9.9 KB per tile for 300 slots), brought into global tile order on the device and
+    merged per panel (K7 final_nms + per-class NMS at 0.4) - every rank ends up with every
+    panel's detections, which is what an all-gather means.  With world == 1 the same code runs
+    without a process group."""
+
+    def __init__(self, n_panels, tiles_per_panel, rank=None, world=None, group=None):
+        self.group = group
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rank, self.world = int(rank), int(world)
+        self.n_panels, self.tiles_per_panel = int(n_panels), int(tiles_per_panel)
+        self.n_tiles = self.n_panels * self.tiles_per_panel
+        self.local_ids = shard_indices(self.n_tiles, self.rank, self.world)
+        self.per_rank = max(shard_sizes(self.n_tiles, self.world))
+
+    def local_slots(self):
+        """(global tile ids of this rank, number of padding slots at the end of its batch)."""
+        return self.local_ids, self.per_rank - len(self.local_ids)
+
+    def gather_tiles(self, class_records_raw, async_op=False):
+        """class_records_raw: (per_rank, stride) uint8 of this rank (padding slots must hold empty
+        records).  Returns ((n_tiles, stride) tensor-or-None, work): with async_op the tensor is
+        produced by `finish`."""
+        gathered, work = gather_detections(class_records_raw, group=self.group, async_op=async_op)
+        if work is not None and async_op:
+            return gathered, work
+        return gathered_to_global(gathered, self.n_tiles), None
+
+    def finish(self, gathered, work):
+        work.wait()
+        return gathered_to_global(gathered, self.n_tiles)

@@ -292,3 +292,29 @@ def predict_case(name, config_cls=HotPathConfig):
         return FakeRpnModel(seed=seed), FakeDetectorModel(objs, C)
 
     return C, images, make_models
+
+
+def tiled_panel_tiles(width, height, tile_size=600, step=200):
+    """Tile rectangles [x0,y0,x1,y1] of one panel, same rule as the reference (RADNet.py:511-540)."""
+    def axis(length):
+        pairs = {(s, s + tile_size) for s in range(0, length, step) if s + tile_size <= length}
+        pairs.add((max(0, length - tile_size), length))
+        return sorted(pairs)
+    return [[x0, y0, x1, y1] for (y0, y1) in axis(height) for (x0, x1) in axis(width)]
+
+
+def tiled_panel_head_outputs(C, panel_seed, tile, rois_xywh, n_slots=300, n_obj=30):
+    """Classifier-head outputs for the kept RoIs of one tile of a synthetic tiled panel: scores from
+    the overlap with the panel's `scene_objects` (so neighbouring tiles detect the same figures and
+    the tile merge has clusters), padded with zeros to n_slots rows.  Returns (P_cls (n_slots,7),
+    P_regr (n_slots,24)) float32."""
+    objs = scene_objects(panel_seed, 1600, 1600, n_obj=n_obj, lo=60, hi=300)
+    model = FakeDetectorModel(objs, C)
+    F = np.zeros((1, 1, 1, 4), dtype=np.float32)
+    F[0, 0, 0, :2] = (tile[0], tile[1])
+    a, r = model.predict([F, np.asarray(rois_xywh)[None]])
+    n = a.shape[1]
+    P_cls = np.zeros((n_slots, a.shape[2]), dtype=np.float32)
+    P_regr = np.zeros((n_slots, r.shape[2]), dtype=np.float32)
+    P_cls[:n], P_regr[:n] = a[0], r[0]
+    return P_cls, P_regr

@@ -238,3 +238,64 @@ def test_repeated_launches_are_bitwise_identical(mods):
             first_a, first_b, first_c = a, b, c
         assert np.array_equal(a, first_a) and np.array_equal(b, first_b) and np.array_equal(c, first_c)
     assert (first_a.view(np.int32)[:, 0] > 0).all()
+
+
+def _oracle_panel(C, tiles, rois, pcs, prs):
+    """Reference flow for one tiled panel: per-tile detections -> final_nms per class -> NMS 0.4."""
+    bbox_total, probs_total = {}, {}
+    for t, tile in enumerate(tiles):
+        n = len(rois[t])
+        for name, (bx, pb) in DO.tile_detections(rois[t], pcs[t][:n], prs[t][:n], C, 1.0, (tile[0], tile[1]), NAMES).items():
+            bbox_total.setdefault(name, []).extend(bx.tolist())
+            probs_total.setdefault(name, []).extend(list(pb))
+    out = {}
+    for name in bbox_total:
+        nb, npb = DO.final_nms(np.array(bbox_total[name]), np.array(probs_total[name]))
+        out[name] = O.non_max_suppression_fast(nb, npb, overlap_thresh=0.4)
+    return out
+
+
+@pytest.mark.parametrize("width,height,n_panels", [(1000, 800, 2), (1600, 1600, 1)])
+def test_tiled_panel_pipeline_end_to_end(mods, width, height, n_panels):
+    """BASELINE configs[3] shape: tiles of a tiled panel through decode -> NMS -> head decode ->
+    per-class NMS -> (gather) -> final_nms -> NMS 0.4, all on the device, against the oracle."""
+    RN, DT, torch = mods
+    from rock_art_radnet_b200 import sharding
+    from rock_art_radnet_b200.pipeline import DetectionPipeline
+    C = _config()
+    tiles = S.tiled_panel_tiles(width, height)
+    T = len(tiles)
+    shard = sharding.TiledPanelSharder(n_panels, T, rank=0, world=1)
+    B = shard.per_rank
+    pipe = DetectionPipeline(C, B, 38, 38, alloc_pooled=False)
+    maps = [S.rpn_maps(1000 * p + t) for p in range(n_panels) for t in range(T)]
+    pipe.decode(torch.from_numpy(np.concatenate([m[0] for m in maps])).cuda(),
+                torch.from_numpy(np.concatenate([m[1] for m in maps])).cuda())
+    pipe.sort_nms()
+    dets = pipe.records.to_numpy()
+    rois, pcs, prs = [], [], []
+    for i in range(B):
+        R = dets[i]["boxes"].copy()
+        R[:, 2] -= R[:, 0]
+        R[:, 3] -= R[:, 1]
+        pc, pr = S.tiled_panel_head_outputs(C, i // T, tiles[i % T], R)
+        rois.append(R); pcs.append(pc); prs.append(pr)
+    origin = torch.tensor([[tiles[i % T][0], tiles[i % T][1]] for i in range(B)], dtype=torch.int32, device="cuda")
+    ratio = torch.ones((B,), dtype=torch.float64, device="cuda")
+    pipe.classify(torch.from_numpy(np.stack(pcs)).cuda(), torch.from_numpy(np.stack(prs)).cuda(), ratio=ratio, origin=origin)
+    glob, _ = shard.gather_tiles(pipe.class_records.raw)
+    tile_rec = DT.ClassRecords(n_panels * T, pipe.max_boxes, glob.device, raw=glob)
+    merged = DT.final_nms_records(tile_rec, n_panels, T, pipe.n_cls)
+    final = DT.class_nms(merged, n_panels, 1, pipe.n_cls, 0.4).to_numpy()
+    DT.check_records(tile_rec.to_numpy(), "tiles")
+    DT.check_records(final, "final")
+    n_clustered = 0
+    for p in range(n_panels):
+        sl = slice(p * T, (p + 1) * T)
+        want = _oracle_panel(C, tiles, rois[sl], pcs[sl], prs[sl])
+        got_b, got_p = DT.record_to_dicts(final[p], NAMES)
+        assert list(got_b) == list(want) and len(want) > 0
+        for k in want:
+            assert np.array_equal(got_b[k], want[k][0]) and np.array_equal(got_p[k], want[k][1])
+        n_clustered += int((merged.to_numpy()[p]["entry"]["aux"] > 1).sum())
+    assert n_clustered > 0          # neighbouring tiles really produced multi-member clusters

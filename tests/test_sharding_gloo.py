@@ -65,3 +65,37 @@ def test_gather_without_process_group_is_identity():
     raw = torch.arange(2 * 40, dtype=torch.uint8).reshape(2, 40)
     g, work = sharding.gather_detections(raw)
     assert work is None and g.shape == (1, 2, 40) and torch.equal(g[0], raw)
+
+
+def _tile_worker(rank, world, port, n_panels, tiles_per_panel, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rock_art_radnet_b200 import sharding
+    shard = sharding.TiledPanelSharder(n_panels, tiles_per_panel)
+    ids, pad = shard.local_slots()
+    stride = 48
+    raw = torch.zeros((shard.per_rank, stride), dtype=torch.uint8)
+    for slot, t in enumerate(ids):
+        raw[slot] = int(t) % 251                      # record bytes encode the global tile id
+    raw[len(ids):] = 255                              # padding slots must be dropped by the reorder
+    glob, _ = shard.gather_tiles(raw)
+    g2, work = shard.gather_tiles(raw, async_op=True)
+    glob2 = shard.finish(g2, work)
+    ok = tuple(glob.shape) == (n_panels * tiles_per_panel, stride) and torch.equal(glob, glob2)
+    ok &= glob[:, 0].tolist() == [t % 251 for t in range(n_panels * tiles_per_panel)]
+    ok &= len(ids) + pad == shard.per_rank
+    np.save(os.path.join(out_dir, "tile_ok_%d.npy" % rank), np.array([int(ok)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_panels,tiles_per_panel", [(1, 36), (3, 7)])
+def test_tiled_panel_sharder_world2_gloo(tmp_path, n_panels, tiles_per_panel):
+    """Tiles of tiled panels (BASELINE configs[3]: 36 tiles of a 1600-px panel) over 2 ranks: gather +
+    reorder to global tile order, padding slots dropped, blocking and asynchronous forms agree."""
+    port = _free_port()
+    mp.spawn(_tile_worker, args=(2, port, n_panels, tiles_per_panel, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(tmp_path / ("tile_ok_%d.npy" % r))[0] == 1

@@ -132,6 +132,56 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
         : "memory");
 }
 
+// ---- thread-block cluster helpers (distributed shared memory) -------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t cluster_map_shared(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// split cluster barrier: every thread of every CTA arrives once and waits once per phase
+__device__ __forceinline__ void cluster_arrive() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier of another CTA of the cluster and announce `bytes` of bulk-copy traffic
+__device__ __forceinline__ void mbar_remote_arrive_expect_tx(uint32_t remote_bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote_bar),
+                 "r"(bytes)
+                 : "memory");
+}
+// shared memory of this CTA -> shared memory of another CTA of the cluster, completion on ITS mbarrier
+__device__ __forceinline__ void bulk_s2s_cluster(uint32_t remote_dst, const void *local_src, uint32_t bytes,
+                                                 uint32_t remote_bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst),
+        "r"(smem_u32(local_src)), "r"(bytes), "r"(remote_bar)
+        : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (bulk copies)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// all threads of all CTAs of the cluster; release/acquire makes the DSMEM stores visible
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // streaming 16-byte store: written once, never re-read by this kernel
 __device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),

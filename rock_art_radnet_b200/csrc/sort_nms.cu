@@ -132,6 +132,7 @@ struct SortNmsParams {
     int table_entries;        // i32 only: umax + 1
     int sel_target;           // candidates the first (selective) sort round aims for
     int look_ahead;           // rows that may run ahead of the retiring row in the NMS hand-off
+    int cluster_ranks;        // cluster form: top ranks resolved through the cluster-wide overlap matrix
     // outputs
     unsigned char *det;       // i32: detection records
     size_t det_stride;
@@ -265,6 +266,41 @@ __device__ __forceinline__ void atomic_max_key(uint64_t *a, uint64_t v) {
     atomicMax(reinterpret_cast<unsigned long long *>(a), (unsigned long long)v);
 }
 
+// number of valid (non-zero) keys and their min / max -> s_sel[0], s_minmax[0..1]
+template <typename KeyT>
+__device__ void key_stats(const KeyT *keys, int N, int *s_sel, KeyT *s_minmax) {
+    const int lane = threadIdx.x & 31;
+    int c = 0;
+    KeyT mn = KeyInfo<KeyT>::max, mx = 0;
+    for (int i = threadIdx.x; i < N; i += kNmsThreads) {
+        const KeyT k = keys[i];
+        if (k) {
+            ++c;
+            mn = k < mn ? k : mn;
+            mx = k > mx ? k : mx;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const KeyT on = __shfl_xor_sync(0xffffffffu, mn, d), ox = __shfl_xor_sync(0xffffffffu, mx, d);
+        mn = on < mn ? on : mn;
+        mx = ox > mx ? ox : mx;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (threadIdx.x == 0) {
+        s_sel[0] = 0;
+        s_minmax[0] = KeyInfo<KeyT>::max;
+        s_minmax[1] = 0;
+    }
+    __syncthreads();
+    if (lane == 0 && c) {
+        atomicAdd(&s_sel[0], c);
+        atomic_min_key(&s_minmax[0], mn);
+        atomic_max_key(&s_minmax[1], mx);
+    }
+    __syncthreads();
+}
+
 // SELECT: a threshold t (>= 1) with count(key >= t) >= target and only a small bucket of extra
 // keys.  256-ary search on the key VALUE range: per-warp 256-bin histograms of (key - lo) >> shift
 // (shared-memory RED, no returns), column sums, a suffix scan by warp 0 from the top bin; the
@@ -275,38 +311,7 @@ template <typename KeyT>
 __device__ KeyT select_threshold(const KeyT *keys, int N, int target, uint32_t *s_cnt, uint32_t *s_hist,
                                  int *s_sel, KeyT *s_minmax, int &M, int &S) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // valid count, min and max key
-    {
-        int c = 0;
-        KeyT mn = KeyInfo<KeyT>::max, mx = 0;
-        for (int i = threadIdx.x; i < N; i += kNmsThreads) {
-            const KeyT k = keys[i];
-            if (k) {
-                ++c;
-                mn = k < mn ? k : mn;
-                mx = k > mx ? k : mx;
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const KeyT on = __shfl_xor_sync(0xffffffffu, mn, d), ox = __shfl_xor_sync(0xffffffffu, mx, d);
-            mn = on < mn ? on : mn;
-            mx = ox > mx ? ox : mx;
-        }
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (threadIdx.x == 0) {
-            s_sel[0] = 0;
-            s_minmax[0] = KeyInfo<KeyT>::max;
-            s_minmax[1] = 0;
-        }
-        __syncthreads();
-        if (lane == 0 && c) {
-            atomicAdd(&s_sel[0], c);
-            atomic_min_key(&s_minmax[0], mn);
-            atomic_max_key(&s_minmax[1], mx);
-        }
-        __syncthreads();
-    }
+    key_stats<KeyT>(keys, N, s_sel, s_minmax);
     M = s_sel[0];
     KeyT lo = s_minmax[0], hi = s_minmax[1];
     S = M;
@@ -374,6 +379,112 @@ __device__ KeyT select_threshold(const KeyT *keys, int N, int target, uint32_t *
     return lo;
 }
 
+// SELECT, hot-path form (uint32 keys staged in shared memory): the same value-range search with ONE
+// 2048-bin block histogram per round (shared-memory RED; 13k keys leave ~6 per bin, so the first round
+// already isolates the target rank to a bucket far smaller than the slack) and a block scan from the
+// top bin.  Equal keys pile onto one counter, which is slower but still correct.
+constexpr int kWideBins = 2048;
+__device__ uint32_t select_threshold_wide(const uint32_t *keys, int N, int target, uint32_t *s_hist2k,
+                                          int *s_scan, int *s_sel, uint32_t *s_minmax, int &M, int &S) {
+    key_stats<uint32_t>(keys, N, s_sel, s_minmax);
+    M = s_sel[0];
+    uint32_t lo = s_minmax[0], hi = s_minmax[1];
+    S = M;
+    if (M <= target) return 1u;
+    int above = 0, need = target, inb = M;
+    const int slack = max(target >> 3, 1);
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const uint32_t range = hi - lo;
+        if (range == 0) break;
+        const int bits = 32 - __clz((int)range);
+        const int shift = bits > 11 ? bits - 11 : 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kWideBins; i += kNmsThreads) s_hist2k[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += kNmsThreads) {
+            const uint32_t k = keys[i];
+            if (k >= lo && k <= hi) atomicAdd(&s_hist2k[(k - lo) >> shift], 1u);
+        }
+        __syncthreads();
+        // thread t owns bins 2047-2t and 2046-2t: thread order = descending key order
+        const int b0 = kWideBins - 1 - 2 * (int)threadIdx.x;
+        const int c0 = (int)s_hist2k[b0], c1 = (int)s_hist2k[b0 - 1];
+        int total;
+        int abv = block_exscan(c0 + c1, s_scan, &total);           // keys in higher bins
+        if (abv < need && need <= abv + c0 + c1) {                 // exactly one thread
+            int b = b0, cnt = c0;
+            if (abv + c0 < need) { b = b0 - 1; cnt = c1; abv += c0; }
+            s_sel[1] = b; s_sel[2] = abv; s_sel[3] = cnt;
+        }
+        __syncthreads();
+        const int b = s_sel[1];
+        above += s_sel[2];
+        need -= s_sel[2];
+        inb = s_sel[3];
+        const uint32_t nlo = lo + ((uint32_t)b << shift);
+        const uint32_t span = (1u << shift) - 1u;
+        hi = (hi - nlo > span) ? nlo + span : hi;
+        lo = nlo;
+        if (shift == 0 || inb <= slack) break;
+    }
+    S = above + inb;
+    return lo;
+}
+
+// SORT, hot-path form: bucket sort of the selected keys by value.  A 2048-bin histogram over [t, max]
+// holds about one key per bin, a block scan from the top bin turns it into descending start offsets,
+// every selected key is scattered into its bucket as a (key << 32 | position) word and each thread
+// orders its two buckets (descending, i.e. higher position first among equal keys) by insertion.
+// Returns the number of sorted words, or -1 when a bucket is too crowded for this scheme (many nearly
+// equal scores) - the caller then takes the general radix path.
+constexpr int kBucketMax = 24;
+__device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_t hi, unsigned long long *out,
+                                int cap, uint32_t *s_hist2k, int *s_start, int *s_scan, int *s_flag) {
+    const uint32_t range = hi - t;
+    const int bits = range ? 32 - __clz((int)range) : 0;
+    const int shift = bits > 11 ? bits - 11 : 0;
+    for (int i = threadIdx.x; i < kWideBins; i += kNmsThreads) s_hist2k[i] = 0;
+    if (threadIdx.x == 0) *s_flag = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += kNmsThreads) {
+        const uint32_t k = keys[i];
+        if (k >= t) atomicAdd(&s_hist2k[(k - t) >> shift], 1u);
+    }
+    __syncthreads();
+    const int b0 = kWideBins - 1 - 2 * (int)threadIdx.x;           // thread order = descending key order
+    const int c0 = (int)s_hist2k[b0], c1 = (int)s_hist2k[b0 - 1];
+    int total;
+    const int ex = block_exscan(c0 + c1, s_scan, &total);
+    s_start[b0] = ex;
+    s_start[b0 - 1] = ex + c0;
+    if (c0 > kBucketMax || c1 > kBucketMax || total > cap) *s_flag = 1;
+    __syncthreads();
+    if (*s_flag) return -1;
+    for (int i = threadIdx.x; i < N; i += kNmsThreads) {
+        const uint32_t k = keys[i];
+        if (k >= t) {
+            const uint32_t b = (k - t) >> shift;
+            const int slot = (int)atomicSub(&s_hist2k[b], 1u) - 1;
+            out[s_start[b] + slot] = ((unsigned long long)k << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        unsigned long long *a = out + (q ? ex + c0 : ex);
+        const int n = q ? c1 : c0;
+        for (int i = 1; i < n; ++i) {
+            const unsigned long long v = a[i];
+            int j = i - 1;
+            while (j >= 0 && a[j] < v) { a[j + 1] = a[j]; --j; }
+            a[j + 1] = v;
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
 // order-preserving compaction of the keys >= t with their positions; returns the count
 template <typename KeyT, typename IdxT>
 __device__ int compact_ge(const KeyT *keys, int N, KeyT t, KeyT *out_k, IdxT *out_i, int *s_scan) {
@@ -439,7 +550,7 @@ __device__ __forceinline__ bool suppressed_by(const typename Traits::Cand *kept,
     return hit;
 }
 
-template <typename Traits, typename KeyT, typename IdxT, bool kSmemSort, bool kKeptSmem>
+template <typename Traits, typename KeyT, typename IdxT, bool kSmemSort, bool kKeptSmem, bool kCluster = false>
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams p) {
     using Cand = typename Traits::Cand;
     constexpr bool kI32 = sizeof(Cand) == sizeof(int4);
@@ -447,11 +558,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);                 // TMA barrier
+    uint64_t *s_lbar = reinterpret_cast<uint64_t *>(smem + 8);            // cluster form: matrix blocks landed (leader)
     int *s_misc = reinterpret_cast<int *>(smem + 16);                     // 16 ints
     int *s_scan = reinterpret_cast<int *>(smem + 96);                     // 34 ints
     uint64_t *s_turn = reinterpret_cast<uint64_t *>(smem + 256);          // [32] hand-off barriers
     KeyT *s_minmax = reinterpret_cast<KeyT *>(smem + 512);                // [2]
     volatile int *s_kafter = reinterpret_cast<volatile int *>(smem + 1536);   // [32] kept count after row w
+    volatile int *s_kmask = reinterpret_cast<volatile int *>(smem + 1792);    // [32] cluster form: lanes kept per group of 32 ranks
+    volatile int *s_ready = s_misc + 9;                                       // cluster form: groups published so far
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + p.sm_off_cnt);  // [32][257]
     volatile int *s_kcount = s_misc + 0;
     int *s_flag = s_misc + 2;
@@ -460,7 +574,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + 2048);         // [256]
     volatile int *s_fault = s_misc + 8;
 
-    const int seg = blockIdx.x;
+    // cluster form: the CTAs of one cluster share a panel; rank 0 leads, the others help with the
+    // overlap matrix of the first ranks and then leave
+    const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
+    const uint32_t csize = kCluster ? cluster_nctarank() : 1u;
+    const int seg = kCluster ? (int)(blockIdx.x / csize) : (int)blockIdx.x;
     const int N = p.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const KeyT *g_keys = reinterpret_cast<const KeyT *>(p.keys) + (size_t)seg * N;
@@ -485,7 +603,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
 #ifdef RADNET_NMS_PROFILE
     long long *prof = reinterpret_cast<long long *>(ws + p.ws_off_kept + 32768);
     int prof_n = 0;
-#define NMS_STAMP() do { __syncthreads(); if (threadIdx.x == 0 && prof_n < 16) prof[prof_n] = clock64(); ++prof_n; } while (0)
+#define NMS_STAMP() do { __syncthreads(); if (threadIdx.x == 0 && prof_n < 16 && crank == 0) prof[prof_n] = clock64(); ++prof_n; } while (0)
 #define NMS_ROW_STAMP(k) do { if (lane == 0 && tile_no == 0) prof[16 + w * 8 + (k)] = clock64(); } while (0)
 #else
 #define NMS_STAMP() do {} while (0)
@@ -496,11 +614,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         *s_kcount = 0;
         *s_ties = 0;
         *s_fault = 0;
+        s_misc[9] = 0;
         mbar_init(s_bar, 1);
         for (int i = 0; i < kNmsWarps; ++i) mbar_init(&s_turn[i], 1);
+        if (kCluster) mbar_init(s_lbar, csize);       // one arrival per CTA of the cluster (matrix blocks)
         mbar_fence_init();
     }
     __syncthreads();
+    // cluster form, split barrier phase A: "my barriers exist" - waited for right before the first
+    // access to another CTA's shared memory, by which time everybody has long arrived
+    if constexpr (kCluster) cluster_arrive();
 
     // ---- stage 0: raw keys -> shared memory (one TMA bulk copy on the hot path) ----------
     const KeyT *raw_k = g_keys;
@@ -555,12 +678,45 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     int tile_no = 0;
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
-        // ---- stage 1: select + compact ---------------------------------------------------
+        // ---- stage 1 + 2: select, compact, sort --------------------------------------------
+        const KeyT *in_k = nullptr;
+        const IdxT *in_i = nullptr;
+        bool sorted_fast = false;
+        const unsigned long long *sk_sorted = nullptr;      // hot path: descending (key, position) words
+        if constexpr (kSmemSort && sizeof(KeyT) == 4) {
+            if (round == 0) {
+                // hot path: wide-histogram select, then a value-bucket sort of the selected keys into the
+                // free ping-pong buffer as (key, position) words in descending order
+                // the sorted words live in the second index buffer; the second key buffer and the first index
+                // buffer (contiguous, untouched by select and sort) hold the cluster overlap matrix
+                unsigned long long *sk = reinterpret_cast<unsigned long long *>(iB);
+                const int sk_cap = (int)((size_t)p.sort_cap * sizeof(IdxT) / 8);
+                uint32_t *hist = reinterpret_cast<uint32_t *>(s_cnt);
+                const KeyT thr_key = select_threshold_wide(raw_k, N, p.sel_target, hist, s_scan, s_sel, s_minmax, M, S);
+                K = min(p.max_boxes, M);
+                NMS_STAMP();     // 2: threshold selected
+                const int got = bucket_sort_desc(raw_k, N, thr_key, s_minmax[1], sk, sk_cap, hist,
+                                                 reinterpret_cast<int *>(hist + kWideBins), s_scan, s_flag);
+                NMS_STAMP();     // 3: (compacted)
+                if (got >= 0) {
+                    S = got;
+                    sk_sorted = sk;
+                    sorted_fast = true;
+                } else {
+                    s_sel[1] = (int)thr_key;      // crowded buckets: general path below, same threshold
+                }
+            }
+        }
+        if (!sorted_fast) {
         KeyT thr_key = (KeyT)1;
         if (round == 0) {
-            thr_key = select_threshold<KeyT>(raw_k, N, p.sel_target, s_cnt, s_hist, s_sel, s_minmax, M, S);
-            K = min(p.max_boxes, M);
-            NMS_STAMP();     // 2: threshold selected
+            if constexpr (kSmemSort && sizeof(KeyT) == 4) {
+                thr_key = (KeyT)s_sel[1];
+            } else {
+                thr_key = select_threshold<KeyT>(raw_k, N, p.sel_target, s_cnt, s_hist, s_sel, s_minmax, M, S);
+                K = min(p.max_boxes, M);
+                NMS_STAMP();     // 2: threshold selected
+            }
         } else if (kSmemSort) {
             // the ping-pong buffers overwrote the staged keys: fetch them again
             for (int i = threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
@@ -573,9 +729,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         if (round == 1) M = S;
         NMS_STAMP();         // 3: compacted
 
-        // ---- stage 2: stable LSD radix sort of the slice -----------------------------------
-        const KeyT *in_k = ck;
-        const IdxT *in_i = ci;
+        // ---- stable LSD radix sort of the slice ------------------------------------------
+        in_k = ck;
+        in_i = ci;
         KeyT *out_k = (ck == kA) ? kB : kA;
         IdxT *out_i = (ci == iA) ? iB : iA;
         if (S > 1) {
@@ -595,6 +751,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                 }
             }
         }
+        }
         // in_k / in_i: S entries ascending by (score, flat index)
         NMS_STAMP();         // 4: sorted
 
@@ -604,8 +761,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             __syncthreads();
             int t = 0;
             for (int i = threadIdx.x; i < S; i += kNmsThreads) {
-                KeyT k = in_k[i];
-                bool tie = (i > 0 && in_k[i - 1] == k) || (i + 1 < S && in_k[i + 1] == k);
+                bool tie;
+                if (sorted_fast) {
+                    const uint32_t k = (uint32_t)(sk_sorted[i] >> 32);
+                    tie = (i > 0 && (uint32_t)(sk_sorted[i - 1] >> 32) == k) ||
+                          (i + 1 < S && (uint32_t)(sk_sorted[i + 1] >> 32) == k);
+                } else {
+                    const KeyT k = in_k[i];
+                    tie = (i > 0 && in_k[i - 1] == k) || (i + 1 < S && in_k[i + 1] == k);
+                }
                 t += tie ? 1 : 0;
             }
             t = __reduce_add_sync(0xffffffffu, t);
@@ -613,15 +777,155 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         }
         __syncthreads();
 
-        // ---- stage 3: greedy suppression over ranks [done, S) ----------------------------
+        // ---- stage 3a (cluster form): the first C1 ranks through a cluster-wide overlap matrix ----
+        // Every CTA of the cluster has just computed the same sorted order.  Row b of the lower-
+        // triangular matrix L holds, one bit per earlier rank a < b, "a overlaps b beyond the
+        // threshold"; rows are dealt round-robin over the CTAs (warp per row, one ballot per 32 pairs)
+        // and written straight into the leader's shared memory (DSMEM).  After one cluster barrier the
+        // helpers leave and ONE warp of the leader resolves the greedy chain with bit operations only:
+        // for each group of 32 ranks, dead = OR_g' (L[b][g'] & keepmask[g']), then the ballot fixed
+        // point inside the group.  No box test remains on the sequential path.
+        int first = done;
+        if constexpr (kCluster) {
+            if (round == 0) {
+                cluster_wait();          // phase A: every CTA of the cluster runs and has its barriers
+                int C1 = 0, stride = 1;
+                const size_t l_bytes = (size_t)p.sort_cap * (sizeof(KeyT) + sizeof(IdxT));      // kB + iA
+                if (sorted_fast) {
+                    C1 = min(S, p.cluster_ranks);
+                    while (C1 > 0 && (size_t)((C1 + 31) & ~31) * (size_t)(((C1 + 31) >> 5) | 1) * 4 > l_bytes) C1 -= 32;
+                    if (C1 < 64) C1 = 0;
+                    stride = ((C1 + 31) >> 5) | 1;               // odd: lanes of a group hit distinct banks
+                }
+                uint32_t *Lm = reinterpret_cast<uint32_t *>(kB);
+                if (C1 > 0) {
+                    const int r = threadIdx.x;
+                    Cand cand = Traits::empty();
+                    if (r < C1) {
+                        const int flat = (int)(uint32_t)sk_sorted[r];
+                        cand = Traits::load(g_boxes, (size_t)flat, flat);
+                    }
+                    s_tile[r] = cand;
+                    __syncthreads();
+                    NMS_STAMP();         // (cluster) candidates gathered
+                    // my block of rows: row b costs ~b pair tests, so equal work means boundaries ~ sqrt
+                    const int C1r = (C1 + 31) & ~31;
+                    auto bound = [&](uint32_t c) {
+                        if (c >= csize) return C1r;
+                        const int v = (int)sqrtf((float)c / (float)csize * (float)C1r * (float)C1r);
+                        return min(C1r, v & ~3);       // 4 rows of an odd number of words = a multiple of 16 bytes
+                    };
+                    const int b0 = bound(crank), b1 = bound(crank + 1);
+                    for (int b = b0 + w; b < b1; b += kNmsWarps) {
+                        const Cand cb = Traits::load_shared(s_tile + b);       // b < C1r <= kTile; rows >= C1 hold empty boxes
+                        const int last = b >> 5;
+                        uint32_t *row = Lm + b * stride;
+                        // every pair is tested unconditionally (no divergent guard); the diagonal word is
+                        // masked to the earlier ranks afterwards
+#pragma unroll 4
+                        for (int wd = 0; wd < last; ++wd) {
+                            const bool hit = Traits::suppress(Traits::load_shared(s_tile + (wd << 5) + lane), cb, ctx);
+                            const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+                            if (lane == 0) row[wd] = bits;
+                        }
+                        const bool hit = Traits::suppress(Traits::load_shared(s_tile + (last << 5) + lane), cb, ctx);
+                        const uint32_t bits = __ballot_sync(0xffffffffu, hit) & ((1u << (b & 31)) - 1u);
+                        if (lane == 0) row[last] = (b < C1) ? bits : 0u;
+                    }
+                    if (crank != 0) fence_proxy_async_smem();     // my rows -> visible to the bulk-copy engine
+                    __syncthreads();
+                    NMS_STAMP();         // (cluster) my rows of the matrix written
+                    if (crank != 0) {
+                        // ship my block into the leader's matrix with one bulk copy that completes on ITS mbarrier
+                        if (threadIdx.x == 0) {
+                            const uint32_t bytes = (uint32_t)(b1 - b0) * (uint32_t)stride * 4u;
+                            const uint32_t rbar = cluster_map_shared(s_lbar, 0);
+                            mbar_remote_arrive_expect_tx(rbar, bytes);
+                            if (bytes) bulk_s2s_cluster(cluster_map_shared(Lm + b0 * stride, 0), Lm + b0 * stride, bytes, rbar);
+                        }
+                        // phase B: stay until the leader has seen every block (my shared memory is the source)
+                        cluster_arrive();
+                        cluster_wait();
+                        return;
+                    }
+                    if (threadIdx.x == 0) mbar_arrive(s_lbar);
+                    mbar_wait(s_lbar, 0);
+                    cluster_arrive();    // phase B: the helpers may leave
+                    cluster_wait();
+                    NMS_STAMP();         // (cluster) matrix complete
+                    // greedy chain: warp g owns ranks 32g..32g+31.  It folds the keep masks of the earlier
+                    // groups into its dead bits as they are published (polling a shared counter: the
+                    // hand-off is a 4-byte store and a load, no box test is left on the sequential path),
+                    // resolves its own group with the ballot fixed point and publishes.
+                    {
+                        const int groups = (C1 + 31) >> 5;
+                        if (w < groups) {
+                            const int b = (w << 5) + lane;
+                            const bool valid = b < C1;
+                            const uint32_t *row = Lm + (size_t)b * stride;     // rows up to C1r exist
+                            uint32_t dead = 0;
+                            uint32_t nxt = (w > 0) ? row[0] : 0u;
+                            for (int gp = 0; gp < w; ++gp) {
+                                const uint32_t cur = nxt;
+                                if (gp + 1 < w) nxt = row[gp + 1];
+                                while (*s_ready <= gp) __nanosleep(32);     // sleep: leave the issue slots to the resolving warp
+                                dead |= cur & (uint32_t)s_kmask[gp];
+                            }
+                            int kc = (w > 0) ? s_kafter[w - 1] : 0;
+                            uint32_t keep = 0;
+                            if (kc < K) {
+                                const uint32_t lower = row[w];
+                                const bool me0 = valid && !dead;
+                                uint32_t und = __ballot_sync(0xffffffffu, me0);
+                                while (und) {
+                                    const bool me = me0 && ((und >> lane) & 1u);
+                                    const uint32_t know = __ballot_sync(0xffffffffu, me && !(lower & keep) && !(lower & und));
+                                    keep |= know;
+                                    const uint32_t dnow = __ballot_sync(0xffffffffu, me && (lower & keep));
+                                    und &= ~(know | dnow);
+                                }
+                                const int room = K - kc;
+                                int nk = __popc(keep);
+                                if (nk > room) {
+                                    keep &= (1u << __fns(keep, 0, room + 1)) - 1u;
+                                    nk = room;
+                                }
+                                if (lane == 0) {          // publish first: the successor only needs the mask and the count
+                                    s_kmask[w] = (int)keep;
+                                    s_kafter[w] = kc + nk;
+                                    __threadfence_block();
+                                    *s_ready = w + 1;
+                                }
+                                if ((keep >> lane) & 1u) kept[kc + __popc(keep & lanemask_lt())] = Traits::load_shared(s_tile + b);
+                                kc += nk;
+                            } else if (lane == 0) {
+                                s_kmask[w] = 0;
+                                s_kafter[w] = kc;
+                                __threadfence_block();
+                                *s_ready = w + 1;
+                            }
+                            if (w == groups - 1 && lane == 0) *s_kcount = kc;
+                        }
+                    }
+                    __syncthreads();
+                    k0 = *s_kcount;
+                    first = C1;
+                    __syncthreads();
+                } else if (crank != 0) {
+                    return;              // nothing to share: the leader goes on alone
+                }
+            }
+        }
+
+        // ---- stage 3: greedy suppression over ranks [first, S) ---------------------------
 #pragma unroll 1
-        for (int base = done; base < S && k0 < K; base += kTile, ++tile_no) {
+        for (int base = first; base < S && k0 < K; base += kTile, ++tile_no) {
             const uint32_t parity = tile_no & 1;
             const int r = base + threadIdx.x;
             const bool active = r < S;
             Cand cand = Traits::empty();
             if (active) {
-                const int flat = (int)in_i[S - 1 - r];
+                const int flat = sorted_fast ? (int)(uint32_t)sk_sorted[r] : (int)in_i[S - 1 - r];
                 cand = Traits::load(g_boxes, (size_t)flat, flat);
             }
             s_tile[threadIdx.x] = cand;
@@ -659,6 +963,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                 if (pw == w - 1) NMS_ROW_STAMP(2);    // about to wait for the immediate predecessor
                 if (!mbar_wait_bounded(&s_turn[pw], parity)) { *s_fault = 1; break; }
                 kc = s_kafter[pw];            // published by exactly the row just acquired
+                if (*s_kcount >= K) kc = K;   // a later row already reached max_boxes: leave at once
                 if (kc >= K) break;
                 if (suppressed_by<Traits, kKeptSmem, kTestBatch>(kept, seen, kc, cand, ctx)) alive = false;
                 seen = kc;
@@ -785,6 +1090,13 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
         int v = atoi(e);
         if (v >= 32) p.sel_target = v;
     }
+    // cluster form: ranks resolved through the overlap matrix (about 2.5 K candidates yield K keeps at 0.7)
+    p.cluster_ranks = (int)align_up((size_t)(5 * K / 2), 32);
+    if (p.cluster_ranks > kTile) p.cluster_ranks = kTile;
+    if (const char *e = getenv("RADNET_NMS_CLUSTER_RANKS")) {
+        int v = atoi(e);
+        if (v >= 64 && v <= kTile) p.cluster_ranks = (v + 31) & ~31;
+    }
     // shared-memory sort: keys ping-pong + uint16 index ping-pong
     size_t cap = align_up((size_t)N, 64);
     size_t sort_bytes = 2 * cap * sizeof(KeyT) + 2 * cap * sizeof(uint16_t);
@@ -805,6 +1117,42 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     return pl;
 }
 
+// CTAs per panel in the cluster form: 8 is the portable maximum, 16 needs the non-portable opt-in (one
+// GPC of a B200 holds 18-20 SMs).  RADNET_NMS_CLUSTER_SIZE overrides (2, 4, 8 or 16).
+static int cluster_size() {
+    static int v = 0;
+    if (v == 0) {
+        v = 8;
+        if (const char *e = getenv("RADNET_NMS_CLUSTER_SIZE")) {
+            const int q = atoi(e);
+            if (q == 2 || q == 4 || q == 8 || q == 16) v = q;
+        }
+    }
+    return v;
+}
+
+template <typename K>
+static int launch_cluster(K kernel, const NmsPlan &pl, int B, cudaStream_t st) {
+    RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    const int cs = cluster_size();
+    if (cs > 8) RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cs));
+    cfg.blockDim = dim3(kNmsThreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RADNET_CUDA(cudaLaunchKernelEx(&cfg, kernel, pl.p));
+    return check_launch("sort_nms_kernel (cluster)");
+}
+
+
 template <typename K>
 static int launch(K kernel, const NmsPlan &pl, int B, cudaStream_t st) {
     RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
@@ -815,6 +1163,42 @@ static int launch(K kernel, const NmsPlan &pl, int B, cudaStream_t st) {
 __global__ void make_keys64_kernel(const double *probs, const uint8_t *valid, int M, uint64_t *keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) keys[i] = (valid && !valid[i]) ? 0ull : score_to_key64(probs[i]);
+}
+
+// clusters of cluster_size() CTAs of the hot-path kernel that the device can hold at once (a cluster
+// needs its SMs inside one GPC, so this is fewer than SMs / cluster size); cached per plan size
+static int max_active_clusters(const NmsPlan &pl) {
+    static size_t cached_smem = 0;
+    static int cached = -1;
+    if (cached >= 0 && cached_smem == pl.smem_bytes) return cached;
+    auto kernel = sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>;
+    int n = 0;
+    const int cs = cluster_size();
+    if (cs > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        cached = 0;
+        cached_smem = pl.smem_bytes;
+        return 0;
+    }
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)cs);
+        cfg.blockDim = dim3(kNmsThreads);
+        cfg.dynamicSmemBytes = pl.smem_bytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    } else {
+        cudaGetLastError();
+    }
+    cached = n;
+    cached_smem = pl.smem_bytes;
+    return n;
 }
 
 }  // namespace radnet
@@ -863,6 +1247,11 @@ extern "C" int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *key
     p.ws = reinterpret_cast<unsigned char *>(ws);
     cudaStream_t st = (cudaStream_t)stream;
     if (pl.smem_sort) {
+        // few panels: a cluster of 8 CTAs per panel shares the overlap tests (latency path);
+        // many panels: one CTA per panel keeps every SM on its own panel (throughput path)
+        bool use_cluster = pl.kept_smem && B <= max_active_clusters(pl);
+        if (const char *e = getenv("RADNET_NMS_CLUSTER")) use_cluster = use_cluster && atoi(e) != 0;
+        if (use_cluster) return launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>, pl, B, st);
         if (pl.kept_smem) return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true>, pl, B, st);
         return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, false>, pl, B, st);
     }

@@ -16,7 +16,10 @@ from rock_art_radnet_b200 import synthetic as S  # noqa: E402
 from rock_art_radnet_b200.pipeline import ProposalPipeline  # noqa: E402
 
 C = S.HotPathConfig()
-names = ["start", "keys+table", "select", "compact", "sort", "nms", "record"]
+CLUSTER = os.environ.get("RADNET_NMS_CLUSTER", "1") != "0"
+# the cluster form (single panel) has one more stamp: the cluster-wide overlap matrix
+names = (["start", "keys+table", "select", "bucket_sort", "ties", "gather", "matrix_rows", "blocks_landed", "chain+tiles", "record"] if CLUSTER
+         else ["start", "keys+table", "select", "bucket_sort", "ties", "nms", "record"])
 for seed in range(3):
     cls, regr = S.rpn_maps(seed)
     pipe = ProposalPipeline(C, 1, 38, 38, alloc_pooled=False)
@@ -30,16 +33,15 @@ for seed in range(3):
     K = 300
     kept_bytes = ((K * 16 + 64 + 255) // 256) * 256
     off = pipe._ws_bytes - (kept_bytes + 32768 + 256) + 32768
-    st = ws[off:off + 8 * 8].view(np.int64)
-    d = np.diff(st[:7])
+    st = ws[off:off + 16 * 8].view(np.int64)
+    d = np.diff(st[:len(names)])
     rows = ws[off + 16 * 8:off + (16 + 32 * 8) * 8].view(np.int64).reshape(32, 8)
-    if seed == 0:
+    if seed == 0 and not CLUSTER:
         t0 = rows[0, 0]
         for w in range(0, 24):
             r = rows[w] - t0
             print("  row %2d gathered=%6d matrix=%6d wait_pred=%6d turn=%6d retired=%6d  (turn->retired %5d, prev retired->my turn %5d)" % (
                 w, r[0], r[1], r[2], r[3], r[4], r[4] - r[3], (r[3] - (rows[w - 1, 4] - t0)) if w else 0))
     ps = ws[off + 8 * 8:off + 16 * 8].view(np.int64)
-    print("   sort passes (cycles since compact, moved):", [(int(v // 2 - st[3]), int(v % 2)) for v in ps[:4]])
-    print("seed", seed, " ".join("%s=%d" % (n, v) for n, v in zip(names[1:], d)), "total cycles", st[6] - st[0],
+    print("seed", seed, " ".join("%s=%d" % (n, v) for n, v in zip(names[1:], d)), "total cycles", st[len(names) - 1] - st[0],
           "n_sorted", pipe.records.to_numpy()[0]["n_sorted"])

@@ -379,57 +379,60 @@ __device__ KeyT select_threshold(const KeyT *keys, int N, int target, uint32_t *
     return lo;
 }
 
-// SELECT, hot-path form (uint32 keys staged in shared memory): the same value-range search with ONE
-// 2048-bin block histogram per round (shared-memory RED; 13k keys leave ~6 per bin, so the first round
-// already isolates the target rank to a bucket far smaller than the slack) and a block scan from the
-// top bin.  Equal keys pile onto one counter, which is slower but still correct.
 constexpr int kWideBins = 2048;
-__device__ uint32_t select_threshold_wide(const uint32_t *keys, int N, int target, uint32_t *s_hist2k,
-                                          int *s_scan, int *s_sel, uint32_t *s_minmax, int &M, int &S) {
-    key_stats<uint32_t>(keys, N, s_sel, s_minmax);
-    M = s_sel[0];
-    uint32_t lo = s_minmax[0], hi = s_minmax[1];
-    S = M;
-    if (M <= target) return 1u;
-    int above = 0, need = target, inb = M;
-    const int slack = max(target >> 3, 1);
-#pragma unroll 1
-    for (int it = 0; it < 4; ++it) {
-        const uint32_t range = hi - lo;
-        if (range == 0) break;
-        const int bits = 32 - __clz((int)range);
-        const int shift = bits > 11 ? bits - 11 : 0;
+
+// SELECT by sampling (hot path): the threshold only has to cut off "about sel_target" top keys - the
+// NMS normally stops long before the slice is used up, and if it does not, a second round sorts the
+// rest - so it is estimated from every 8th key: statistics and a 2048-bin histogram of ~N/8 keys instead
+// of two passes over all of them.  The cut is placed 15 % (+8 keys) below the target rank of the sample,
+// which makes a slice smaller than sel_target unlikely (and harmless).  Returns the threshold key; the
+// exact size of the slice and the number of valid keys come out of the bucket sort that follows.
+constexpr int kSampleStride = 8;
+__device__ uint32_t select_threshold_sampled(const uint32_t *keys, int N, int target, uint32_t *s_hist2k,
+                                             int *s_scan, int *s_sel, uint32_t *s_minmax) {
+    const int lane = threadIdx.x & 31;
+    const int ns = (N + kSampleStride - 1) / kSampleStride;
+    {
+        int c = 0;
+        uint32_t mn = 0xFFFFFFFFu, mx = 0;
+        for (int j = threadIdx.x; j < ns; j += kNmsThreads) {
+            const uint32_t k = keys[j * kSampleStride];
+            if (k) { ++c; mn = min(mn, k); mx = max(mx, k); }
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (threadIdx.x == 0) { s_sel[0] = 0; s_minmax[0] = 0xFFFFFFFFu; s_minmax[1] = 0; }
         __syncthreads();
-        for (int i = threadIdx.x; i < kWideBins; i += kNmsThreads) s_hist2k[i] = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < N; i += kNmsThreads) {
-            const uint32_t k = keys[i];
-            if (k >= lo && k <= hi) atomicAdd(&s_hist2k[(k - lo) >> shift], 1u);
+        if (lane == 0 && c) {
+            atomicAdd(&s_sel[0], c);
+            atomicMin(&s_minmax[0], mn);
+            atomicMax(&s_minmax[1], mx);
         }
         __syncthreads();
-        // thread t owns bins 2047-2t and 2046-2t: thread order = descending key order
-        const int b0 = kWideBins - 1 - 2 * (int)threadIdx.x;
-        const int c0 = (int)s_hist2k[b0], c1 = (int)s_hist2k[b0 - 1];
-        int total;
-        int abv = block_exscan(c0 + c1, s_scan, &total);           // keys in higher bins
-        if (abv < need && need <= abv + c0 + c1) {                 // exactly one thread
-            int b = b0, cnt = c0;
-            if (abv + c0 < need) { b = b0 - 1; cnt = c1; abv += c0; }
-            s_sel[1] = b; s_sel[2] = abv; s_sel[3] = cnt;
-        }
-        __syncthreads();
-        const int b = s_sel[1];
-        above += s_sel[2];
-        need -= s_sel[2];
-        inb = s_sel[3];
-        const uint32_t nlo = lo + ((uint32_t)b << shift);
-        const uint32_t span = (1u << shift) - 1u;
-        hi = (hi - nlo > span) ? nlo + span : hi;
-        lo = nlo;
-        if (shift == 0 || inb <= slack) break;
     }
-    S = above + inb;
-    return lo;
+    const int Ms = s_sel[0];
+    const uint32_t lo = s_minmax[0], hi = s_minmax[1];
+    const int need = (target + kSampleStride - 1) / kSampleStride * 23 / 20 + 8;
+    if (Ms <= need || hi <= lo) return 1u;              // few valid keys (or one value): take them all
+    const uint32_t range = hi - lo;
+    const int bits = 32 - __clz((int)range);
+    const int shift = bits > 11 ? bits - 11 : 0;
+    for (int i = threadIdx.x; i < kWideBins; i += kNmsThreads) s_hist2k[i] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < ns; j += kNmsThreads) {
+        const uint32_t k = keys[j * kSampleStride];
+        if (k) atomicAdd(&s_hist2k[(k - lo) >> shift], 1u);
+    }
+    __syncthreads();
+    const int b0 = kWideBins - 1 - 2 * (int)threadIdx.x;           // thread order = descending key order
+    const int c0 = (int)s_hist2k[b0], c1 = (int)s_hist2k[b0 - 1];
+    int total;
+    const int abv = block_exscan(c0 + c1, s_scan, &total);
+    if (abv < need && need <= abv + c0 + c1) s_sel[1] = (abv + c0 < need) ? b0 - 1 : b0;   // exactly one thread
+    __syncthreads();
+    const uint32_t t = lo + ((uint32_t)s_sel[1] << shift);
+    return t ? t : 1u;
 }
 
 // SORT, hot-path form: bucket sort of the selected keys by value.  A 2048-bin histogram over [t, max]
@@ -440,17 +443,30 @@ __device__ uint32_t select_threshold_wide(const uint32_t *keys, int N, int targe
 // equal scores) - the caller then takes the general radix path.
 constexpr int kBucketMax = 24;
 __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_t hi, unsigned long long *out,
-                                int cap, uint32_t *s_hist2k, int *s_start, int *s_scan, int *s_flag) {
-    const uint32_t range = hi - t;
+                                int cap, uint32_t *s_hist2k, int *s_start, int *s_scan, int *s_flag, int *s_valid) {
+    const uint32_t range = hi > t ? hi - t : 0u;
     const int bits = range ? 32 - __clz((int)range) : 0;
     const int shift = bits > 11 ? bits - 11 : 0;
     for (int i = threadIdx.x; i < kWideBins; i += kNmsThreads) s_hist2k[i] = 0;
-    if (threadIdx.x == 0) *s_flag = 0;
+    if (threadIdx.x == 0) { *s_flag = 0; *s_valid = 0; }
     __syncthreads();
-    for (int i = threadIdx.x; i < N; i += kNmsThreads) {
-        const uint32_t k = keys[i];
-        if (k >= t) atomicAdd(&s_hist2k[(k - t) >> shift], 1u);
+    // pass 1 over all keys: histogram of the selected ones (keys above `hi`, which may come from a sample,
+    // share the top bin), count of the valid ones, and a per-thread bit mask of which of my keys are selected
+    uint32_t mine = 0;
+    int nvalid = 0;
+    {
+        int q = 0;
+        for (int i = threadIdx.x; i < N; i += kNmsThreads, ++q) {
+            const uint32_t k = keys[i];
+            nvalid += k ? 1 : 0;
+            if (k >= t) {
+                atomicAdd(&s_hist2k[min((k - t) >> shift, (uint32_t)(kWideBins - 1))], 1u);
+                if (q < 32) mine |= 1u << q;
+            }
+        }
     }
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+    if ((threadIdx.x & 31) == 0 && nvalid) atomicAdd(s_valid, nvalid);
     __syncthreads();
     const int b0 = kWideBins - 1 - 2 * (int)threadIdx.x;           // thread order = descending key order
     const int c0 = (int)s_hist2k[b0], c1 = (int)s_hist2k[b0 - 1];
@@ -458,16 +474,18 @@ __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_
     const int ex = block_exscan(c0 + c1, s_scan, &total);
     s_start[b0] = ex;
     s_start[b0 - 1] = ex + c0;
-    if (c0 > kBucketMax || c1 > kBucketMax || total > cap) *s_flag = 1;
+    if (c0 > kBucketMax || c1 > kBucketMax || total > cap || N > 32 * kNmsThreads) *s_flag = 1;
     __syncthreads();
     if (*s_flag) return -1;
-    for (int i = threadIdx.x; i < N; i += kNmsThreads) {
+    // pass 2 touches only the selected keys
+    while (mine) {
+        const int q = __ffs(mine) - 1;
+        mine &= mine - 1;
+        const int i = threadIdx.x + q * kNmsThreads;
         const uint32_t k = keys[i];
-        if (k >= t) {
-            const uint32_t b = (k - t) >> shift;
-            const int slot = (int)atomicSub(&s_hist2k[b], 1u) - 1;
-            out[s_start[b] + slot] = ((unsigned long long)k << 32) | (unsigned)i;
-        }
+        const uint32_t b = min((k - t) >> shift, (uint32_t)(kWideBins - 1));
+        const int slot = (int)atomicSub(&s_hist2k[b], 1u) - 1;
+        out[s_start[b] + slot] = ((unsigned long long)k << 32) | (unsigned)i;
     }
     __syncthreads();
 #pragma unroll
@@ -692,31 +710,27 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                 unsigned long long *sk = reinterpret_cast<unsigned long long *>(iB);
                 const int sk_cap = (int)((size_t)p.sort_cap * sizeof(IdxT) / 8);
                 uint32_t *hist = reinterpret_cast<uint32_t *>(s_cnt);
-                const KeyT thr_key = select_threshold_wide(raw_k, N, p.sel_target, hist, s_scan, s_sel, s_minmax, M, S);
-                K = min(p.max_boxes, M);
+                const KeyT thr_key = select_threshold_sampled(raw_k, N, p.sel_target, hist, s_scan, s_sel, s_minmax);
                 NMS_STAMP();     // 2: threshold selected
                 const int got = bucket_sort_desc(raw_k, N, thr_key, s_minmax[1], sk, sk_cap, hist,
-                                                 reinterpret_cast<int *>(hist + kWideBins), s_scan, s_flag);
+                                                 reinterpret_cast<int *>(hist + kWideBins), s_scan, s_flag, &s_sel[2]);
                 NMS_STAMP();     // 3: (compacted)
                 if (got >= 0) {
                     S = got;
+                    M = s_sel[2];
+                    K = min(p.max_boxes, M);
                     sk_sorted = sk;
                     sorted_fast = true;
-                } else {
-                    s_sel[1] = (int)thr_key;      // crowded buckets: general path below, same threshold
                 }
+                // else: crowded buckets (many nearly equal scores) - the general path below selects and sorts
             }
         }
         if (!sorted_fast) {
         KeyT thr_key = (KeyT)1;
         if (round == 0) {
-            if constexpr (kSmemSort && sizeof(KeyT) == 4) {
-                thr_key = (KeyT)s_sel[1];
-            } else {
-                thr_key = select_threshold<KeyT>(raw_k, N, p.sel_target, s_cnt, s_hist, s_sel, s_minmax, M, S);
-                K = min(p.max_boxes, M);
-                NMS_STAMP();     // 2: threshold selected
-            }
+            thr_key = select_threshold<KeyT>(raw_k, N, p.sel_target, s_cnt, s_hist, s_sel, s_minmax, M, S);
+            K = min(p.max_boxes, M);
+            if constexpr (!(kSmemSort && sizeof(KeyT) == 4)) NMS_STAMP();     // 2: threshold selected
         } else if (kSmemSort) {
             // the ping-pong buffers overwrote the staged keys: fetch them again
             for (int i = threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
@@ -1117,12 +1131,13 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     return pl;
 }
 
-// CTAs per panel in the cluster form: 8 is the portable maximum, 16 needs the non-portable opt-in (one
-// GPC of a B200 holds 18-20 SMs).  RADNET_NMS_CLUSTER_SIZE overrides (2, 4, 8 or 16).
-static int cluster_size() {
-    static int v = 0;
-    if (v == 0) {
-        v = 8;
+// CTAs per panel in the cluster form: 16 (non-portable opt-in; one GPC of a B200 holds 18-20 SMs) for the
+// very few panels that many clusters fit, 8 (the portable maximum) for a few more, otherwise one CTA per
+// panel.  RADNET_NMS_CLUSTER_SIZE forces 2, 4, 8 or 16; RADNET_NMS_CLUSTER=0 turns the form off.
+static int forced_cluster_size() {
+    static int v = -1;
+    if (v < 0) {
+        v = 0;
         if (const char *e = getenv("RADNET_NMS_CLUSTER_SIZE")) {
             const int q = atoi(e);
             if (q == 2 || q == 4 || q == 8 || q == 16) v = q;
@@ -1132,9 +1147,8 @@ static int cluster_size() {
 }
 
 template <typename K>
-static int launch_cluster(K kernel, const NmsPlan &pl, int B, cudaStream_t st) {
+static int launch_cluster(K kernel, const NmsPlan &pl, int B, int cs, cudaStream_t st) {
     RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    const int cs = cluster_size();
     if (cs > 8) RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * cs));
@@ -1165,22 +1179,17 @@ __global__ void make_keys64_kernel(const double *probs, const uint8_t *valid, in
     if (i < M) keys[i] = (valid && !valid[i]) ? 0ull : score_to_key64(probs[i]);
 }
 
-// clusters of cluster_size() CTAs of the hot-path kernel that the device can hold at once (a cluster
-// needs its SMs inside one GPC, so this is fewer than SMs / cluster size); cached per plan size
-static int max_active_clusters(const NmsPlan &pl) {
-    static size_t cached_smem = 0;
-    static int cached = -1;
-    if (cached >= 0 && cached_smem == pl.smem_bytes) return cached;
+// clusters of `cs` CTAs of the hot-path kernel that the device can hold at once (a cluster needs its SMs
+// inside one GPC, so this is fewer than SMs / cs); cached per plan size
+static int max_active_clusters(const NmsPlan &pl, int cs) {
+    static size_t cached_smem[17] = {0};
+    static int cached[17] = {0};
+    if (cached_smem[cs] == pl.smem_bytes) return cached[cs];
     auto kernel = sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>;
     int n = 0;
-    const int cs = cluster_size();
-    if (cs > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-        cudaGetLastError();
-        cached = 0;
-        cached_smem = pl.smem_bytes;
-        return 0;
-    }
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes) == cudaSuccess) {
+    bool ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes) == cudaSuccess;
+    if (ok && cs > 8) ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (ok) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)cs);
         cfg.blockDim = dim3(kNmsThreads);
@@ -1192,13 +1201,24 @@ static int max_active_clusters(const NmsPlan &pl) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
-    } else {
-        cudaGetLastError();
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) n = 0;
     }
-    cached = n;
-    cached_smem = pl.smem_bytes;
+    cudaGetLastError();
+    cached[cs] = n;
+    cached_smem[cs] = pl.smem_bytes;
     return n;
+}
+
+// cluster size for a launch of B panels; 0 = one CTA per panel
+static int choose_cluster(const NmsPlan &pl, int B) {
+    if (!pl.smem_sort || !pl.kept_smem) return 0;
+    if (const char *e = getenv("RADNET_NMS_CLUSTER")) {
+        if (atoi(e) == 0) return 0;
+    }
+    if (const int f = forced_cluster_size()) return B <= max_active_clusters(pl, f) ? f : 0;
+    if (B <= max_active_clusters(pl, 16)) return 16;
+    if (B <= max_active_clusters(pl, 8)) return 8;
+    return 0;
 }
 
 }  // namespace radnet
@@ -1247,11 +1267,10 @@ extern "C" int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *key
     p.ws = reinterpret_cast<unsigned char *>(ws);
     cudaStream_t st = (cudaStream_t)stream;
     if (pl.smem_sort) {
-        // few panels: a cluster of 8 CTAs per panel shares the overlap tests (latency path);
+        // few panels: a cluster of 8-16 CTAs per panel shares the overlap tests (latency path);
         // many panels: one CTA per panel keeps every SM on its own panel (throughput path)
-        bool use_cluster = pl.kept_smem && B <= max_active_clusters(pl);
-        if (const char *e = getenv("RADNET_NMS_CLUSTER")) use_cluster = use_cluster && atoi(e) != 0;
-        if (use_cluster) return launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>, pl, B, st);
+        if (const int cs = choose_cluster(pl, B))
+            return launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>, pl, B, cs, st);
         if (pl.kept_smem) return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true>, pl, B, st);
         return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, false>, pl, B, st);
     }

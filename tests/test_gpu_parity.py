@@ -68,7 +68,7 @@ def test_decode_boxes_and_kept_indices_bit_exact(pkg):
         assert np.array_equal(dets[b]["boxes"], dbg["boxes"])
         assert np.array_equal(dets[b]["scores"], dbg["probs"])
         assert dets[b]["n_candidates"] == keep.sum() and dets[b]["score_ties"] == 0
-        assert 2048 <= dets[b]["n_sorted"] <= 2048 + 256      # radix select: only the top slice is sorted
+        assert 1700 <= dets[b]["n_sorted"] <= 3264            # sampled select: only about the top 2.4k keys are sorted
 
 
 @pytest.mark.parametrize("H,W,scales,thr,mb", [
@@ -108,7 +108,7 @@ def test_rpn_to_roi_score_ties_follow_documented_rule(pkg):
     det = pipe.records.to_numpy()[0]
     # ties are counted among the n_sorted top-scoring candidates the kernel had to sort
     top = np.sort(flat[dbg[2]])[::-1][:det["n_sorted"]]
-    assert det["n_sorted"] >= 2048 and det["score_ties"] == O.count_score_ties(top)
+    assert det["n_sorted"] >= 1700 and det["score_ties"] == O.count_score_ties(top)
 
 
 def test_rpn_to_roi_errors(pkg):

@@ -146,6 +146,10 @@ struct SortNmsParams {
     // dynamic shared memory carve-up (bytes from the base)
     int sm_off_cnt, sm_off_sort, sm_off_table, sm_off_kept;
     int sort_cap;             // elements per smem sort buffer
+    // hot path (uint32 keys staged in shared memory): staged keys, sorted (key, position) words, cluster matrix
+    int sm_off_stage, sm_off_sk, sm_off_L;
+    int sk_cap;               // sorted words that fit
+    int l_bytes;              // bytes available for the cluster overlap matrix
 };
 
 // block-wide exclusive scan of one int per thread (1024 threads); returns exclusive prefix,
@@ -568,10 +572,15 @@ __device__ __forceinline__ bool suppressed_by(const typename Traits::Cand *kept,
     return hit;
 }
 
-template <typename Traits, typename KeyT, typename IdxT, bool kSmemSort, bool kKeptSmem, bool kCluster = false>
+template <typename Traits, typename KeyT, typename IdxT, bool kSmemSort, bool kKeptSmem, bool kCluster = false,
+          bool kStagedOnly = false>
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams p) {
     using Cand = typename Traits::Cand;
     constexpr bool kI32 = sizeof(Cand) == sizeof(int4);
+    // kSmemSort: the general sort's ping-pong buffers live in shared memory (and the hot path borrows them);
+    // kStagedOnly: only the hot path's buffers do (larger panels), the general sort runs in global scratch
+    constexpr bool kStaged = kSmemSort || kStagedOnly;
+    constexpr bool kFast = kStaged && sizeof(KeyT) == 4;
     constexpr int kTestBatch = kI32 ? 8 : 2;      // kept boxes fetched per batch (register budget)
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -646,16 +655,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     // ---- stage 0: raw keys -> shared memory (one TMA bulk copy on the hot path) ----------
     const KeyT *raw_k = g_keys;
     bool tma_pending = false;
-    if (kSmemSort) {
+    if (kStaged) {
+        KeyT *stage = kSmemSort ? kA : reinterpret_cast<KeyT *>(smem + p.sm_off_stage);
         const size_t bytes = (size_t)N * sizeof(KeyT);
         const uint32_t bulk = ((reinterpret_cast<uintptr_t>(g_keys) & 15) == 0) ? (uint32_t)(bytes & ~(size_t)15) : 0u;
         if (threadIdx.x == 0 && bulk) {
             mbar_expect_tx(s_bar, bulk);
-            tma_bulk_g2s(kA, g_keys, bulk, s_bar);
+            tma_bulk_g2s(stage, g_keys, bulk, s_bar);
         }
         // tail (and the whole array when the source is not 16-byte aligned)
-        for (int i = (int)(bulk / sizeof(KeyT)) + threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
-        raw_k = kA;
+        for (int i = (int)(bulk / sizeof(KeyT)) + threadIdx.x; i < N; i += kNmsThreads) stage[i] = g_keys[i];
+        raw_k = stage;
         tma_pending = bulk != 0;
     }
 
@@ -701,14 +711,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         const IdxT *in_i = nullptr;
         bool sorted_fast = false;
         const unsigned long long *sk_sorted = nullptr;      // hot path: descending (key, position) words
-        if constexpr (kSmemSort && sizeof(KeyT) == 4) {
+        if constexpr (kFast) {
             if (round == 0) {
-                // hot path: wide-histogram select, then a value-bucket sort of the selected keys into the
-                // free ping-pong buffer as (key, position) words in descending order
-                // the sorted words live in the second index buffer; the second key buffer and the first index
-                // buffer (contiguous, untouched by select and sort) hold the cluster overlap matrix
-                unsigned long long *sk = reinterpret_cast<unsigned long long *>(iB);
-                const int sk_cap = (int)((size_t)p.sort_cap * sizeof(IdxT) / 8);
+                // hot path: sampled select, then a value-bucket sort of the selected keys as (key, position)
+                // words in descending order.  Neither touches the area of the cluster overlap matrix (in the
+                // full shared-memory layout: sorted words in the second index buffer, matrix in the second
+                // key buffer + first index buffer).
+                unsigned long long *sk = reinterpret_cast<unsigned long long *>(smem + p.sm_off_sk);
+                const int sk_cap = p.sk_cap;
                 uint32_t *hist = reinterpret_cast<uint32_t *>(s_cnt);
                 const KeyT thr_key = select_threshold_sampled(raw_k, N, p.sel_target, hist, s_scan, s_sel, s_minmax);
                 NMS_STAMP();     // 2: threshold selected
@@ -730,7 +740,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         if (round == 0) {
             thr_key = select_threshold<KeyT>(raw_k, N, p.sel_target, s_cnt, s_hist, s_sel, s_minmax, M, S);
             K = min(p.max_boxes, M);
-            if constexpr (!(kSmemSort && sizeof(KeyT) == 4)) NMS_STAMP();     // 2: threshold selected
+            if constexpr (!kFast) NMS_STAMP();     // 2: threshold selected
         } else if (kSmemSort) {
             // the ping-pong buffers overwrote the staged keys: fetch them again
             for (int i = threadIdx.x; i < N; i += kNmsThreads) kA[i] = g_keys[i];
@@ -804,14 +814,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
             if (round == 0) {
                 cluster_wait();          // phase A: every CTA of the cluster runs and has its barriers
                 int C1 = 0, stride = 1;
-                const size_t l_bytes = (size_t)p.sort_cap * (sizeof(KeyT) + sizeof(IdxT));      // kB + iA
+                const size_t l_bytes = (size_t)p.l_bytes;
                 if (sorted_fast) {
                     C1 = min(S, p.cluster_ranks);
                     while (C1 > 0 && (size_t)((C1 + 31) & ~31) * (size_t)(((C1 + 31) >> 5) | 1) * 4 > l_bytes) C1 -= 32;
                     if (C1 < 64) C1 = 0;
                     stride = ((C1 + 31) >> 5) | 1;               // odd: lanes of a group hit distinct banks
                 }
-                uint32_t *Lm = reinterpret_cast<uint32_t *>(kB);
+                uint32_t *Lm = reinterpret_cast<uint32_t *>(smem + p.sm_off_L);
                 if (C1 > 0) {
                     const int r = threadIdx.x;
                     Cand cand = Traits::empty();
@@ -1062,6 +1072,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
 // ----------------------------------------------------------------------------------
 struct NmsPlan {
     bool smem_sort;
+    bool staged_only;         // hot-path buffers in shared memory, general sort in global scratch
     bool kept_smem;
     size_t smem_bytes;
     size_t ws_stride;
@@ -1117,7 +1128,32 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     pl.smem_sort = allow_smem_sort && N <= 65535 && off + sort_bytes <= (size_t)smem_limit;
     p.sm_off_sort = (int)off;
     p.sort_cap = (int)cap;
-    if (pl.smem_sort) off += sort_bytes;
+    pl.staged_only = false;
+    if (pl.smem_sort) {
+        // the hot path borrows the ping-pong buffers: keys staged in kA, matrix in kB + iA, sorted words in iB
+        p.sm_off_stage = (int)off;
+        p.sm_off_L = (int)(off + cap * sizeof(KeyT));
+        p.l_bytes = (int)(cap * (sizeof(KeyT) + sizeof(uint16_t)));
+        p.sm_off_sk = (int)(off + cap * (2 * sizeof(KeyT) + sizeof(uint16_t)));
+        p.sk_cap = (int)(cap * sizeof(uint16_t) / 8);
+        off += sort_bytes;
+    } else if (allow_smem_sort && sizeof(KeyT) == 4 && pl.kept_smem && N <= 32 * kNmsThreads) {
+        // larger panels (12 anchors, 600x800 px): only the hot path's own buffers fit
+        const size_t stage_bytes = align_up(cap * sizeof(KeyT), 128);
+        const int sk_cap = (p.sel_target * 3 / 2 + 255) & ~255;
+        const size_t sk_bytes = (size_t)sk_cap * 8;
+        const int rows = p.cluster_ranks;
+        const size_t l_bytes = align_up((size_t)rows * (size_t)((rows >> 5) | 1) * 4, 128);
+        if (off + stage_bytes + sk_bytes + l_bytes <= (size_t)smem_limit) {
+            pl.staged_only = true;
+            p.sm_off_stage = (int)off;
+            p.sm_off_sk = (int)(off + stage_bytes);
+            p.sk_cap = sk_cap;
+            p.sm_off_L = (int)(off + stage_bytes + sk_bytes);
+            p.l_bytes = (int)l_bytes;
+            off += stage_bytes + sk_bytes + l_bytes;
+        }
+    }
     pl.smem_bytes = off;
     // global scratch (always sized so that either variant can run)
     size_t w = 0;
@@ -1182,10 +1218,14 @@ __global__ void make_keys64_kernel(const double *probs, const uint8_t *valid, in
 // clusters of `cs` CTAs of the hot-path kernel that the device can hold at once (a cluster needs its SMs
 // inside one GPC, so this is fewer than SMs / cs); cached per plan size
 static int max_active_clusters(const NmsPlan &pl, int cs) {
-    static size_t cached_smem[17] = {0};
-    static int cached[17] = {0};
-    if (cached_smem[cs] == pl.smem_bytes) return cached[cs];
-    auto kernel = sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>;
+    static size_t cached_smem[2][17] = {{0}};
+    static int cached_n[2][17] = {{0}};
+    size_t *cached_smem_row = cached_smem[pl.staged_only ? 1 : 0];
+    int *cached = cached_n[pl.staged_only ? 1 : 0];
+    if (cached_smem_row[cs] == pl.smem_bytes) return cached[cs];
+    const void *kernel = pl.staged_only
+        ? (const void *)sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true, true, true>
+        : (const void *)sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>;
     int n = 0;
     bool ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes) == cudaSuccess;
     if (ok && cs > 8) ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
@@ -1205,13 +1245,13 @@ static int max_active_clusters(const NmsPlan &pl, int cs) {
     }
     cudaGetLastError();
     cached[cs] = n;
-    cached_smem[cs] = pl.smem_bytes;
+    cached_smem_row[cs] = pl.smem_bytes;
     return n;
 }
 
 // cluster size for a launch of B panels; 0 = one CTA per panel
 static int choose_cluster(const NmsPlan &pl, int B) {
-    if (!pl.smem_sort || !pl.kept_smem) return 0;
+    if (!(pl.smem_sort || pl.staged_only) || !pl.kept_smem) return 0;
     if (const char *e = getenv("RADNET_NMS_CLUSTER")) {
         if (atoi(e) == 0) return 0;
     }
@@ -1273,6 +1313,11 @@ extern "C" int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *key
             return launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>, pl, B, cs, st);
         if (pl.kept_smem) return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true>, pl, B, st);
         return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, false>, pl, B, st);
+    }
+    if (pl.staged_only) {
+        if (const int cs = choose_cluster(pl, B))
+            return launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true, true, true>, pl, B, cs, st);
+        return launch(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true, false, true>, pl, B, st);
     }
     if (pl.kept_smem) return launch(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true>, pl, B, st);
     return launch(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, false>, pl, B, st);

@@ -179,6 +179,10 @@ int radnet_roi_targets(const int32_t *rois, int R, const double *gt, const int32
                        const double *h_regr_std4, int32_t *x_roi, int32_t *y_class,
                        double *y_regr, double *ious, int32_t *count, void *stream);
 
+/* utils.iou(a, b) (reference faster_rcnn/utils.py:77-109) for n box pairs: a, b [n][4] float64
+ * (x1,y1,x2,y2) -> out [n] float64; 0.0 for degenerate boxes, else inter/(union+1e-6). */
+int radnet_iou_pairs(const double *a, const double *b, long long n, double *out, void *stream);
+
 /* ------------------------------------------------ f1/f2: detection post-processing
  * Labelled detection record, the unit exchanged between these entry points and between ranks
  * (stride = radnet_cls_record_bytes(max_det)):
@@ -245,6 +249,11 @@ size_t radnet_final_nms_workspace_bytes(int S, int n_in, int in_max_det, int n_c
 int radnet_final_nms(const void *rec_in, int in_max_det, int S, int n_in, const int32_t *in_count,
                      int n_cls, double avg_thr, double conf_thr, int n_obj_avg, void *rec_out,
                      int out_max_det, void *ws, size_t ws_bytes, void *stream);
+
+/* RADNet.get_real_coordinates (RADNet.py:44-51) for n coordinates: out[i] = int(round(v[i] // ratio)),
+ * Python float floor division.  (radnet_classify_nms / radnet_class_nms apply the same rule fused.) */
+int radnet_real_coordinates(const int32_t *v, long long n, double ratio, int32_t *out, void *stream);
+
 
 #ifdef __cplusplus
 }

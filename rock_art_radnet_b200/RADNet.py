@@ -3,7 +3,8 @@
 `RADNet(C, model_rpn, model_detector, preprocess_func)` keeps the reference's constructor,
 attributes and the methods that sit on or right after the hot path:
 
-  get_real_coordinates, format_img_size / format_img_channels / format_img   (host, as the reference)
+  get_real_coordinates                                                       RADNet.py:44-51
+  format_img_size / format_img_channels / format_img                         (OpenCV on the host, as the reference)
   apply_spatial_pyramid_pooling(R, feature_map) -> (bboxes, probs)           RADNet.py:98-152
   final_nms(boxes, probs, ...) -> (boxes, probs)                             RADNet.py:156-240
   predict(images) -> list of detection dicts                                 RADNet.py:502-718
@@ -50,11 +51,19 @@ class RADNet:
         self.preprocess_func = preprocess_func
         self.class_mapping = {v: k for k, v in C.class_mapping.items()}
 
-    # ------------------------------------------------------------------ host-side helpers
+    # ------------------------------------------------------------------ helpers
     def get_real_coordinates(self, ratio, x1, y1, x2, y2):
-        """Resized-image pixels -> original pixels (RADNet.py:44-51).  Scalar host helper kept for
-        API parity; `predict` applies the same rule on the device (radnet_classify_nms)."""
-        return tuple(int(round(v // ratio)) for v in (x1, y1, x2, y2))
+        """Resized-image pixels -> original pixels, `int(round(v // ratio))` (RADNet.py:44-51), evaluated by
+        `radnet_real_coordinates`; `predict` applies the same rule fused into the per-class NMS kernel."""
+        if not ratio > 0:
+            raise ZeroDivisionError("float floor division by zero")
+        D.require_cuda()
+        dev = torch.device("cuda:%d" % torch.cuda.current_device())
+        v = D.to_device(np.asarray([x1, y1, x2, y2]), np.int32, dev)
+        out = D.empty((4,), np.int32, dev)
+        from . import _lib
+        _lib.call("radnet_real_coordinates", D.ptr(v), 4, float(ratio), D.ptr(out), D.stream_ptr(dev))
+        return tuple(int(t) for t in out.cpu().numpy())
 
     def format_img_size(self, img):
         """Resize so that the short side is C.img_size (RADNet.py:53-74); OpenCV, on the host."""

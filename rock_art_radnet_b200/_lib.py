@@ -44,6 +44,8 @@ SIGNATURES = {
     "radnet_roi_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_double,
                                    c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
+    "radnet_iou_pairs": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
+    "radnet_real_coordinates": (c_int, [c_void_p, c_longlong, c_double, c_void_p, c_void_p]),
     "radnet_cls_record_bytes": (c_size_t, [c_int]),
     "radnet_classify_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                        c_void_p, c_double, c_void_p, c_int, c_void_p, c_int, c_void_p]),

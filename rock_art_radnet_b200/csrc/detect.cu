@@ -879,6 +879,12 @@ __global__ void __launch_bounds__(kDetThreads, 1) cluster_kernel(ClusterParams p
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+__global__ void real_coordinates_kernel(const int32_t *__restrict__ v, long long n, double ratio,
+                                        int32_t *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = real_coordinate(v[i], ratio);
+}
+
 static int optin_smem() {
     int dev = 0, v = 232448;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -1062,3 +1068,14 @@ extern "C" int radnet_final_nms(const void *rec_in, int in_max_det, int S, int n
     return launch_cluster(rec_in, in_max_det, S, n_in, in_count, n_cls, 1, avg_thr, conf_thr, n_obj_avg, 0x7fffffff,
                           nullptr, nullptr, rec_out, out_max_det, ws, ws_bytes, (cudaStream_t)stream, "final_nms");
 }
+
+extern "C" int radnet_real_coordinates(const int32_t *v, long long n, double ratio, int32_t *out, void *stream) {
+    RADNET_CHECK_ARG(v && out && n >= 0, "real_coordinates: bad arguments");
+    RADNET_CHECK_ARG(ratio > 0.0 && ratio < 1e300, "real_coordinates: ratio must be positive and finite");
+    if (n == 0) return RADNET_OK;
+    const long long blocks = (n + 255) / 256;
+    RADNET_CHECK_ARG(blocks <= 0x7fffffffLL, "real_coordinates: n too large");
+    real_coordinates_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(v, n, ratio, out);
+    return check_launch("real_coordinates_kernel");
+}
+

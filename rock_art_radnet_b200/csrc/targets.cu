@@ -588,3 +588,24 @@ extern "C" int radnet_roi_targets(const int32_t *rois, int R, const double *gt, 
     roi_targets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p);
     return check_launch("roi_targets_kernel");
 }
+
+// utils.iou(a, b) for n box pairs (reference utils.py:77-109): API parity, not on the batched hot path
+namespace radnet {
+__global__ void iou_pairs_kernel(const double *__restrict__ a, const double *__restrict__ b, long long n,
+                                 double *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *p = a + 4 * i, *q = b + 4 * i;
+    out[i] = ref_iou(p[0], p[1], p[2], p[3], q[0], q[1], q[2], q[3]);
+}
+}  // namespace radnet
+
+extern "C" int radnet_iou_pairs(const double *a, const double *b, long long n, double *out, void *stream) {
+    RADNET_CHECK_ARG(a && b && out && n >= 0, "iou_pairs: bad arguments");
+    if (n == 0) return RADNET_OK;
+    const long long blocks = (n + 255) / 256;
+    RADNET_CHECK_ARG(blocks <= 0x7fffffffLL, "iou_pairs: n too large");
+    radnet::iou_pairs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
+    return radnet::check_launch("iou_pairs_kernel");
+}
+

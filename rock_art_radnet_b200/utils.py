@@ -22,15 +22,24 @@ def get_new_img_size(width, height, img_min_side=300):
     return int(f * width), img_min_side
 
 
+def iou_pairs(a, b):
+    """IoU of n box pairs, a and b (n,4) as (x1,y1,x2,y2) -> (n,) float64 (reference utils.py:77-109,
+    evaluated by `radnet_iou_pairs` on the device)."""
+    D.require_cuda()
+    dev = torch.device("cuda:%d" % torch.cuda.current_device())
+    a_d = D.to_device(np.asarray(a, dtype=np.float64).reshape(-1, 4), np.float64, dev)
+    b_d = D.to_device(np.asarray(b, dtype=np.float64).reshape(-1, 4), np.float64, dev)
+    if a_d.shape != b_d.shape:
+        raise ValueError("iou_pairs: a and b must hold the same number of boxes")
+    out = D.empty((int(a_d.shape[0]),), np.float64, dev)
+    _lib.call("radnet_iou_pairs", D.ptr(a_d), D.ptr(b_d), int(a_d.shape[0]), D.ptr(out), D.stream_ptr(dev))
+    return out.cpu().numpy()
+
+
 def iou(a, b):
-    """Scalar IoU of (x1,y1,x2,y2) boxes, host convenience (reference utils.py:77-109)."""
-    if a[0] >= a[2] or a[1] >= a[3] or b[0] >= b[2] or b[1] >= b[3]:
-        return 0.0
-    w = min(a[2], b[2]) - max(a[0], b[0])
-    h = min(a[3], b[3]) - max(a[1], b[1])
-    inter = 0 if (w < 0 or h < 0) else w * h
-    union = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
-    return float(inter) / float(union + 1e-6)
+    """Scalar IoU of (x1,y1,x2,y2) boxes (reference utils.py:99-109): 0.0 for degenerate boxes, else
+    inter / (union + 1e-6).  Same device routine as the target-assignment kernels use."""
+    return float(iou_pairs([a[:4]], [b[:4]])[0])
 
 
 class RpnTargetBatch:

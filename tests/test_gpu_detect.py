@@ -299,3 +299,19 @@ def test_tiled_panel_pipeline_end_to_end(mods, width, height, n_panels):
             assert np.array_equal(got_b[k], want[k][0]) and np.array_equal(got_p[k], want[k][1])
         n_clustered += int((merged.to_numpy()[p]["entry"]["aux"] > 1).sum())
     assert n_clustered > 0          # neighbouring tiles really produced multi-member clusters
+
+
+def test_scalar_helpers_on_the_device(mods):
+    """utils.iou and RADNet.get_real_coordinates (API-parity helpers) evaluated by the library."""
+    RN, DT, _ = mods
+    from rock_art_radnet_b200.utils import iou, iou_pairs
+    rng = np.random.default_rng(0)
+    a = np.sort(rng.uniform(0, 50, (300, 2, 2)), axis=1).transpose(0, 2, 1).reshape(300, 4)[:, [0, 2, 1, 3]]
+    b = np.sort(rng.uniform(0, 50, (300, 2, 2)), axis=1).transpose(0, 2, 1).reshape(300, 4)[:, [0, 2, 1, 3]]
+    got = iou_pairs(a, b)
+    assert all(got[i] == O.iou(list(a[i]), list(b[i])) for i in range(300)) and (got > 0).any()
+    assert iou([0, 0, 0, 5], [0, 0, 5, 5]) == 0.0 and iou([0, 0, 4, 4], [2, 2, 6, 6]) == O.iou([0, 0, 4, 4], [2, 2, 6, 6])
+    net = RN.RADNet(_config(), None, None, lambda x: x)
+    for ratio in (1.0, 0.75, 0.3, 600 / 799.0, 1.7, 2.0):
+        for v in rng.integers(0, 3000, (20, 4)):
+            assert net.get_real_coordinates(ratio, *[np.int64(t) for t in v]) == DO.get_real_coordinates(ratio, *v)

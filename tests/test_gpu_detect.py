@@ -315,3 +315,79 @@ def test_scalar_helpers_on_the_device(mods):
     for ratio in (1.0, 0.75, 0.3, 600 / 799.0, 1.7, 2.0):
         for v in rng.integers(0, 3000, (20, 4)):
             assert net.get_real_coordinates(ratio, *[np.int64(t) for t in v]) == DO.get_real_coordinates(ratio, *v)
+
+
+def test_capacity_limits_are_flagged_not_truncated(mods):
+    RN, DT, torch = mods
+    C = _config()
+    dev = torch.device("cuda")
+    # (1) decode into a record with fewer slots than detections
+    R = S.random_rois(3, 300)[0]
+    a, r = S.RandomHeadModel(3, C, sharp=4.0).predict([None, R[None]])
+    small = DT.ClassRecords(1, 8, dev)
+    rec = DT.classify_decode(a, r, C, rois=R[None].astype(np.int32), out=small).to_numpy()
+    assert rec["header"][0, DT.H_NDET] == -2
+    with pytest.raises(Exception) as ei:
+        DT.check_records(rec, "test")
+    assert "RADNET_E_UNSUPPORTED" in str(ei.value)
+    # (2) tile merge / per-class NMS into too small an output
+    b, p = S.clustered_boxes(1, 12, 6, 0.7, 1.0)
+    rec_in = DT.ClassRecords.from_arrays([(np.zeros(len(p), np.int32), p, b)], len(p), dev)
+    assert DT.final_nms_records(rec_in, 1, 1, 7, out_max_det=3).to_numpy()["header"][0, DT.H_NDET] == -2
+    assert DT.class_nms(rec_in, 1, 1, 7, 0.4, out_max_det=3).to_numpy()["header"][0, DT.H_NDET] == -2
+    assert DT.final_nms_records(rec_in, 1, 1, 7, out_max_det=12).to_numpy()["header"][0, DT.H_NDET] == 12
+    # (3) more than 4096 boxes of one class in one image
+    b, p = S.clustered_boxes(2, 50, 100, 0.7, 1.0)
+    big = DT.ClassRecords.from_arrays([(np.zeros(len(p), np.int32), p, b)], len(p), dev)
+    assert DT.final_nms_records(big, 1, 1, 7).to_numpy()["header"][0, DT.H_NDET] == -2
+    # 4096 exactly is fine
+    ok = DT.ClassRecords.from_arrays([(np.zeros(4096, np.int32), p[:4096], b[:4096])], 4096, dev)
+    got = DT.final_nms_records(ok, 1, 1, 7).to_numpy()[0]
+    ob, op = DO.final_nms(b[:4096], p[:4096])
+    n = int(got["header"][DT.H_NDET])
+    assert n == len(op) and np.array_equal(got["entry"]["box"][:n], ob) and np.array_equal(got["entry"]["prob"][:n], op)
+
+
+def test_maximum_sizes_1024_rois_32_classes(mods):
+    RN, DT, _ = mods
+    C = _config()
+    n_cls = 32
+    names = {i: "c%d" % i for i in range(n_cls)}
+    C.classifier_regr_std = [8.0, 8.0, 4.0, 4.0]
+    R = S.random_rois(9, 1024)[0]
+    R[:, 2:] = np.maximum(R[:, 2:], 3)
+    a, r = S.RandomHeadModel(9, C, n_cls=n_cls, sharp=5.0, regr_scale=0.2).predict([None, R[None]])
+    rec = DT.classify_nms(a, r, C, rois=R[None].astype(np.int32), ratio=[0.6], origin=[(7, 9)]).to_numpy()
+    DT.check_records(rec, "test")
+    want = DO.tile_detections(R, a[0], r[0], C, 0.6, (7, 9), names)
+    got_b, got_p = DT.record_to_dicts(rec[0], names)
+    assert list(got_b) == list(want) and len(want) >= 20
+    for k in want:
+        assert np.array_equal(got_b[k], want[k][0]) and np.array_equal(got_p[k], want[k][1])
+
+
+def test_in_count_limits_the_records_used(mods):
+    RN, DT, torch = mods
+    dev = torch.device("cuda")
+    groups = []
+    for j in range(6):
+        b, p = S.clustered_boxes(400 + j, 6, 5, 0.7, 1.0)
+        groups.append((np.full(len(p), j % 3, np.int32), p, b))
+    rec_in = DT.ClassRecords.from_arrays(groups, 30, dev)
+    # two segments of three records; the second segment uses only its first record
+    out = DT.final_nms_records(rec_in, 2, 3, 7, in_count=[3, 1]).to_numpy()
+    for seg, used in ((0, [0, 1, 2]), (1, [3])):
+        got_b, got_p = DT.record_to_dicts(out[seg], NAMES)
+        cls = np.concatenate([groups[j][0] for j in used])
+        pb = np.concatenate([groups[j][1] for j in used])
+        bx = np.concatenate([groups[j][2] for j in used])
+        order = []
+        for c in cls:
+            if c not in order:
+                order.append(int(c))
+        assert [NAMES[c] for c in order] == list(got_b)
+        for c in order:
+            ob, op = DO.final_nms(bx[cls == c], pb[cls == c])
+            assert np.array_equal(got_b[NAMES[c]], ob) and np.array_equal(got_p[NAMES[c]], op)
+    nm = DT.class_nms(rec_in, 2, 3, 7, 0.4, in_count=[2, 3]).to_numpy()
+    assert nm["header"][0, DT.H_NIN] == 60 and nm["header"][1, DT.H_NIN] == 90

@@ -182,6 +182,17 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// volatile 64-bit shared-memory accesses by 32-bit shared address (no generic-address arithmetic on the
+// polling path)
+__device__ __forceinline__ unsigned long long lds_volatile_u64(uint32_t addr) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_u64(uint32_t addr, unsigned long long v) {
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
 // streaming 16-byte store: written once, never re-read by this kernel
 __device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),

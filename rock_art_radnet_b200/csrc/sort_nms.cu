@@ -44,6 +44,7 @@ constexpr int kTile = kNmsThreads;              // candidates per NMS tile
 constexpr int kMaxTableEntries = 65535;
 constexpr int kKeptSmemMax = 1024;              // kept boxes held in shared memory
 constexpr int kLookAhead = 6;                   // rows that may run ahead of the retiring row
+constexpr int kChainGroups = 4;                 // cluster form: groups of 32 ranks resolved by one warp of the chain
 constexpr int kSmemHeader = 3072;               // barriers, misc words, scan scratch, row counts, 256-bin histogram
 
 // ----------------------------------------------------------------------------------
@@ -447,7 +448,8 @@ __device__ uint32_t select_threshold_sampled(const uint32_t *keys, int N, int ta
 // equal scores) - the caller then takes the general radix path.
 constexpr int kBucketMax = 24;
 __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_t hi, unsigned long long *out,
-                                int cap, uint32_t *s_hist2k, int *s_start, int *s_scan, int *s_flag, int *s_valid) {
+                                int cap, uint32_t *s_hist2k, int *s_start, int *s_scan, int *s_flag, int *s_valid,
+                                int *s_ties) {
     const uint32_t range = hi > t ? hi - t : 0u;
     const int bits = range ? 32 - __clz((int)range) : 0;
     const int shift = bits > 11 ? bits - 11 : 0;
@@ -492,6 +494,7 @@ __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_
         out[s_start[b] + slot] = ((unsigned long long)k << 32) | (unsigned)i;
     }
     __syncthreads();
+    int ties = 0;              // equal keys share a bucket: count the tied entries here, no extra pass
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         unsigned long long *a = out + (q ? ex + c0 : ex);
@@ -502,7 +505,12 @@ __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_
             while (j >= 0 && a[j] < v) { a[j + 1] = a[j]; --j; }
             a[j + 1] = v;
         }
+        for (int i = 0; i < n; ++i) {
+            const uint32_t k = (uint32_t)(a[i] >> 32);
+            ties += ((i > 0 && (uint32_t)(a[i - 1] >> 32) == k) || (i + 1 < n && (uint32_t)(a[i + 1] >> 32) == k)) ? 1 : 0;
+        }
     }
+    if (ties) atomicAdd(s_ties, ties);
     __syncthreads();
     return total;
 }
@@ -591,8 +599,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     uint64_t *s_turn = reinterpret_cast<uint64_t *>(smem + 256);          // [32] hand-off barriers
     KeyT *s_minmax = reinterpret_cast<KeyT *>(smem + 512);                // [2]
     volatile int *s_kafter = reinterpret_cast<volatile int *>(smem + 1536);   // [32] kept count after row w
-    volatile int *s_kmask = reinterpret_cast<volatile int *>(smem + 1792);    // [32] cluster form: lanes kept per group of 32 ranks
-    volatile int *s_ready = s_misc + 9;                                       // cluster form: groups published so far
+    // cluster form: per group of 32 ranks {kept count after the group + 1, lanes kept}; 0 = not yet published
+    volatile unsigned long long *s_pub = reinterpret_cast<volatile unsigned long long *>(smem + 1664);   // [32]
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + p.sm_off_cnt);  // [32][257]
     volatile int *s_kcount = s_misc + 0;
     int *s_flag = s_misc + 2;
@@ -637,11 +645,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
 #define NMS_ROW_STAMP(k) do {} while (0)
 #endif
     NMS_STAMP();
+    if (kCluster && threadIdx.x < 32) s_pub[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) {
         *s_kcount = 0;
         *s_ties = 0;
         *s_fault = 0;
-        s_misc[9] = 0;
         mbar_init(s_bar, 1);
         for (int i = 0; i < kNmsWarps; ++i) mbar_init(&s_turn[i], 1);
         if (kCluster) mbar_init(s_lbar, csize);       // one arrival per CTA of the cluster (matrix blocks)
@@ -674,13 +682,27 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
     if (kI32) {
         const double thr = p.thr;
         for (int u = threadIdx.x; u < p.table_entries; u += kNmsThreads) {
-            double d = __dadd_rn((double)u, 1e-6);
-            double g = floor(__dmul_rn(thr, d)) - 1.0;
-            int c = (g > 0.0) ? ((g < 65534.0) ? (int)g : 65535) : 0;
-            int lim = c + 4;
-            // smallest inter with inter/(u+1e-6) > thr, found with the float64 divide itself
-            while (c < lim && c <= u && !(__ddiv_rn((double)c, d) > thr)) ++c;
-            bool ok = (c <= u) && (c < lim) && (__ddiv_rn((double)c, d) > thr);
+            // tab[u] = smallest inter with inter/(u+1e-6) > thr.  In exact arithmetic that is the first
+            // integer above pm = thr*(u+1e-6); the rounded divide can only disagree when pm is within a few
+            // ulps of an integer, so the divide itself is consulted only then (the table stays bit-exact and
+            // costs two float64 multiplies per entry instead of three divides).
+            const double d = __dadd_rn((double)u, 1e-6);
+            const double pm = __dmul_rn(thr, d);
+            const double fl = floor(pm);
+            const double eps = __dmul_rn(1e-12, fabs(pm) + 1.0);
+            int c;
+            bool ok;
+            if (pm - fl > eps && (fl + 1.0) - pm > eps) {
+                const double first = fmax(fl + 1.0, 0.0);
+                ok = first <= (double)u && first < 65535.0;
+                c = ok ? (int)first : 0;
+            } else {
+                const double g = fl - 1.0;
+                c = (g > 0.0) ? ((g < 65534.0) ? (int)g : 65535) : 0;
+                const int lim = c + 4;
+                while (c < lim && c <= u && !(__ddiv_rn((double)c, d) > thr)) ++c;
+                ok = (c <= u) && (c < lim) && (__ddiv_rn((double)c, d) > thr);
+            }
             s_tab[u] = ok ? (uint16_t)c : (uint16_t)0xFFFF;
         }
     }
@@ -723,7 +745,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                 const KeyT thr_key = select_threshold_sampled(raw_k, N, p.sel_target, hist, s_scan, s_sel, s_minmax);
                 NMS_STAMP();     // 2: threshold selected
                 const int got = bucket_sort_desc(raw_k, N, thr_key, s_minmax[1], sk, sk_cap, hist,
-                                                 reinterpret_cast<int *>(hist + kWideBins), s_scan, s_flag, &s_sel[2]);
+                                                 reinterpret_cast<int *>(hist + kWideBins), s_scan, s_flag, &s_sel[2], s_ties);
                 NMS_STAMP();     // 3: (compacted)
                 if (got >= 0) {
                     S = got;
@@ -780,20 +802,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         NMS_STAMP();         // 4: sorted
 
         // ---- score ties among the sorted candidates (reported) -----------
-        {
+        // (the hot path counted them inside its buckets)
+        if (!sorted_fast) {
             if (threadIdx.x == 0) *s_ties = 0;
             __syncthreads();
             int t = 0;
             for (int i = threadIdx.x; i < S; i += kNmsThreads) {
-                bool tie;
-                if (sorted_fast) {
-                    const uint32_t k = (uint32_t)(sk_sorted[i] >> 32);
-                    tie = (i > 0 && (uint32_t)(sk_sorted[i - 1] >> 32) == k) ||
-                          (i + 1 < S && (uint32_t)(sk_sorted[i + 1] >> 32) == k);
-                } else {
-                    const KeyT k = in_k[i];
-                    tie = (i > 0 && in_k[i - 1] == k) || (i + 1 < S && in_k[i + 1] == k);
-                }
+                const KeyT k = in_k[i];
+                const bool tie = (i > 0 && in_k[i - 1] == k) || (i + 1 < S && in_k[i + 1] == k);
                 t += tie ? 1 : 0;
             }
             t = __reduce_add_sync(0xffffffffu, t);
@@ -877,58 +893,97 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                     cluster_arrive();    // phase B: the helpers may leave
                     cluster_wait();
                     NMS_STAMP();         // (cluster) matrix complete
-                    // greedy chain: warp g owns ranks 32g..32g+31.  It folds the keep masks of the earlier
-                    // groups into its dead bits as they are published (polling a shared counter: the
-                    // hand-off is a 4-byte store and a load, no box test is left on the sequential path),
-                    // resolves its own group with the ballot fixed point and publishes.
+                    // greedy chain.  A warp owns kChainGroups consecutive groups of 32 ranks (one candidate of
+                    // each group per lane).  While the earlier warps work it folds their published keep masks
+                    // into the dead bits of all its candidates; at its turn it resolves its groups one after the
+                    // other in registers (ballot + vote per group when no two live candidates of the group
+                    // overlap, the ballot fixed point otherwise) and publishes ONE 64-bit word per group
+                    // {kept count after the group + 1, keep mask}.  The hand-off between warps is a single
+                    // shared-memory store and a polled load; no box test is left on the sequential path.
                     {
                         const int groups = (C1 + 31) >> 5;
-                        if (w < groups) {
-                            const int b = (w << 5) + lane;
-                            const bool valid = b < C1;
-                            const uint32_t *row = Lm + (size_t)b * stride;     // rows up to C1r exist
-                            uint32_t dead = 0;
-                            uint32_t nxt = (w > 0) ? row[0] : 0u;
-                            for (int gp = 0; gp < w; ++gp) {
-                                const uint32_t cur = nxt;
-                                if (gp + 1 < w) nxt = row[gp + 1];
-                                while (*s_ready <= gp) __nanosleep(32);     // sleep: leave the issue slots to the resolving warp
-                                dead |= cur & (uint32_t)s_kmask[gp];
+                        const int g0 = w * kChainGroups;
+                        const uint32_t pub_addr = smem_u32(const_cast<unsigned long long *>(s_pub));
+                        if (g0 < groups) {
+                            const uint32_t *row[kChainGroups];
+                            uint32_t dead[kChainGroups];
+                            bool valid[kChainGroups];
+#pragma unroll
+                            for (int q = 0; q < kChainGroups; ++q) {
+                                const int b = ((g0 + q) << 5) + lane;
+                                valid[q] = b < C1;
+                                row[q] = Lm + (size_t)min(b, C1r - 1) * stride;        // rows up to C1r exist
+                                dead[q] = 0;
                             }
-                            int kc = (w > 0) ? s_kafter[w - 1] : 0;
-                            uint32_t keep = 0;
-                            if (kc < K) {
-                                const uint32_t lower = row[w];
-                                const bool me0 = valid && !dead;
-                                uint32_t und = __ballot_sync(0xffffffffu, me0);
-                                while (und) {
-                                    const bool me = me0 && ((und >> lane) & 1u);
-                                    const uint32_t know = __ballot_sync(0xffffffffu, me && !(lower & keep) && !(lower & und));
-                                    keep |= know;
-                                    const uint32_t dnow = __ballot_sync(0xffffffffu, me && (lower & keep));
-                                    und &= ~(know | dnow);
+                            int kc = 0;
+                            for (int gp = 0; gp < g0; ++gp) {
+                                uint32_t cur[kChainGroups];
+#pragma unroll
+                                for (int q = 0; q < kChainGroups; ++q) cur[q] = row[q][gp];
+                                unsigned long long pub;
+                                while ((pub = lds_volatile_u64(pub_addr + 8u * (uint32_t)gp)) == 0ull) {}
+#pragma unroll
+                                for (int q = 0; q < kChainGroups; ++q) dead[q] |= cur[q] & (uint32_t)pub;
+                                kc = (int)(pub >> 32) - 1;
+                            }
+                            uint32_t mine[kChainGroups];               // keep masks of my own groups
+                            int at[kChainGroups];                      // kept count before each of them
+                            // (the matrix words my groups need from each other were fetched while waiting)
+                            uint32_t lower_of[kChainGroups], cross[kChainGroups][kChainGroups];
+#pragma unroll
+                            for (int q = 0; q < kChainGroups; ++q) {
+                                lower_of[q] = (g0 + q < groups) ? row[q][g0 + q] : 0u;
+#pragma unroll
+                                for (int e = 0; e < q; ++e) cross[q][e] = (g0 + q < groups) ? row[q][g0 + e] : 0u;
+                            }
+#pragma unroll
+                            for (int q = 0; q < kChainGroups; ++q) {
+                                const int g = g0 + q;
+                                mine[q] = 0;
+                                at[q] = kc;
+                                if (g >= groups) continue;
+                                uint32_t keep = 0;
+                                int nk = 0;
+                                if (kc < K) {
+                                    uint32_t d = dead[q];
+#pragma unroll
+                                    for (int e = 0; e < q; ++e) d |= cross[q][e] & mine[e];
+                                    const uint32_t lower = lower_of[q];
+                                    const bool me0 = valid[q] && !d;
+                                    uint32_t und = __ballot_sync(0xffffffffu, me0);
+                                    if (!__any_sync(0xffffffffu, me0 && (lower & und))) {
+                                        keep = und;                    // no two live candidates of the group overlap
+                                    } else {
+                                        while (und) {
+                                            const bool me = me0 && ((und >> lane) & 1u);
+                                            const uint32_t know = __ballot_sync(0xffffffffu, me && !(lower & keep) && !(lower & und));
+                                            keep |= know;
+                                            const uint32_t dnow = __ballot_sync(0xffffffffu, me && (lower & keep));
+                                            und &= ~(know | dnow);
+                                        }
+                                    }
+                                    const int room = K - kc;
+                                    nk = __popc(keep);
+                                    if (nk > room) {
+                                        keep &= (1u << __fns(keep, 0, room + 1)) - 1u;
+                                        nk = room;
+                                    }
                                 }
-                                const int room = K - kc;
-                                int nk = __popc(keep);
-                                if (nk > room) {
-                                    keep &= (1u << __fns(keep, 0, room + 1)) - 1u;
-                                    nk = room;
-                                }
-                                if (lane == 0) {          // publish first: the successor only needs the mask and the count
-                                    s_kmask[w] = (int)keep;
-                                    s_kafter[w] = kc + nk;
-                                    __threadfence_block();
-                                    *s_ready = w + 1;
-                                }
-                                if ((keep >> lane) & 1u) kept[kc + __popc(keep & lanemask_lt())] = Traits::load_shared(s_tile + b);
+                                // publish first: the successors only need the mask and the count
+                                if (lane == 0)
+                                    sts_volatile_u64(pub_addr + 8u * (uint32_t)g, ((unsigned long long)(unsigned)(kc + nk + 1) << 32) | keep);
+                                mine[q] = keep;
                                 kc += nk;
-                            } else if (lane == 0) {
-                                s_kmask[w] = 0;
-                                s_kafter[w] = kc;
-                                __threadfence_block();
-                                *s_ready = w + 1;
+#ifdef RADNET_NMS_PROFILE
+                                if (lane == 0) prof[16 + g * 8 + 7] = clock64();      // after the hand-off
+#endif
+                                if (g == groups - 1 && lane == 0) *s_kcount = kc;
                             }
-                            if (w == groups - 1 && lane == 0) *s_kcount = kc;
+                            // the kept boxes themselves are only read after the block-wide barrier below
+#pragma unroll
+                            for (int q = 0; q < kChainGroups; ++q)
+                                if ((mine[q] >> lane) & 1u)
+                                    kept[at[q] + __popc(mine[q] & lanemask_lt())] = Traits::load_shared(s_tile + ((g0 + q) << 5) + lane);
                         }
                     }
                     __syncthreads();

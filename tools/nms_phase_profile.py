@@ -42,6 +42,10 @@ for seed in range(3):
             r = rows[w] - t0
             print("  row %2d gathered=%6d matrix=%6d wait_pred=%6d turn=%6d retired=%6d  (turn->retired %5d, prev retired->my turn %5d)" % (
                 w, r[0], r[1], r[2], r[3], r[4], r[4] - r[3], (r[3] - (rows[w - 1, 4] - t0)) if w else 0))
+    if seed == 0 and CLUSTER:
+        print("  chain groups (cycles between the publications of consecutive groups):",
+              [int(rows[g, 7] - rows[g - 1, 7]) if g else 0 for g in range(24)])
+        print("  first publication at", int(rows[0, 7] - st[7]), "cycles after 'blocks landed'; last at", int(rows[:24, 7].max() - st[7]))
     ps = ws[off + 8 * 8:off + 16 * 8].view(np.int64)
     print("seed", seed, " ".join("%s=%d" % (n, v) for n, v in zip(names[1:], d)), "total cycles", st[len(names) - 1] - st[0],
           "n_sorted", pipe.records.to_numpy()[0]["n_sorted"])

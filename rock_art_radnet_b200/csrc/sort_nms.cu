@@ -449,13 +449,16 @@ __device__ uint32_t select_threshold_sampled(const uint32_t *keys, int N, int ta
 constexpr int kBucketMax = 24;
 __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_t hi, unsigned long long *out,
                                 int cap, uint32_t *s_hist2k, int *s_start, int *s_scan, int *s_flag, int *s_valid,
-                                int *s_ties) {
+                                int *s_ties, long long *dbg = nullptr) {
+#define BS_STAMP(i) do { if (dbg && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
+    BS_STAMP(0);
     const uint32_t range = hi > t ? hi - t : 0u;
     const int bits = range ? 32 - __clz((int)range) : 0;
     const int shift = bits > 11 ? bits - 11 : 0;
     for (int i = threadIdx.x; i < kWideBins; i += kNmsThreads) s_hist2k[i] = 0;
     if (threadIdx.x == 0) { *s_flag = 0; *s_valid = 0; }
     __syncthreads();
+    BS_STAMP(1);
     // pass 1 over all keys: histogram of the selected ones (keys above `hi`, which may come from a sample,
     // share the top bin), count of the valid ones, and a per-thread bit mask of which of my keys are selected
     uint32_t mine = 0;
@@ -474,6 +477,7 @@ __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_
     nvalid = __reduce_add_sync(0xffffffffu, nvalid);
     if ((threadIdx.x & 31) == 0 && nvalid) atomicAdd(s_valid, nvalid);
     __syncthreads();
+    BS_STAMP(2);
     const int b0 = kWideBins - 1 - 2 * (int)threadIdx.x;           // thread order = descending key order
     const int c0 = (int)s_hist2k[b0], c1 = (int)s_hist2k[b0 - 1];
     int total;
@@ -482,6 +486,7 @@ __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_
     s_start[b0 - 1] = ex + c0;
     if (c0 > kBucketMax || c1 > kBucketMax || total > cap || N > 32 * kNmsThreads) *s_flag = 1;
     __syncthreads();
+    BS_STAMP(3);
     if (*s_flag) return -1;
     // pass 2 touches only the selected keys
     while (mine) {
@@ -494,6 +499,7 @@ __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_
         out[s_start[b] + slot] = ((unsigned long long)k << 32) | (unsigned)i;
     }
     __syncthreads();
+    BS_STAMP(4);
     int ties = 0;              // equal keys share a bucket: count the tied entries here, no extra pass
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -512,6 +518,8 @@ __device__ int bucket_sort_desc(const uint32_t *keys, int N, uint32_t t, uint32_
     }
     if (ties) atomicAdd(s_ties, ties);
     __syncthreads();
+    BS_STAMP(5);
+#undef BS_STAMP
     return total;
 }
 
@@ -745,7 +753,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                 const KeyT thr_key = select_threshold_sampled(raw_k, N, p.sel_target, hist, s_scan, s_sel, s_minmax);
                 NMS_STAMP();     // 2: threshold selected
                 const int got = bucket_sort_desc(raw_k, N, thr_key, s_minmax[1], sk, sk_cap, hist,
-                                                 reinterpret_cast<int *>(hist + kWideBins), s_scan, s_flag, &s_sel[2], s_ties);
+                                                 reinterpret_cast<int *>(hist + kWideBins), s_scan, s_flag, &s_sel[2], s_ties
+#ifdef RADNET_NMS_PROFILE
+                                                 , (crank == 0) ? prof + 300 : nullptr
+#endif
+                                                 );
                 NMS_STAMP();     // 3: (compacted)
                 if (got >= 0) {
                     S = got;

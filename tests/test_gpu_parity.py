@@ -384,3 +384,94 @@ def test_pipeline_batch_end_to_end(pkg):
         assert np.array_equal(pooled[b, :k], ref)
         assert not pooled[b, k:].any()                               # unused slots are zero-filled
     assert dets[2]["boxes"].shape[0] < 300
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def _device_panels(n, seed):
+    """n synthetic 600-px panels generated on the device: unique scores per panel, N(0,0.5) regression."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    N = 38 * 38 * 9
+    perm = torch.stack([torch.randperm(N, device="cuda", generator=g) for _ in range(n)])
+    cls = ((perm.float() + 0.5) / N).reshape(n, 38, 38, 9).contiguous()
+    regr = (0.5 * torch.randn((n, 38, 38, 36), device="cuda", generator=g)).contiguous()
+    return cls, regr
+
+
+def test_full_size_batch_properties(pkg):
+    """BASELINE configs[2] at full size (64 panels, 300 RoIs, 14x14x1024 pooling = 15.4 GB): the batch result
+    is (1) identical run to run, (2) identical, panel by panel, to single-panel launches (which take the
+    cluster form of sort+NMS) and to the reference's call pattern for the pooling (RoiPoolingConv on chunks of
+    20 RoIs), (3) equal to the CPU oracle on sampled panels."""
+    from rock_art_radnet_b200.pipeline import ProposalPipeline
+    from rock_art_radnet_b200.RoiPoolingConv import RoiPoolingConv
+    C = S.HotPathConfig()
+    B, H, W, Cn = 64, 38, 38, 1024
+    maps = [S.rpn_maps(300 + s, realistic=bool(s % 3 == 0)) for s in range(B)]
+    cls = torch.from_numpy(np.concatenate([m[0] for m in maps])).cuda()
+    regr = torch.from_numpy(np.concatenate([m[1] for m in maps])).cuda()
+    feat = torch.randn((B, H, W, Cn), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    pipe = ProposalPipeline(C, B, H, W, channels=Cn, pool_size=14, max_boxes=300, overlap_thresh=0.7)
+    rec, pooled = pipe(cls, regr, feat)
+    pipe.check_stats()
+    raw1 = rec.raw.clone()
+    sums1 = pooled.view(B, -1).double().sum(dim=1).clone()
+    rec, pooled = pipe(cls, regr, feat)
+    assert torch.equal(rec.raw, raw1) and torch.equal(pooled.view(B, -1).double().sum(dim=1), sums1)      # (1)
+    dets = rec.to_numpy()
+    assert all(d["boxes"].shape[0] == 300 for d in dets)
+    single = ProposalPipeline(C, 1, H, W, alloc_pooled=False)
+    layer = RoiPoolingConv(14, 20)
+    for b in (0, 17, 63):
+        single.decode(cls[b:b + 1], regr[b:b + 1])
+        single.sort_nms()
+        assert torch.equal(single.records.raw[0], rec.raw[b])                                               # (2)
+        R = dets[b]["boxes"].copy()
+        R[:, 2] -= R[:, 0]
+        R[:, 3] -= R[:, 1]
+        rois = torch.from_numpy(R).cuda()
+        for k in (0, 140, 280):
+            out = layer([feat[b:b + 1], rois[None, k:k + 20]])
+            assert torch.equal(out[0], pooled[b, k:k + 20])
+    for b in (5, 40):                                                                                       # (3)
+        want = O.rpn_to_roi(maps[b][0], maps[b][1], C, max_boxes=300, overlap_thresh=0.7)
+        assert np.array_equal(dets[b]["boxes"], want)
+        xywh = want.copy()
+        xywh[:, 2] -= xywh[:, 0]
+        xywh[:, 3] -= xywh[:, 1]
+        ref = O.roi_pooling_conv(feat[b:b + 1].cpu().numpy(), xywh[None, :40], 14)[0]
+        assert np.array_equal(pooled[b, :40].cpu().numpy(), ref)
+
+
+def test_sweep_records_do_not_depend_on_batching(pkg):
+    """BASELINE configs[4] in small: a sweep over 192 device-generated panels gives byte-identical detection
+    records whether it is cut into batches of 64, 16, 8 or 4 panels - i.e. whichever form of sort+NMS a launch
+    takes (one CTA per panel, clusters of 8, clusters of 16) - and whichever rank a panel lands on."""
+    from rock_art_radnet_b200 import sharding
+    from rock_art_radnet_b200.pipeline import ProposalPipeline
+    C = S.HotPathConfig()
+    n = 192
+    cls, regr = _device_panels(n, 11)
+    results = {}
+    for B in (64, 16, 8, 4):
+        pipe = ProposalPipeline(C, B, 38, 38, alloc_pooled=False)
+        out = []
+        for s in range(0, n, B):
+            pipe.decode(cls[s:s + B], regr[s:s + B])
+            pipe.sort_nms()
+            out.append(pipe.records.raw.clone())
+        pipe.check_stats()
+        results[B] = torch.cat(out)
+    for B in (16, 8, 4):
+        assert torch.equal(results[B], results[64]), "batch size %d" % B
+    assert int(results[64].view(torch.int32)[:, 0].min()) == 300
+    # sharded over 3 ranks (simulated): each rank's panels, gathered and reordered, give the same bytes
+    world, per = 3, 64
+    parts = []
+    for r in range(world):
+        ids = torch.from_numpy(sharding.shard_indices(n, r, world)).cuda()
+        pipe = ProposalPipeline(C, per, 38, 38, alloc_pooled=False)
+        pipe.decode(cls[ids], regr[ids])
+        pipe.sort_nms()
+        parts.append(pipe.records.raw.clone())
+    glob = sharding.gathered_to_global(torch.stack(parts), n)
+    assert torch.equal(glob, results[64])

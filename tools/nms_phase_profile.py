@@ -46,6 +46,9 @@ for seed in range(3):
         print("  chain groups (cycles between the publications of consecutive groups):",
               [int(rows[g, 7] - rows[g - 1, 7]) if g else 0 for g in range(24)])
         print("  first publication at", int(rows[0, 7] - st[7]), "cycles after 'blocks landed'; last at", int(rows[:24, 7].max() - st[7]))
+    if seed == 0:
+        bs = ws[off + 300 * 8:off + 306 * 8].view(np.int64)
+        print("  bucket sort (zero, pass 1 + histogram, scan, scatter, insertion + ties):", np.diff(bs).tolist())
     ps = ws[off + 8 * 8:off + 16 * 8].view(np.int64)
     print("seed", seed, " ".join("%s=%d" % (n, v) for n, v in zip(names[1:], d)), "total cycles", st[len(names) - 1] - st[0],
           "n_sorted", pipe.records.to_numpy()[0]["n_sorted"])

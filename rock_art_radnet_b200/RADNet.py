@@ -161,9 +161,14 @@ class RADNet:
         R[:, 2] -= R[:, 0]                                   # (x1,y1,x2,y2) -> (x,y,w,h), RADNet.py:564-565
         R[:, 3] -= R[:, 1]
         rois, P_cls, P_regr = self._head_outputs(R, F)
+        # every view gets a record of the same capacity (300 proposals at most, padded to whole chunks), so the
+        # records of all views of an image form one array for the merge kernels
+        n_rois = self.C.n_rois
+        cap = -(-300 // n_rois) * n_rois
+        out = DT.ClassRecords(1, max(cap, rois.shape[0]), torch.device("cuda:%d" % torch.cuda.current_device()))
         return DT.classify_nms(P_cls[None], P_regr[None], self.C, rois=rois[None],
                                bbox_threshold=self.bbox_threshold, nms_thresh=0.2, max_boxes=300,
-                               ratio=[ratio], origin=[[int(origin[0]), int(origin[1])]])
+                               ratio=[ratio], origin=[[int(origin[0]), int(origin[1])]], out=out)
 
     def predict(self, images):
         """images: list of HxWx3 arrays (the image types of one panel).  Returns the reference's list

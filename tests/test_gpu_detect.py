@@ -391,3 +391,26 @@ def test_in_count_limits_the_records_used(mods):
             assert np.array_equal(got_b[NAMES[c]], ob) and np.array_equal(got_p[NAMES[c]], op)
     nm = DT.class_nms(rec_in, 2, 3, 7, 0.4, in_count=[2, 3]).to_numpy()
     assert nm["header"][0, DT.H_NIN] == 60 and nm["header"][1, DT.H_NIN] == 90
+
+
+def test_predict_views_with_different_proposal_counts(mods):
+    """Small feature maps: every tile keeps a different number (< 300) of proposals, so the padded RoI
+    count differs from view to view; the merge still sees one array of equally sized records."""
+    pytest.importorskip("cv2")
+    RN, DT, _ = mods
+    C, images, _ = S.predict_case("w1000_h800_tiles")
+    objs = S.scene_objects(7, 1000, 800, n_obj=14)
+
+    def models():
+        return S.FakeRpnModel(seed=7, map_size=lambda w, h: (9, 8)), S.FakeDetectorModel(objs, C)
+
+    m_rpn, m_det = models()
+    got = RN.RADNet(C, m_rpn, m_det, lambda x: x).predict(images)
+    o_rpn, o_det = models()
+    fmt = RN.RADNet(C, None, None, lambda x: x).format_img
+    want = DO.RADNetOracle(C, o_rpn, o_det, fmt).predict(images)
+    assert m_det.calls == o_det.calls and m_det.calls < 6 * 15          # fewer chunks than 300 proposals would need
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a['class'] == b['class'] and a['prob'] == b['prob']
+        assert (a['x1'], a['y1'], a['x2'], a['y2']) == (b['x1'], b['y1'], b['x2'], b['y2'])

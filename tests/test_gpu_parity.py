@@ -475,3 +475,30 @@ def test_sweep_records_do_not_depend_on_batching(pkg):
         parts.append(pipe.records.raw.clone())
     glob = sharding.gathered_to_global(torch.stack(parts), n)
     assert torch.equal(glob, results[64])
+
+
+def test_pipelined_stream_equals_sequential_pipeline(pkg):
+    """PipelinedProposalStream (decode+NMS of batch k+1 under the pool of batch k) returns, batch by batch,
+    the bytes of the plain ProposalPipeline."""
+    from rock_art_radnet_b200.pipeline import PipelinedProposalStream, ProposalPipeline
+    C = S.HotPathConfig()
+    B, Cn = 6, 256
+    cls, regr = _device_panels(5 * B, 21)
+    feat = torch.randn((5 * B, 38, 38, Cn), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    seq = ProposalPipeline(C, B, 38, 38, channels=Cn, pool_size=7)
+    want = []
+    for k in range(5):
+        rec, pooled = seq(cls[k * B:(k + 1) * B], regr[k * B:(k + 1) * B], feat[k * B:(k + 1) * B])
+        want.append((rec.raw.clone(), pooled.clone()))
+    pipe = PipelinedProposalStream(C, B, 38, 38, channels=Cn, pool_size=7)
+    pipe.begin()
+    got = []
+    for k in range(5):
+        rec, pooled = pipe.submit(cls[k * B:(k + 1) * B], regr[k * B:(k + 1) * B], feat[k * B:(k + 1) * B])
+        # the slot's records stay valid until two submissions later; the shared pooled buffer until the next pool
+        with torch.cuda.stream(pipe.pool_stream):
+            got.append((rec.raw.clone(), pooled.clone()))
+    pipe.end()
+    torch.cuda.synchronize()
+    for (a, b), (c, d) in zip(got, want):
+        assert torch.equal(a, c) and torch.equal(b, d)

@@ -12,11 +12,19 @@
 //   np.round == rint() (half to even)                                (rpn.py:335-338)
 //   x/2. is evaluated as x*0.5: both are exact in binary floating point, the multiply is
 //   one DMUL instead of a ~25-instruction DDIV sequence
+//
+// Float32 shortcut: the four values that get rounded (x1, y1, w1, h1) are first evaluated in float32.
+// With every magnitude below 128 the float32 result is within 7 * 2^-24 * 128 = 5.4e-5 of the float64 one
+// (three roundings on the centre, six on the size incl. expf's 2 ulp, one on the difference), so whenever
+// it lies more than 2e-4 away from a half-integer, rintf() of it IS np.round() of the reference value;
+// the float64 path (two exp() in double) then runs only for the ~0.2 % of anchors near a rounding
+// boundary, for large maps / sizes, and for non-finite inputs.  Outputs stay bit-exact.
 #include "common.cuh"
 
 namespace radnet {
 
 constexpr int kDecodeCells = 64;      // cells per CTA
+static_assert(kDecodeCells == 64, "the write-out loop shifts by 6");
 constexpr int kDecodeThreads = 256;
 
 struct DecodedBox {
@@ -65,7 +73,7 @@ __device__ __forceinline__ DecodedBox decode_one(int c, int r, double aw, double
     // rows the reference deletes: (x1 - x2 >= 0) | (y1 - y2 >= 0)         (rpn.py:163)
     bool drop = (__dsub_rn(x, x2) >= 0.0) || (__dsub_rn(y, y2) >= 0.0);
     if (!drop) flags |= 1;
-    if (nan_any) flags |= 2;   // survives the delete and trips the NMS assert (rpn.py:400-401)
+    if (nan_any && !drop) flags |= 2;   // survives the delete and trips the NMS assert (rpn.py:400-401)
     if (!drop && !nan_any &&
         (x != rint(x) || y != rint(y) || x2 != rint(x2) || y2 != rint(y2)))
         flags |= 8;
@@ -73,10 +81,36 @@ __device__ __forceinline__ DecodedBox decode_one(int c, int r, double aw, double
     return o;
 }
 
+// float32 evaluation of one anchor; returns false when the float64 path has to decide
+__device__ __forceinline__ bool decode_fast(int c, int r, float wf, float hf, float4 t, int rows, int cols,
+                                            int4 &box, int &valid) {
+    const float txw = t.x * wf, tyh = t.y * hf;
+    const float cx1 = txw + (float)c, cy1 = tyh + (float)r;            // anchor centre is the cell corner (rpn.py:127-128, 325-326)
+    const float w1 = expf(t.z) * wf, h1 = expf(t.w) * hf;
+    const float x1 = cx1 - 0.5f * w1, y1 = cy1 - 0.5f * h1;
+    const float big = fmaxf(fmaxf(fmaxf(fabsf(txw), fabsf(tyh)), fmaxf(fabsf(cx1), fabsf(cy1))),
+                            fmaxf(fmaxf(w1, h1), fmaxf(fabsf(x1), fabsf(y1))));
+    // distance of each rounded value to the nearest half-integer
+    const float dx = fabsf(x1 - floorf(x1) - 0.5f), dy = fabsf(y1 - floorf(y1) - 0.5f);
+    const float dw = fabsf(w1 - floorf(w1) - 0.5f), dh = fabsf(h1 - floorf(h1) - 0.5f);
+    const float near = fminf(fminf(dx, dy), fminf(dw, dh));
+    // fmaxf / fminf drop NaN operands, so NaN is tested explicitly; inf fails the magnitude test
+    const bool no_nan = x1 == x1 && y1 == y1 && w1 == w1 && h1 == h1;
+    if (!no_nan || !(big < 128.f) || !(near > 2e-4f)) return false;
+    int x = __float2int_rn(x1), y = __float2int_rn(y1);
+    int w = max(1, __float2int_rn(w1)), h = max(1, __float2int_rn(h1));   // rpn.py:137-138
+    int x2 = w + x, y2 = h + y;                                        // rpn.py:143-144
+    x = max(0, x); y = max(0, y);                                      // rpn.py:147-148
+    x2 = min(cols - 1, x2); y2 = min(rows - 1, y2);                    // rpn.py:149-150
+    valid = !((x - x2 >= 0) || (y - y2 >= 0));                         // rpn.py:163
+    box = make_int4(x, y, x2, y2);
+    return true;
+}
+
 template <bool kF64>
 __global__ void __launch_bounds__(kDecodeThreads)
 decode_clip_kernel(const float *__restrict__ cls, const float *__restrict__ regr, int H, int W,
-                   int A, AnchorTable anchors, float std_scaling, int use_regr,
+                   int A, unsigned magic_a, unsigned magic_w, AnchorTable anchors, float std_scaling, int use_regr,
                    int32_t *__restrict__ boxes_i32, uint32_t *__restrict__ keys,
                    double *__restrict__ boxes_f64, float *__restrict__ scores,
                    uint8_t *__restrict__ valid, int32_t *__restrict__ stats) {
@@ -101,17 +135,34 @@ decode_clip_kernel(const float *__restrict__ cls, const float *__restrict__ regr
     const float4 *regr_b = reinterpret_cast<const float4 *>(regr + ((size_t)b * N + (size_t)cell0 * A) * 4);
     int n_valid = 0, n_nonfinite = 0, n_tie = 0, n_nonint = 0;
     for (int p = threadIdx.x; p < ncell * A; p += kDecodeThreads) {
-        int cl = p / A;
-        int a = p - cl * A;
-        int cell = cell0 + cl;
-        int r = cell / W, c = cell - r * W;
+        // p / A and cell / W by multiply-high with host-made reciprocals (exact in the checked ranges)
+        const int cl = magic_a ? (int)__umulhi((unsigned)p, magic_a) : p / A;
+        const int a = p - cl * A;
+        const int cell = cell0 + cl;
+        const int r = magic_w ? (int)__umulhi((unsigned)cell, magic_w) : cell / W;
+        const int c = cell - r * W;
         float4 t = __ldg(regr_b + p);
         float s = __ldg(cls_b + p);
         t.x = __fdiv_rn(t.x, std_scaling);
         t.y = __fdiv_rn(t.y, std_scaling);
         t.z = __fdiv_rn(t.z, std_scaling);
         t.w = __fdiv_rn(t.w, std_scaling);
-        DecodedBox d = decode_one(c, r, anchors.wh[a][0], anchors.wh[a][1], t, use_regr, H, W);
+        int4 fbox;
+        int fvalid = 0;
+        const double aw = anchors.wh[a][0], ah = anchors.wh[a][1];
+        if (use_regr && decode_fast(c, r, (float)aw, (float)ah, t, H, W, fbox, fvalid)) {
+            n_valid += fvalid;
+            if (kF64) {
+                s_boxd[a * kPad + cl] = make_double4((double)fbox.x, (double)fbox.y, (double)fbox.z, (double)fbox.w);
+                s_key[a * kPad + cl] = __float_as_uint(s);
+                reinterpret_cast<uint8_t *>(s_key + (size_t)A * kPad)[a * kPad + cl] = (uint8_t)fvalid;
+            } else {
+                s_box[a * kPad + cl] = fbox;
+                s_key[a * kPad + cl] = fvalid ? score_to_key(s) : 0u;
+            }
+            continue;
+        }
+        DecodedBox d = decode_one(c, r, aw, ah, t, use_regr, H, W);
         n_valid += d.flags & 1;
         n_nonfinite += (d.flags >> 1) & 1;
         n_tie += (d.flags >> 2) & 1;
@@ -145,8 +196,8 @@ decode_clip_kernel(const float *__restrict__ cls, const float *__restrict__ regr
 
     // transposed, coalesced write-out: anchor-major rows of ncell entries
     for (int p = threadIdx.x; p < ncell * A; p += kDecodeThreads) {
-        int a = p / ncell;
-        int cl = p - a * ncell;
+        const int a = (ncell == kDecodeCells) ? (p >> 6) : p / ncell;
+        const int cl = p - a * ncell;
         size_t o = (size_t)b * N + (size_t)a * HW + cell0 + cl;
         if (kF64) {
             double4 v = s_boxd[a * kPad + cl];
@@ -198,6 +249,10 @@ static int decode_common(bool f64, const float *cls, const float *regr, int B, i
     cudaStream_t st = (cudaStream_t)stream;
     RADNET_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4 * B, st));
     const int HW = H * W;
+    // floor(n / d) == umulhi(n, ceil(2^32 / d)) whenever n * d < 2^32
+    const unsigned magic_a = A > 1 ? (unsigned)((0x100000000ULL + (unsigned)A - 1) / (unsigned)A) : 0u;   // n < 64 * 64
+    const unsigned magic_w = ((unsigned long long)HW * (unsigned)W < 0x100000000ULL && W > 1)
+                                 ? (unsigned)((0x100000000ULL + (unsigned)W - 1) / (unsigned)W) : 0u;
     dim3 grid((HW + kDecodeCells - 1) / kDecodeCells, B);
     size_t per = f64 ? (sizeof(double4) + sizeof(uint32_t) + 1) : (sizeof(int4) + sizeof(uint32_t));
     size_t smem = (size_t)A * (kDecodeCells + 1) * per + 16;
@@ -205,12 +260,12 @@ static int decode_common(bool f64, const float *cls, const float *regr, int B, i
         RADNET_CUDA(cudaFuncSetAttribute(decode_clip_kernel<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         decode_clip_kernel<true><<<grid, kDecodeThreads, smem, st>>>(
-            cls, regr, H, W, A, tab, std_scaling, use_regr, nullptr, nullptr, boxes_f64, scores, valid, stats);
+            cls, regr, H, W, A, magic_a, magic_w, tab, std_scaling, use_regr, nullptr, nullptr, boxes_f64, scores, valid, stats);
     } else {
         RADNET_CUDA(cudaFuncSetAttribute(decode_clip_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         decode_clip_kernel<false><<<grid, kDecodeThreads, smem, st>>>(
-            cls, regr, H, W, A, tab, std_scaling, use_regr, boxes_i32, keys, nullptr, nullptr, nullptr, stats);
+            cls, regr, H, W, A, magic_a, magic_w, tab, std_scaling, use_regr, boxes_i32, keys, nullptr, nullptr, nullptr, stats);
     }
     return check_launch("decode_clip_kernel");
 }

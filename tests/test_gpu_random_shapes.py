@@ -117,3 +117,33 @@ def test_calc_region_props_and_calc_iou_random(pkg, seed):
         assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2].dtype == ref[2].dtype
         np.testing.assert_allclose(got[2], ref[2], rtol=1e-12, atol=0)
         assert np.array_equal(np.asarray(got[3]), np.asarray(ref[3]))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_decode_random_with_extremes(pkg, seed):
+    """K1 alone against the oracle's decode: random map shapes, regression spreads from 0.5 to 20 (so the
+    float32 shortcut, its float64 fallback near rounding boundaries and the large-magnitude path all run),
+    NaN and inf deltas planted in every fourth case."""
+    from rock_art_radnet_b200.pipeline import ProposalPipeline
+    rng = np.random.default_rng(1000 + seed)
+    C = S.HotPathConfig((64, 128, 256, 512) if seed % 3 == 0 else (128, 256, 512))
+    A = C.num_anchors
+    H, W = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+    cls = rng.random((1, H, W, A)).astype(np.float32)
+    regr = ([0.5, 2.0, 6.0, 20.0][seed % 4] * rng.standard_normal((1, H, W, 4 * A))).astype(np.float32)
+    if seed % 4 == 1:
+        regr.flat[rng.integers(0, regr.size, 25)] = np.float32(np.nan)
+        regr.flat[rng.integers(0, regr.size, 25)] = np.float32(np.inf)
+        regr.flat[rng.integers(0, regr.size, 25)] = np.float32(-np.inf)
+    pipe = ProposalPipeline(C, 1, H, W, alloc_pooled=False)
+    pipe.decode(torch.from_numpy(cls).cuda(), torch.from_numpy(regr).cuda())
+    boxes = pipe.boxes.cpu().numpy()[0]
+    keys = pipe.keys.cpu().numpy()[0]
+    stats = pipe.stats.cpu().numpy()[0]
+    with np.errstate(all="ignore"):
+        all_boxes, _, keep = O.decode_proposals(cls, regr, C)[:3]
+    finite = np.isfinite(all_boxes).all(axis=1)
+    ok = keep & finite
+    assert np.array_equal(keys != 0, ok)
+    assert np.array_equal(boxes[ok].astype(np.float64), all_boxes[ok])
+    assert stats[0] == keep.sum() and stats[1] == (keep & ~finite).sum() and stats[2] == 0

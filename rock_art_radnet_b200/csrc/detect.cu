@@ -497,6 +497,7 @@ struct ClusterParams {
     unsigned char *ws;      // int counter[S] (padded), then [S][n_cls] { int hdr[8]; DetEntry e[cap] }
     size_t ws_counters, ws_seg_stride, ws_cls_stride;
     int cap;                // entries per (segment, class) in shared memory (power of two)
+    int skip_if_done;       // plain NMS: leave segments whose record was already written by the bit-matrix kernel
 };
 
 enum { C_COUNT = 0, C_FIRST, C_TIES, C_DEGEN, C_EMPTY, C_NIN, C_FAULT, C_RANGE };
@@ -549,6 +550,9 @@ __global__ void __launch_bounds__(kDetThreads, 1) cluster_kernel(ClusterParams p
     unsigned char *ws_cls = ws_seg + (size_t)c * p.ws_cls_stride;
     int32_t *chdr = reinterpret_cast<int32_t *>(ws_cls);
     DetEntry *cout = reinterpret_cast<DetEntry *>(ws_cls + 32);
+    if (p.skip_if_done &&
+        reinterpret_cast<const volatile int32_t *>(p.rec_out + (size_t)seg * p.out_stride)[H_NDET] != -2)
+        return;               // few enough boxes: the bit-matrix kernel launched before this one has done the segment
     if (threadIdx.x < 8) s_stat[threadIdx.x] = (threadIdx.x == C_FIRST) ? 0x7fffffff : 0;
     __syncthreads();
 
@@ -950,7 +954,7 @@ static int fill_head(ClassNmsParams &p, const float *p_cls, const float *p_regr,
 static int launch_cluster(const void *rec_in, int in_max_det, int S, int n_in, const int32_t *in_count, int n_cls,
                           int average, double thr, double conf_thr, int n_obj_avg, int max_boxes,
                           const double *ratio, const int32_t *origin, void *rec_out, int out_max_det, void *ws,
-                          size_t ws_bytes, cudaStream_t st, const char *who) {
+                          size_t ws_bytes, cudaStream_t st, const char *who, int skip_if_done = 0) {
     long long total_cap = (long long)n_in * in_max_det;
     int cap = round_pow2((int)(total_cap < kClusterCap ? total_cap : kClusterCap));
     const size_t need = radnet_final_nms_workspace_bytes(S, n_in, in_max_det, n_cls);
@@ -969,6 +973,7 @@ static int launch_cluster(const void *rec_in, int in_max_det, int S, int n_in, c
     p.out_max_det = out_max_det;
     p.ws = reinterpret_cast<unsigned char *>(ws);
     p.cap = cap;
+    p.skip_if_done = skip_if_done;
     p.ws_counters = align_up((size_t)S * 4, 256);
     p.ws_cls_stride = 32 + (size_t)cap * sizeof(DetEntry);
     p.ws_seg_stride = (size_t)n_cls * p.ws_cls_stride;
@@ -1053,8 +1058,24 @@ extern "C" int radnet_class_nms(const void *rec_in, int in_max_det, int S, int n
         return launch_class_nms<kModeRecNms>(p, S, n_in * in_max_det, (cudaStream_t)stream);
     }
     RADNET_CHECK_ARG(ws, "class_nms: null workspace");
+    // The records can hold more than the bit-matrix kernel takes, but they rarely do: it goes first with its
+    // maximum capacity and marks the segments it could not hold (-2); the iterative kernel then only works on those.
+    int skip = 0;
+    if (n_in <= kMatrixCap) {
+        ClassNmsParams p{};
+        p.rec_in = reinterpret_cast<const unsigned char *>(rec_in);
+        p.in_stride = radnet_cls_record_bytes(in_max_det);
+        p.n_in = n_in; p.in_count = in_count; p.n_cls = n_cls;
+        p.thr = thr; p.max_boxes = max_boxes; p.ratio = ratio; p.origin = origin;
+        p.rec_out = reinterpret_cast<unsigned char *>(rec_out);
+        p.out_stride = radnet_cls_record_bytes(out_max_det);
+        p.out_max_det = out_max_det;
+        const int rc = launch_class_nms<kModeRecNms>(p, S, kMatrixCap, (cudaStream_t)stream);
+        if (rc) return rc;
+        skip = 1;
+    }
     return launch_cluster(rec_in, in_max_det, S, n_in, in_count, n_cls, 0, thr, 0.0, 0, max_boxes, ratio, origin,
-                          rec_out, out_max_det, ws, ws_bytes, (cudaStream_t)stream, "class_nms");
+                          rec_out, out_max_det, ws, ws_bytes, (cudaStream_t)stream, "class_nms", skip);
 }
 
 extern "C" int radnet_final_nms(const void *rec_in, int in_max_det, int S, int n_in, const int32_t *in_count,

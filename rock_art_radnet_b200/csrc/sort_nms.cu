@@ -44,6 +44,7 @@ constexpr int kTile = kNmsThreads;              // candidates per NMS tile
 constexpr int kMaxTableEntries = 65535;
 constexpr int kKeptSmemMax = 1024;              // kept boxes held in shared memory
 constexpr int kLookAhead = 6;                   // rows that may run ahead of the retiring row
+constexpr float kLeaderShare = 1.0f;            // cluster form: the leader's share of matrix work relative to a helper's
 constexpr int kChainGroups = 4;                 // cluster form: groups of 32 ranks resolved by one warp of the chain
 constexpr int kSmemHeader = 3072;               // barriers, misc words, scan scratch, row counts, 256-bin histogram
 
@@ -862,9 +863,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
                     NMS_STAMP();         // (cluster) candidates gathered
                     // my block of rows: row b costs ~b pair tests, so equal work means boundaries ~ sqrt
                     const int C1r = (C1 + 31) & ~31;
+                    // (the leader takes a smaller share: its rows need no copy, the helpers' blocks still
+                    // have to cross the cluster after they are computed)
                     auto bound = [&](uint32_t c) {
                         if (c >= csize) return C1r;
-                        const int v = (int)sqrtf((float)c / (float)csize * (float)C1r * (float)C1r);
+                        if (c == 0) return 0;
+                        const float lead = kLeaderShare / (float)csize;
+                        const float area = (csize > 1) ? lead + (float)(c - 1) * (1.f - lead) / (float)(csize - 1) : 1.f;
+                        const int v = (int)sqrtf(area * (float)C1r * (float)C1r);
                         return min(C1r, v & ~3);       // 4 rows of an odd number of words = a multiple of 16 bytes
                     };
                     const int b0 = bound(crank), b1 = bound(crank + 1);

@@ -414,3 +414,37 @@ def test_predict_views_with_different_proposal_counts(mods):
     for a, b in zip(got, want):
         assert a['class'] == b['class'] and a['prob'] == b['prob']
         assert (a['x1'], a['y1'], a['x2'], a['y2']) == (b['x1'], b['y1'], b['x2'], b['y2'])
+
+
+def test_empty_inputs(mods):
+    """Nothing clears the threshold / no boxes at all: every stage returns empty records, the mirror class
+    returns what the reference returns ({} / [] / [])."""
+    RN, DT, torch = mods
+    C = _config()
+    dev = torch.device("cuda")
+    R = S.random_rois(1, 40)[0]
+    pc = np.zeros((1, 40, 7), np.float32)
+    pc[..., 6] = 1.0                                            # everything is 'bg'
+    pr = np.zeros((1, 40, 24), np.float32)
+    rec = DT.classify_nms(pc, pr, C, rois=R[None].astype(np.int32))
+    host = rec.to_numpy()
+    DT.check_records(host, "empty")
+    assert host["header"][0, DT.H_NDET] == 0 and host["header"][0, DT.H_NCLASSES] == 0 and (host["order"][0] == -1).all()
+    pc[..., 6], pc[..., 0] = 0.4, 0.6                           # best class below bbox_threshold
+    assert DT.classify_decode(pc, pr, C, rois=R[None].astype(np.int32)).to_numpy()["header"][0, DT.H_NDET] == 0
+    tiles = DT.ClassRecords(6, 300, dev)                        # six tiles without detections
+    merged = DT.final_nms_records(tiles, 2, 3, 7)
+    final = DT.class_nms(merged, 1, 2, 7, 0.4).to_numpy()
+    DT.check_records(merged.to_numpy(), "empty")
+    assert (merged.to_numpy()["header"][:, DT.H_NDET] == 0).all() and final["header"][0, DT.H_NDET] == 0
+    assert DT.record_to_dicts(final[0], NAMES) == ({}, {})
+
+    class NoRois:
+        def predict(self, inputs):
+            raise AssertionError("the detector must not be called without RoIs")
+
+    net = RN.RADNet(C, None, NoRois(), lambda x: x)
+    assert net.apply_spatial_pyramid_pooling(np.zeros((0, 4), np.int64), None) == ({}, {})
+    assert net.final_nms(np.zeros((0, 4)), np.zeros((0,))) == []
+    from rock_art_radnet_b200.rpn import non_max_suppression_fast
+    assert non_max_suppression_fast(np.zeros((0, 4)), np.zeros((0,))) == []

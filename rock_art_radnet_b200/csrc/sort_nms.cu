@@ -1382,14 +1382,21 @@ extern "C" int radnet_sort_nms_i32(const int32_t *boxes_i32, const uint32_t *key
     if (pl.smem_sort) {
         // few panels: a cluster of 8-16 CTAs per panel shares the overlap tests (latency path);
         // many panels: one CTA per panel keeps every SM on its own panel (throughput path)
-        if (const int cs = choose_cluster(pl, B))
-            return launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>, pl, B, cs, st);
+        if (const int cs = choose_cluster(pl, B)) {
+            // a refused cluster launch (nothing has run yet) is not an error: the one-CTA form does the same job
+            if (launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>, pl, B, cs, st) == RADNET_OK)
+                return RADNET_OK;
+            cudaGetLastError();
+        }
         if (pl.kept_smem) return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true>, pl, B, st);
         return launch(sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, false>, pl, B, st);
     }
     if (pl.staged_only) {
-        if (const int cs = choose_cluster(pl, B))
-            return launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true, true, true>, pl, B, cs, st);
+        if (const int cs = choose_cluster(pl, B)) {
+            if (launch_cluster(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true, true, true>, pl, B, cs, st) == RADNET_OK)
+                return RADNET_OK;
+            cudaGetLastError();
+        }
         return launch(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true, false, true>, pl, B, st);
     }
     if (pl.kept_smem) return launch(sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true>, pl, B, st);

@@ -55,3 +55,28 @@ def test_elf_is_sm_100a_only():
     out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = {ln.split(".")[-2] for ln in out.splitlines() if "ELF file" in ln}
     assert archs == {"sm_100a"}, archs
+
+
+def test_cluster_form_uses_dsmem_bulk_copy_and_cluster_barriers():
+    funcs = _sass()
+    # <BoxI32, uint32 keys, uint16 idx, smem sort, kept in smem, kCluster = true, ...>
+    cluster = [v for k, v in funcs.items() if "sort_nms_kernelINS_6BoxI32EjtLb1ELb1ELb1" in k]
+    one_cta = [v for k, v in funcs.items() if "sort_nms_kernelINS_6BoxI32EjtLb1ELb1ELb0" in k]
+    assert len(cluster) == 1 and len(one_cta) == 1
+    text = "\n".join(cluster[0])
+    assert "UBLKCP.S.S" in text                              # cp.async.bulk shared::cta -> shared::cluster (matrix blocks)
+    assert "UBLKCP.S.G" in text                              # cp.async.bulk global -> shared (key staging)
+    assert "UCGABAR_ARV" in text and "UCGABAR_WAIT" in text  # split barrier.cluster phases
+    assert "UCGABAR" not in "\n".join(one_cta[0])            # the one-CTA form has no cluster traffic
+    # the staged-only layout (12 anchors, 600x800 px) has a cluster form too
+    assert any("sort_nms_kernelINS_6BoxI32EjjLb0ELb1ELb1ELb1" in k for k in funcs)
+
+
+def test_detection_kernels_keep_float64_divide_and_float32_rules():
+    funcs = _sass()
+    det = {k: "\n".join(v) for k, v in funcs.items() if "class_nms_kernel" in k or "cluster_kernel" in k}
+    assert len(det) == 4                                     # decode, head+NMS, records+NMS, cluster (final_nms)
+    for name, text in det.items():
+        assert "DFMA" in text or "MUFU.RCP64H" in text, name  # float64 decode / exact inter/(union+1e-6) divide
+        if "class_nms_kernelILi0" not in name:                 # every form but decode-only builds ballot bit masks
+            assert "VOTE" in text, name

@@ -15,7 +15,9 @@
  *     `h_` (host).  Buffers are caller-allocated; sizes of scratch areas come
  *     from the matching `*_workspace_bytes` function.
  *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous with
- *     respect to the host.  The library keeps no global device state.
+ *     respect to the host.  The library keeps no device state of its own: every buffer,
+ *     including scratch, belongs to the caller.  Host-side it keeps only per-device
+ *     caches of device attributes (atomics) and the tuning options below.
  *   - return value: 0 = RADNET_OK, negative = RADNET_E_*.  Nothing throws.
  *     `radnet_last_error_string()` returns a thread-local description.
  *   - there is no CPU fallback: without a CUDA device every compute entry point
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RADNET_ABI_VERSION 1
+#define RADNET_ABI_VERSION 2
 
 enum {
     RADNET_OK = 0,
@@ -58,6 +60,15 @@ const char *radnet_error_name(int code);
 /* Device facts used by the host to size launches: out[0]=SM count, out[1]=max opt-in
  * shared memory per block, out[2]=compute capability major*10+minor. */
 int radnet_device_info(int *h_out3);
+
+/* Process-wide tuning options, read (atomically) by every launch.  Each is seeded once, when the
+ * library is loaded, from the environment variable RADNET_<NAME IN CAPITALS>.  Every value gives the
+ * same results; the options choose between equivalent code paths (tests use them to exercise all of
+ * them):  nms_cluster (-1 auto, 0 one CTA per panel), nms_cluster_size (0 auto | 2 | 4 | 8 | 16),
+ * nms_cluster_ranks, nms_sel_target, nms_lookahead (0 = default), roipool_force_direct (0 | 1),
+ * roipool_form (0 auto | 1 whole-map slices | 2 row bands), targets_hit_cap (0 = default). */
+int radnet_set_option(const char *h_name, long long value);
+int radnet_get_option(const char *h_name, long long *h_value);
 
 /* ---------------------------------------------------------------- K1: decode + clip
  * Replaces the anchor loop of rpn_to_roi (reference faster_rcnn/rpn.py:91-166) and
@@ -143,41 +154,63 @@ int radnet_roi_pool(const float *feat, int B, int H, int W, int C, const void *d
 
 /* --------------------------------------------------- K3: RPN anchor target assignment
  * Replaces the deterministic part of calc_region_props (reference faster_rcnn/utils.py:
- * 585-775 and 815-816; upstream name calc_rpn) for B panels.  The RNG-driven 256-region
- * subsampling (utils.py:777-813) stays on the host in the Python shim.
+ * 585-775 and 815-816; upstream name calc_rpn) for B panels, in ONE launch.  The RNG-driven
+ * 256-region subsampling (utils.py:777-813) is radnet_rpn_subsample below.
  *   gt        [B][Gmax][4] float64 x1,x2,y1,y2 in resized-image pixels (utils.py:608-613)
  *   gt_is_bg  [B][Gmax]    uint8, 1 = class 'bg' (utils.py:690)
  *   gt_count  [B]          int32
  *   h_anchor_px [A][2]     float64 anchor (w,h) in pixels, a = ratio_idx + n_ratios*size_idx
  *   img_wh    [B][2]       float64 resized width,height (utils.py:629,638)
  *   n_ratios               len(anchor_box_ratios), to split a into (ratio_idx,size_idx)
- * Outputs (channel-first, as returned by the reference):
- *   y_rpn_cls  [B][2A][H][W] float64 = [valid | overlap]              (utils.py:815)
- *   y_rpn_regr [B][8A][H][W] float64 = [repeat(overlap,4) | regr]     (utils.py:816)
+ *   layout                 RADNET_TARGETS_CHANNEL_FIRST: as returned by the reference
+ *                            y_rpn_cls  [B][2A][H][W] float64 = [valid | overlap]          (utils.py:815)
+ *                            y_rpn_regr [B][8A][H][W] float64 = [repeat(overlap,4) | regr] (utils.py:816)
+ *                          RADNET_TARGETS_NHWC: as the training loop consumes them (utils.py:477-478)
+ *                            y_rpn_cls  [B][H][W][2A],  y_rpn_regr [B][H][W][8A]
+ *   regr_scale             factor applied to the regr half (1.0, or C.std_scaling: utils.py:475)
  *   best_anchor [B][Gmax][4] int32 {jy, ix, ratio_idx, size_idx} or -1 (utils.py:697)
  *   n_hits      [B][Gmax]    int32 positives per GT before forcing    (utils.py:707)
- */
-size_t radnet_rpn_targets_workspace_bytes(int B, int Gmax);
+ *   ws          scratch of radnet_rpn_targets_workspace_bytes(B,Gmax,H,W,A) bytes.  Its first part is
+ *               per-panel state that every successful launch leaves zeroed: call
+ *               radnet_rpn_targets_workspace_init once after allocating it (and after a failed launch).
+ * Both output tensors must be 16-byte aligned. */
+enum { RADNET_TARGETS_CHANNEL_FIRST = 0, RADNET_TARGETS_NHWC = 1 };
+size_t radnet_rpn_targets_workspace_bytes(int B, int Gmax, int H, int W, int A);
+int radnet_rpn_targets_workspace_init(void *ws, size_t ws_bytes, int B, int Gmax, void *stream);
 int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, const int32_t *gt_count,
                        int B, int Gmax, int H, int W, int A, int n_ratios,
                        const double *h_anchor_px, double rpn_stride, const double *img_wh,
-                       double max_overlap, double *y_rpn_cls, double *y_rpn_regr,
-                       int32_t *best_anchor, int32_t *n_hits, void *ws, size_t ws_bytes,
-                       void *stream);
+                       double max_overlap, int layout, double regr_scale, double *y_rpn_cls,
+                       double *y_rpn_regr, int32_t *best_anchor, int32_t *n_hits, void *ws,
+                       size_t ws_bytes, void *stream);
 
 /* ----------------------------------------------------------- a4: RoI target assignment
  * Replaces the per-RoI loop of calc_iou (reference faster_rcnn/rpn.py:209-282).
  *   rois   [R][4] int32 x1,y1,x2,y2;  gt [G][4] float64 x1,x2,y1,y2 in feature cells
- *   (already rounded by the host, rpn.py:197-200);  gt_class [G] int32 class index.
- *   bg_class  index of 'bg';  n_cls = len(class_mapping);  regr_std [4].
+ *   (already rounded by the host, rpn.py:197-200);  gt_class [G] int32 class index, -1 = the
+ *   figure's class is not in class_mapping (only an error if it is some RoI's best match).
+ *   bg_class  index of 'bg' = n_cls-1;  n_cls = len(class_mapping);  regr_std [4].
  * Outputs compacted in RoI order: x_roi [R][4] int32 (x,y,w,h), y_class [R][n_cls] int32,
  * y_regr [R][8*(n_cls-1)] float64 = [labels | coords], ious [R] float64,
+ * best_gt [R] int32 (index of the matched figure of a positive row, -1 for 'bg' rows; may be NULL),
  * count [1] int32 = number of rows written.
  */
 int radnet_roi_targets(const int32_t *rois, int R, const double *gt, const int32_t *gt_class,
                        int G, int n_cls, int bg_class, double min_overlap, double max_overlap,
                        const double *h_regr_std4, int32_t *x_roi, int32_t *y_class,
-                       double *y_regr, double *ious, int32_t *count, void *stream);
+                       double *y_regr, double *ious, int32_t *best_gt, int32_t *count, void *stream);
+
+/* The same for B panels in one launch (one CTA per panel) - the training path right after K2.
+ * RoIs: det != NULL: the kept boxes of the B detection records (xyxy); else rois [B][R][4] int32
+ * xyxy with roi_count [B] (NULL = R).  gt [B][Gmax][4], gt_class [B][Gmax], gt_count [B] (NULL = Gmax).
+ * Outputs are [B][R][...] with rows >= count[b] left untouched. */
+int radnet_roi_targets_batch(const void *det, int det_max_boxes, const int32_t *rois,
+                             const int32_t *roi_count, int B, int R, const double *gt,
+                             const int32_t *gt_class, const int32_t *gt_count, int Gmax, int n_cls,
+                             int bg_class, double min_overlap, double max_overlap,
+                             const double *h_regr_std4, int32_t *x_roi, int32_t *y_class,
+                             double *y_regr, double *ious, int32_t *best_gt, int32_t *count,
+                             void *stream);
 
 /* utils.iou(a, b) (reference faster_rcnn/utils.py:77-109) for n box pairs: a, b [n][4] float64
  * (x1,y1,x2,y2) -> out [n] float64; 0.0 for degenerate boxes, else inter/(union+1e-6). */

@@ -17,6 +17,8 @@ c_double = ctypes.c_double
 c_float = ctypes.c_float
 c_longlong = ctypes.c_longlong
 
+ABI_VERSION = 2      # RADNET_ABI_VERSION of include/radnet_b200.h
+
 # name -> (restype, argtypes); mirrors include/radnet_b200.h one to one
 SIGNATURES = {
     "radnet_det_record_bytes": (c_size_t, [c_int]),
@@ -37,13 +39,20 @@ SIGNATURES = {
                                c_void_p, c_size_t, c_void_p]),
     "radnet_roi_pool": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                 c_int, c_int, c_void_p, c_void_p]),
-    "radnet_rpn_targets_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "radnet_set_option": (c_int, [ctypes.c_char_p, c_longlong]),
+    "radnet_get_option": (c_int, [ctypes.c_char_p, c_void_p]),
+    "radnet_rpn_targets_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "radnet_rpn_targets_workspace_init": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "radnet_rpn_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                   c_void_p, c_double, c_void_p, c_double, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+                                   c_void_p, c_double, c_void_p, c_double, c_int, c_double, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "radnet_roi_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_double,
                                    c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_void_p]),
+    "radnet_roi_targets_batch": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                         c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
     "radnet_iou_pairs": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     "radnet_real_coordinates": (c_int, [c_void_p, c_longlong, c_double, c_void_p, c_void_p]),
     "radnet_cls_record_bytes": (c_size_t, [c_int]),
@@ -86,8 +95,9 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = ABI mismatch, also loud
         fn.restype = res
         fn.argtypes = args
-    if lib.radnet_version() != 1:
-        raise ImportError("libradnet_b200.so ABI version %d != 1" % lib.radnet_version())
+    if lib.radnet_version() != ABI_VERSION:
+        raise ImportError("libradnet_b200.so ABI version %d != %d - rebuild it with "
+                          "`python -m rock_art_radnet_b200.build`" % (lib.radnet_version(), ABI_VERSION))
     _lib = lib
     return lib
 
@@ -104,3 +114,30 @@ def call(name, *args):
 
 def det_record_bytes(max_boxes):
     return int(load().radnet_det_record_bytes(int(max_boxes)))
+
+
+def set_option(name, value):
+    """Process-wide tuning option of the library (include/radnet_b200.h, radnet_set_option)."""
+    call("radnet_set_option", name.encode(), int(value))
+
+
+def get_option(name):
+    out = ctypes.c_longlong(0)
+    call("radnet_get_option", name.encode(), ctypes.addressof(out))
+    return int(out.value)
+
+
+class option:
+    """`with option("nms_cluster", 0): ...` - set an option for a block, restore it afterwards."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = get_option(self.name)
+        set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.old)
+        return False

@@ -1,6 +1,10 @@
 // capi.cu - error plumbing and device facts for the C ABI in include/radnet_b200.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -20,7 +24,89 @@ int cuda_fail(cudaError_t e, const char *what) {
     return RADNET_E_CUDA;
 }
 
+// ---- options ---------------------------------------------------------------------------------------
+static const char *const kOptionNames[kOptCount] = {
+    "nms_cluster", "nms_cluster_size", "nms_cluster_ranks", "nms_sel_target",
+    "nms_lookahead", "roipool_force_direct", "targets_hit_cap", "roipool_form"};
+static const long long kOptionDefaults[kOptCount] = {-1, 0, 0, 0, 0, 0, 0, 0};
+
+struct OptionTable {
+    std::atomic<long long> v[kOptCount];
+    OptionTable() {
+        for (int i = 0; i < kOptCount; ++i) {
+            long long val = kOptionDefaults[i];
+            char env[64] = "RADNET_";
+            size_t n = strlen(env);
+            for (const char *c = kOptionNames[i]; *c && n + 1 < sizeof(env); ++c)
+                env[n++] = (char)((*c >= 'a' && *c <= 'z') ? *c - 32 : *c);
+            env[n] = 0;
+            if (const char *e = getenv(env)) val = atoll(e);
+            v[i].store(val, std::memory_order_relaxed);
+        }
+    }
+};
+static OptionTable g_options;       // built when the library is loaded
+
+long long get_option(int opt) { return g_options.v[opt].load(std::memory_order_relaxed); }
+
+static int option_index(const char *name) {
+    if (!name) return -1;
+    for (int i = 0; i < kOptCount; ++i)
+        if (strcmp(name, kOptionNames[i]) == 0) return i;
+    return -1;
+}
+
+// ---- per-device facts ------------------------------------------------------------------------------
+static std::atomic<int> g_smem_optin[64];
+static std::atomic<int> g_sm_count[64];
+
+static int cached_attr(std::atomic<int> *table, cudaDeviceAttr attr, int dev) {
+    if (dev < 0 || dev >= 64) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, attr, dev) != cudaSuccess) return -1;
+        return v;
+    }
+    int v = table[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
+    cudaError_t e = cudaDeviceGetAttribute(&v, attr, dev);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaDeviceGetAttribute");
+        return -1;
+    }
+    table[dev].store(v, std::memory_order_relaxed);
+    return v;
+}
+
+int device_smem_optin(int dev) { return cached_attr(g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); }
+int device_sm_count(int dev) { return cached_attr(g_sm_count, cudaDevAttrMultiProcessorCount, dev); }
+
+static std::mutex g_attr_mutex;
+int SmemAttrCache::ensure(const void *func, int dev, size_t bytes) {
+    if (bytes <= 48 * 1024) return RADNET_OK;
+    const int d = (dev >= 0 && dev < 64) ? dev : 0;
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    if ((size_t)granted[d] >= bytes && dev == d) return RADNET_OK;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    if (dev == d) granted[d] = (int)bytes;
+    return RADNET_OK;
+}
+
 }  // namespace radnet
+
+extern "C" int radnet_set_option(const char *name, long long value) {
+    const int i = radnet::option_index(name);
+    RADNET_CHECK_ARG(i >= 0, "set_option: unknown option '%s'", name ? name : "(null)");
+    radnet::g_options.v[i].store(value, std::memory_order_relaxed);
+    return RADNET_OK;
+}
+
+extern "C" int radnet_get_option(const char *name, long long *h_value) {
+    const int i = radnet::option_index(name);
+    RADNET_CHECK_ARG(i >= 0 && h_value, "get_option: unknown option '%s'", name ? name : "(null)");
+    *h_value = radnet::get_option(i);
+    return RADNET_OK;
+}
 
 extern "C" int radnet_version(void) { return RADNET_ABI_VERSION; }
 

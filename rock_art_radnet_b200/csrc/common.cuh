@@ -42,6 +42,34 @@ struct AnchorTable {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- process-wide tuning options (radnet_set_option / radnet_get_option) ---------------------------
+// Atomics, seeded once from the environment (RADNET_<NAME>) when the library is loaded; launches only
+// read them.  Any value gives the same results - they select between equivalent code paths.
+enum Option {
+    kOptNmsCluster = 0,      // nms_cluster: -1 auto, 0 never, 1 when it fits
+    kOptNmsClusterSize,      // nms_cluster_size: 0 auto, else 2/4/8/16
+    kOptNmsClusterRanks,     // nms_cluster_ranks: 0 auto
+    kOptNmsSelTarget,        // nms_sel_target: 0 auto
+    kOptNmsLookahead,        // nms_lookahead: 0 auto
+    kOptRoipoolForceDirect,  // roipool_force_direct: 0/1
+    kOptTargetsHitCap,       // targets_hit_cap: 0 auto
+    kOptRoipoolForm,         // roipool_form: 0 auto, 1 whole-map slices, 2 cluster halves
+    kOptCount
+};
+long long get_option(int opt);
+
+// max opt-in shared memory per block of device `dev`, cached per device; -1 (error set) on failure
+int device_smem_optin(int dev);
+// SM count of device `dev`, cached per device
+int device_sm_count(int dev);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch needs more than was already
+// granted on that device (one instance per kernel, function-local static)
+struct SmemAttrCache {
+    int granted[64] = {};
+    int ensure(const void *func, int dev, size_t bytes);
+};
+
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
 

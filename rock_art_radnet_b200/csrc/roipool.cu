@@ -286,7 +286,10 @@ __global__ void __launch_bounds__(256) roi_pool_direct_kernel(RoiPoolParams p) {
 
 template <int LANES>
 static int launch_slice(const RoiPoolParams &p, int B, size_t smem, cudaStream_t st) {
-    RADNET_CUDA(cudaFuncSetAttribute(roi_pool_slice_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static SmemAttrCache smem_cache;        // one per LANES instantiation
+    int dev = 0;
+    RADNET_CUDA(cudaGetDevice(&dev));
+    if (int rc = smem_cache.ensure(reinterpret_cast<const void *>(roi_pool_slice_kernel<LANES>), dev, smem)) return rc;
     roi_pool_slice_kernel<LANES><<<B * p.n_slices, kPoolThreads, smem, st>>>(p);
     return check_launch("roi_pool_slice_kernel");
 }
@@ -295,11 +298,8 @@ static int launch_slice(const RoiPoolParams &p, int B, size_t smem, cudaStream_t
 
 using namespace radnet;
 
-// RADNET_ROIPOOL_FORCE_DIRECT=1 forces the direct kernel (parity tests exercise both)
-static bool force_direct() {
-    const char *e = getenv("RADNET_ROIPOOL_FORCE_DIRECT");
-    return e && e[0] == '1';
-}
+// option roipool_force_direct = 1 forces the direct kernel (parity tests exercise both)
+static bool force_direct() { return get_option(kOptRoipoolForceDirect) == 1; }
 
 extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, const void *det, int det_max_boxes,
                                const int32_t *rois, const int32_t *roi_count, int rois_per_panel, int pool,
@@ -318,9 +318,10 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
     p.rois = rois; p.roi_count = roi_count; p.R = rois_per_panel; p.pool = pool; p.out = out;
     cudaStream_t st = (cudaStream_t)stream;
 
-    int dev = 0, smem_limit = 0;
+    int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
-    RADNET_CUDA(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int smem_limit = device_smem_optin(dev);
+    if (smem_limit < 0) return RADNET_E_CUDA;
     const size_t HW = (size_t)H * W;
     const size_t per_roi = (size_t)pool * sizeof(YEntry) + sizeof(int2);
     if (C % 4 == 0 && !force_direct() && HW < 65536 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&

@@ -33,6 +33,9 @@
 // bit-exactly like NumPy.
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace radnet {
@@ -1152,14 +1155,15 @@ struct NmsPlan {
     SortNmsParams p;
 };
 
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return dev;
+}
+
 static int max_optin_smem() {
-    static int v = -1;
-    if (v < 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 232448;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) v = 232448;
-    }
-    return v;
+    const int v = device_smem_optin(current_device());
+    return v > 0 ? v : 232448;
 }
 
 template <typename Cand, typename KeyT>
@@ -1180,20 +1184,17 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
     // first sort round: about this many top-scoring candidates (see the kernel)
     p.sel_target = (4 * K > 2048) ? 4 * K : 2048;
     p.look_ahead = kLookAhead;
-    if (const char *e = getenv("RADNET_NMS_LOOKAHEAD")) {     // tuning knob (any value is correct)
-        int v = atoi(e);
-        if (v >= 1 && v <= 32) p.look_ahead = v;
-    }
-    if (const char *e = getenv("RADNET_NMS_SEL_TARGET")) {
-        int v = atoi(e);
-        if (v >= 32) p.sel_target = v;
+    {   // tuning knobs (any value is correct)
+        const long long la = get_option(kOptNmsLookahead), stg = get_option(kOptNmsSelTarget);
+        if (la >= 1 && la <= 32) p.look_ahead = (int)la;
+        if (stg >= 32 && stg <= (1 << 20)) p.sel_target = (int)stg;
     }
     // cluster form: ranks resolved through the overlap matrix (about 2.5 K candidates yield K keeps at 0.7)
     p.cluster_ranks = (int)align_up((size_t)(5 * K / 2), 32);
     if (p.cluster_ranks > kTile) p.cluster_ranks = kTile;
-    if (const char *e = getenv("RADNET_NMS_CLUSTER_RANKS")) {
-        int v = atoi(e);
-        if (v >= 64 && v <= kTile) p.cluster_ranks = (v + 31) & ~31;
+    {
+        const long long v = get_option(kOptNmsClusterRanks);
+        if (v >= 64 && v <= kTile) p.cluster_ranks = ((int)v + 31) & ~31;
     }
     // shared-memory sort: keys ping-pong + uint16 index ping-pong
     size_t cap = align_up((size_t)N, 64);
@@ -1244,21 +1245,32 @@ static NmsPlan make_plan(int N, int max_boxes, int table_entries, bool allow_sme
 // very few panels that many clusters fit, 8 (the portable maximum) for a few more, otherwise one CTA per
 // panel.  RADNET_NMS_CLUSTER_SIZE forces 2, 4, 8 or 16; RADNET_NMS_CLUSTER=0 turns the form off.
 static int forced_cluster_size() {
-    static int v = -1;
-    if (v < 0) {
-        v = 0;
-        if (const char *e = getenv("RADNET_NMS_CLUSTER_SIZE")) {
-            const int q = atoi(e);
-            if (q == 2 || q == 4 || q == 8 || q == 16) v = q;
+    const long long q = get_option(kOptNmsClusterSize);
+    return (q == 2 || q == 4 || q == 8 || q == 16) ? (int)q : 0;
+}
+
+// per-kernel, per-device record of the function attributes already set (dynamic shared memory, non-portable
+// cluster size), so that a launch does not call cudaFuncSetAttribute again
+template <typename K>
+static int ensure_attrs(K kernel, size_t smem_bytes, bool nonportable) {
+    static SmemAttrCache smem_cache;
+    static std::atomic<unsigned long long> np_done{0};
+    const int dev = current_device();
+    int rc = smem_cache.ensure(reinterpret_cast<const void *>(kernel), dev, smem_bytes);
+    if (rc) return rc;
+    if (nonportable) {
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (!(np_done.load(std::memory_order_relaxed) & bit)) {
+            RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            np_done.fetch_or(bit, std::memory_order_relaxed);
         }
     }
-    return v;
+    return RADNET_OK;
 }
 
 template <typename K>
 static int launch_cluster(K kernel, const NmsPlan &pl, int B, int cs, cudaStream_t st) {
-    RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    if (cs > 8) RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (int rc = ensure_attrs(kernel, pl.smem_bytes, cs > 8)) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * cs));
     cfg.blockDim = dim3(kNmsThreads);
@@ -1278,7 +1290,7 @@ static int launch_cluster(K kernel, const NmsPlan &pl, int B, int cs, cudaStream
 
 template <typename K>
 static int launch(K kernel, const NmsPlan &pl, int B, cudaStream_t st) {
-    RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    if (int rc = ensure_attrs(kernel, pl.smem_bytes, false)) return rc;
     kernel<<<B, kNmsThreads, pl.smem_bytes, st>>>(pl.p);
     return check_launch("sort_nms_kernel");
 }
@@ -1291,10 +1303,13 @@ __global__ void make_keys64_kernel(const double *probs, const uint8_t *valid, in
 // clusters of `cs` CTAs of the hot-path kernel that the device can hold at once (a cluster needs its SMs
 // inside one GPC, so this is fewer than SMs / cs); cached per plan size
 static int max_active_clusters(const NmsPlan &pl, int cs) {
-    static size_t cached_smem[2][17] = {{0}};
-    static int cached_n[2][17] = {{0}};
-    size_t *cached_smem_row = cached_smem[pl.staged_only ? 1 : 0];
-    int *cached = cached_n[pl.staged_only ? 1 : 0];
+    static std::mutex mtx;
+    static size_t cached_smem[64][2][17] = {{{0}}};
+    static int cached_n[64][2][17] = {{{0}}};
+    const int dev = current_device() & 63;
+    std::lock_guard<std::mutex> lock(mtx);
+    size_t *cached_smem_row = cached_smem[dev][pl.staged_only ? 1 : 0];
+    int *cached = cached_n[dev][pl.staged_only ? 1 : 0];
     if (cached_smem_row[cs] == pl.smem_bytes) return cached[cs];
     const void *kernel = pl.staged_only
         ? (const void *)sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true, true, true>
@@ -1325,9 +1340,7 @@ static int max_active_clusters(const NmsPlan &pl, int cs) {
 // cluster size for a launch of B panels; 0 = one CTA per panel
 static int choose_cluster(const NmsPlan &pl, int B) {
     if (!(pl.smem_sort || pl.staged_only) || !pl.kept_smem) return 0;
-    if (const char *e = getenv("RADNET_NMS_CLUSTER")) {
-        if (atoi(e) == 0) return 0;
-    }
+    if (get_option(kOptNmsCluster) == 0) return 0;
     if (const int f = forced_cluster_size()) return B <= max_active_clusters(pl, f) ? f : 0;
     if (B <= max_active_clusters(pl, 16)) return 16;
     if (B <= max_active_clusters(pl, 8)) return 8;

@@ -149,18 +149,13 @@ def apply_regr_np(X, T):
         return X
 
 
-def calc_iou(R, img_data, C, class_mapping):
-    """Classifier-head targets for proposals R (n,4) x1,y1,x2,y2 (reference rpn.py:176-296).
-
-    Returns (X (1,n',4) int64 xywh, Y1 (1,n',n_cls) int64 one-hot, Y2 (1,n',8(n_cls-1))
-    [labels | coords], IoUs list) or (None,)*4 when no RoI reaches classifier_min_overlap."""
+def gt_feature_cells(img_data, C, class_mapping):
+    """Figures of one image in feature cells, as calc_iou builds them (reference rpn.py:185-200):
+    (gta (G,4) float64 x1,x2,y1,y2 - Python banker's rounding -, class index (G,) int32 with -1 for a
+    class name that is not in class_mapping)."""
     bboxes = img_data['bboxes']
     width, height = img_data['width'], img_data['height']
     rw, rh = get_new_img_size(width, height, C.img_size)                      # rpn.py:189
-    n_cls = len(class_mapping)
-    bg = class_mapping['bg']
-    if bg != n_cls - 1:
-        raise ValueError("calc_iou: class_mapping['bg'] must be the last index")
     gta = np.zeros((len(bboxes), 4))
     gcls = np.zeros((len(bboxes),), dtype=np.int32)
     for k, bb in enumerate(bboxes):                                           # rpn.py:193-200
@@ -168,7 +163,73 @@ def calc_iou(R, img_data, C, class_mapping):
         gta[k, 1] = int(round(bb['x2'] * (rw / float(width)) / C.rpn_stride))
         gta[k, 2] = int(round(bb['y1'] * (rh / float(height)) / C.rpn_stride))
         gta[k, 3] = int(round(bb['y2'] * (rh / float(height)) / C.rpn_stride))
-        gcls[k] = class_mapping[bb['class']]
+        # a class missing from class_mapping only matters if the figure is some RoI's best match
+        # (the reference looks the name up at rpn.py:263, after the match)
+        gcls[k] = class_mapping.get(bb['class'], -1)
+    return gta, gcls
+
+
+def _check_bg_last(class_mapping):
+    n_cls = len(class_mapping)
+    bg = class_mapping['bg']
+    if bg != n_cls - 1:
+        # the reference sizes the regression block as 4*(n_cls-1) and indexes it with 4*class_num
+        # (rpn.py:266-273): with 'bg' anywhere else its rows become ragged lists - not a defined layout
+        raise ValueError("calc_iou: class_mapping['bg'] must be the last index")
+    return n_cls, bg
+
+
+class RoiTargetBatch:
+    """Batched classifier-head targets (calc_iou, reference rpn.py:209-282) for B panels in one launch,
+    device-resident: the training path right after K2.
+
+    `run` takes the figures of every panel in feature cells (`gt_feature_cells`) and the RoIs either as
+    the detection records of `ProposalPipeline.sort_nms` (det=...) or as a dense (B,R,4) int32 xyxy
+    tensor, and returns CUDA tensors compacted per panel in RoI order (rows >= count[b] are stale):
+      x_roi (B,R,4) int32 xywh, y_class (B,R,n_cls) int32 one-hot, y_regr (B,R,8(n_cls-1)) float64
+      [labels | coords], ious (B,R) float64, best_gt (B,R) int32 (-1 for 'bg' rows), count (B,) int32."""
+
+    def __init__(self, C, class_mapping, batch, R, Gmax, device=None):
+        D.require_cuda()
+        _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.C = C
+        self.n_cls, self.bg = _check_bg_last(class_mapping)
+        self.B, self.R, self.Gmax = int(batch), int(R), int(Gmax)
+        dev = self.device
+        n_regr = 4 * (self.n_cls - 1)
+        self.x_roi = D.empty((self.B, self.R, 4), np.int32, dev)
+        self.y_class = D.empty((self.B, self.R, self.n_cls), np.int32, dev)
+        self.y_regr = D.empty((self.B, self.R, 2 * n_regr), np.float64, dev)
+        self.ious = D.empty((self.B, self.R), np.float64, dev)
+        self.best_gt = D.empty((self.B, self.R), np.int32, dev)
+        self.count = D.zeros((self.B,), np.int32, dev)
+        self._std = D.host_f64(C.classifier_regr_std)
+
+    def run(self, gt_cells, gt_class, gt_count, det=None, rois=None, roi_count=None):
+        """gt_cells (B,Gmax,4) float64, gt_class (B,Gmax) int32, gt_count (B,) int32 or None: CUDA tensors.
+        det: DetectionRecords (its max_boxes >= R) or rois (B,R,4) int32 xyxy [+ roi_count (B,) int32]."""
+        C = self.C
+        det_raw = det.raw if det is not None else None
+        _lib.call("radnet_roi_targets_batch", D.ptr(det_raw), det.max_boxes if det is not None else 0,
+                  D.ptr(rois), D.ptr(roi_count), self.B, self.R, D.ptr(gt_cells), D.ptr(gt_class),
+                  D.ptr(gt_count), self.Gmax, self.n_cls, self.bg, float(C.classifier_min_overlap),
+                  float(C.classifier_max_overlap), D.ptr(self._std), D.ptr(self.x_roi), D.ptr(self.y_class),
+                  D.ptr(self.y_regr), D.ptr(self.ious), D.ptr(self.best_gt), D.ptr(self.count),
+                  D.stream_ptr(self.device))
+        return self.x_roi, self.y_class, self.y_regr, self.ious, self.best_gt, self.count
+
+
+def calc_iou(R, img_data, C, class_mapping):
+    """Classifier-head targets for proposals R (n,4) x1,y1,x2,y2 (reference rpn.py:176-296).
+
+    Returns (X (1,n',4) int64 xywh, Y1 (1,n',n_cls) int64 one-hot, Y2 (1,n',8(n_cls-1))
+    [labels | coords], IoUs list) or (None,)*4 when no RoI reaches classifier_min_overlap.
+    KeyError when the best-matching figure of a positive RoI has a class outside class_mapping
+    (rpn.py:263); ValueError unless 'bg' is the last class index."""
+    bboxes = img_data['bboxes']
+    n_cls, bg = _check_bg_last(class_mapping)
+    gta, gcls = gt_feature_cells(img_data, C, class_mapping)
     R = np.asarray(R)
     n = int(R.shape[0])
     if n == 0:
@@ -184,14 +245,19 @@ def calc_iou(R, img_data, C, class_mapping):
     y_cls = D.empty((n, n_cls), np.int32, dev)
     y_regr = D.empty((n, 2 * n_regr), np.float64, dev)
     ious = D.empty((n,), np.float64, dev)
+    best_gt = D.empty((n,), np.int32, dev)
     count = D.zeros((1,), np.int32, dev)
     _lib.call("radnet_roi_targets", D.ptr(r_dev), n, D.ptr(g_dev), D.ptr(c_dev), G, n_cls, int(bg),
               float(C.classifier_min_overlap), float(C.classifier_max_overlap),
               D.ptr(D.host_f64(C.classifier_regr_std)), D.ptr(x_roi), D.ptr(y_cls), D.ptr(y_regr),
-              D.ptr(ious), D.ptr(count), D.stream_ptr(dev))
+              D.ptr(ious), D.ptr(best_gt), D.ptr(count), D.stream_ptr(dev))
     m = int(count.cpu().numpy()[0])
     if m == 0:
         return None, None, None, None                                         # rpn.py:284-285
+    if (gcls < 0).any():
+        for g in best_gt[:m].cpu().numpy():
+            if g >= 0 and gcls[g] < 0:
+                raise KeyError(bboxes[int(g)]['class'])                       # class_mapping[cls_name], rpn.py:263
     X = x_roi[:m].cpu().numpy().astype(np.int64)
     Y1 = y_cls[:m].cpu().numpy().astype(np.int64)
     Y2 = y_regr[:m].cpu().numpy()

@@ -42,28 +42,48 @@ def iou(a, b):
     return float(iou_pairs([a[:4]], [b[:4]])[0])
 
 
+LAYOUT_CHANNEL_FIRST = 0      # RADNET_TARGETS_CHANNEL_FIRST: the reference's return layout (utils.py:815-816)
+LAYOUT_NHWC = 1               # RADNET_TARGETS_NHWC: what the training loop feeds the losses (utils.py:477-478)
+
+
 class RpnTargetBatch:
     """Pre-allocated batched RPN target assignment (K3) for B panels with up to Gmax figures each.
 
-    `run` launches `radnet_rpn_targets` on the current stream and returns the resident output
-    tensors (overwritten by the next call): y_rpn_cls (B,2A,H,W), y_rpn_regr (B,8A,H,W) float64,
-    best_anchor (B,Gmax,4) int32, n_hits (B,Gmax) int32 - BEFORE the RNG subsampling of
-    utils.py:777-813."""
+    `run` launches `radnet_rpn_targets` (one kernel) on the current stream and returns the resident
+    output tensors (overwritten by the next call) - BEFORE the RNG subsampling of utils.py:777-813:
 
-    def __init__(self, C, batch, Gmax, H, W, device=None):
+      layout=LAYOUT_CHANNEL_FIRST  y_rpn_cls (B,2A,H,W), y_rpn_regr (B,8A,H,W) float64
+      layout=LAYOUT_NHWC           y_rpn_cls (B,H,W,2A), y_rpn_regr (B,H,W,8A) float64 with the regr half
+                                   multiplied by `regr_scale` (C.std_scaling: utils.py:475)
+      best_anchor (B,Gmax,4) int32, n_hits (B,Gmax) int32."""
+
+    def __init__(self, C, batch, Gmax, H, W, device=None, layout=LAYOUT_CHANNEL_FIRST, regr_scale=1.0):
         D.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.C, self.B, self.Gmax, self.H, self.W = C, int(batch), int(Gmax), int(H), int(W)
         self.A = len(C.anchor_box_scales) * len(C.anchor_box_ratios)
+        self.layout, self.regr_scale = int(layout), float(regr_scale)
         dev = self.device
-        self.y_cls = D.empty((self.B, 2 * self.A, self.H, self.W), np.float64, dev)
-        self.y_regr = D.empty((self.B, 8 * self.A, self.H, self.W), np.float64, dev)
-        self.best = D.empty((self.B, max(self.Gmax, 1), 4), np.int32, dev)
-        self.hits = D.zeros((self.B, max(self.Gmax, 1)), np.int32, dev)
-        self.ws_bytes = int(self.lib.radnet_rpn_targets_workspace_bytes(self.B, self.Gmax))
+        A, B = self.A, self.B
+        if self.layout == LAYOUT_NHWC:
+            self.y_cls = D.empty((B, self.H, self.W, 2 * A), np.float64, dev)
+            self.y_regr = D.empty((B, self.H, self.W, 8 * A), np.float64, dev)
+        else:
+            self.y_cls = D.empty((B, 2 * A, self.H, self.W), np.float64, dev)
+            self.y_regr = D.empty((B, 8 * A, self.H, self.W), np.float64, dev)
+        self.best = D.empty((B, max(self.Gmax, 1), 4), np.int32, dev)
+        self.hits = D.zeros((B, max(self.Gmax, 1)), np.int32, dev)
+        self.ws_bytes = int(self.lib.radnet_rpn_targets_workspace_bytes(B, self.Gmax, self.H, self.W, A))
         self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
+        self.reset_workspace()
         self._anchors = anchor_pixels(C)
+
+    def reset_workspace(self):
+        """Zero the per-panel state at the head of the workspace (once after allocation; every
+        successful launch leaves it zeroed again)."""
+        _lib.call("radnet_rpn_targets_workspace_init", D.ptr(self.ws), self.ws_bytes, self.B, self.Gmax,
+                  D.stream_ptr(self.device))
 
     def run(self, gt_boxes, gt_is_bg, gt_count, img_wh):
         """gt_boxes (B,Gmax,4) float64 x1,x2,y1,y2 in resized pixels, gt_is_bg (B,Gmax) uint8,
@@ -71,12 +91,14 @@ class RpnTargetBatch:
         C = self.C
         _lib.call("radnet_rpn_targets", D.ptr(gt_boxes), D.ptr(gt_is_bg), D.ptr(gt_count), self.B, self.Gmax,
                   self.H, self.W, self.A, len(C.anchor_box_ratios), D.ptr(self._anchors), float(C.rpn_stride),
-                  D.ptr(img_wh), float(C.rpn_max_overlap), D.ptr(self.y_cls), D.ptr(self.y_regr),
-                  D.ptr(self.best), D.ptr(self.hits), D.ptr(self.ws), self.ws_bytes, D.stream_ptr(self.device))
+                  D.ptr(img_wh), float(C.rpn_max_overlap), self.layout, self.regr_scale, D.ptr(self.y_cls),
+                  D.ptr(self.y_regr), D.ptr(self.best), D.ptr(self.hits), D.ptr(self.ws), self.ws_bytes,
+                  D.stream_ptr(self.device))
         return self.y_cls, self.y_regr, self.best[:, :self.Gmax], self.hits[:, :self.Gmax]
 
 
-def rpn_targets_device(C, gt_boxes, gt_is_bg, gt_count, H, W, img_wh, device=None):
+def rpn_targets_device(C, gt_boxes, gt_is_bg, gt_count, H, W, img_wh, device=None,
+                       layout=LAYOUT_CHANNEL_FIRST, regr_scale=1.0):
     """One-shot batched call (allocates its outputs).  gt_boxes (B,Gmax,4) float64 x1,x2,y1,y2 in
     resized pixels, gt_is_bg (B,Gmax) uint8, gt_count (B,) int32, img_wh (B,2) float64; NumPy or
     CUDA tensors.  Returns CUDA tensors as RpnTargetBatch.run."""
@@ -85,7 +107,7 @@ def rpn_targets_device(C, gt_boxes, gt_is_bg, gt_count, H, W, img_wh, device=Non
     gt_count = D.to_device(gt_count, np.int32, dev)
     B = int(gt_count.shape[0])
     Gmax = int(gt_boxes.shape[1]) if gt_boxes is not None else 0
-    batch = RpnTargetBatch(C, B, Gmax, H, W, device=dev)
+    batch = RpnTargetBatch(C, B, Gmax, H, W, device=dev, layout=layout, regr_scale=regr_scale)
     gt_dev = D.to_device(gt_boxes, np.float64, dev) if Gmax else None
     bg_dev = D.to_device(gt_is_bg, np.uint8, dev) if Gmax else None
     wh_dev = D.to_device(img_wh, np.float64, dev)

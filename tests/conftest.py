@@ -53,3 +53,18 @@ def dense_regr(g, name):
     out = np.zeros(int(np.prod(shape)))
     out[g[name + "/y_rpn_regr_nz_idx"]] = g[name + "/y_rpn_regr_nz_val"]
     return out.reshape(shape)
+
+
+@pytest.fixture
+def lib_option():
+    """lib_option(name, value): set a tuning option of libradnet_b200 for the duration of one test."""
+    from rock_art_radnet_b200 import _lib
+    saved = {}
+
+    def setter(name, value):
+        saved.setdefault(name, _lib.get_option(name))
+        _lib.set_option(name, value)
+
+    yield setter
+    for name, value in saved.items():
+        _lib.set_option(name, value)

@@ -25,14 +25,14 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_sizes_without_gpu():
     from rock_art_radnet_b200 import _lib
     lib = _lib.load()
-    assert lib.radnet_version() == 1
+    assert lib.radnet_version() == _lib.ABI_VERSION
     assert lib.radnet_det_record_bytes(300) == 16 + 300 * 24
     assert lib.radnet_det_record_bytes(7) % 16 == 0
     assert lib.radnet_error_name(0) == b"RADNET_OK" and lib.radnet_error_name(-2) == b"RADNET_E_CUDA"
     ws = lib.radnet_sort_nms_i32_workspace_bytes(64, 12996, 38, 38, 300)
     assert ws >= 64 * 12996 * 16 and ws % 256 == 0
     assert lib.radnet_nms_f64_workspace_bytes(1000, 300) > 1000 * 8 * 3
-    assert lib.radnet_rpn_targets_workspace_bytes(64, 20) >= 64 * 20 * 8
+    assert lib.radnet_rpn_targets_workspace_bytes(64, 20, 38, 38, 9) >= 64 * (20 * 12 + 9 * 38 * 38 * 8)
 
 
 def test_argument_errors_are_reported_not_thrown():

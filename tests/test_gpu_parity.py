@@ -228,9 +228,9 @@ def test_rpn_targets_batched_presample_vs_oracle(pkg):
         assert np.array_equal(hits[b, :g], nh)
 
 
-def test_rpn_targets_hit_list_overflow_replay(pkg, monkeypatch):
+def test_rpn_targets_hit_list_overflow_replay(pkg, lib_option):
     """With a 3-entry positive-cell list the kernel must fall back to the figure-by-figure replay."""
-    monkeypatch.setenv("RADNET_TARGETS_HIT_CAP", "3")
+    lib_option("targets_hit_cap", 3)
     C = S.HotPathConfig()
     img = S.gt_figures(6, 30, 1000, 700, classes=("boat", "human"))
     wr, hr = O.get_new_img_size(1000, 700, C.img_size)
@@ -332,8 +332,8 @@ def test_roi_pooling_conv_vs_oracle(pkg, H, W, Cn, pool):
     assert np.array_equal(got, ref), "expected bit-exact float32 (no FMA contraction)"
 
 
-def test_roi_pooling_direct_kernel_matches(pkg, monkeypatch):
-    monkeypatch.setenv("RADNET_ROIPOOL_FORCE_DIRECT", "1")
+def test_roi_pooling_direct_kernel_matches(pkg, lib_option):
+    lib_option("roipool_force_direct", 1)
     feat = S.feature_map(2, 38, 38, 256)
     rois = _all_size_rois(38, 38)
     got = pkg.RoiPoolingConv(14, rois.shape[1])([feat, rois])

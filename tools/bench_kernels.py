@@ -149,13 +149,34 @@ def main():
         gt_d = torch.from_numpy(gt).cuda(); bg_d = torch.from_numpy(bg).cuda()
         cnt_d = torch.full((B,), G, dtype=torch.int32, device="cuda")
         wh_d = torch.tensor([[600.0, 600.0]] * B, dtype=torch.float64, device="cuda")
-        tb = RpnTargetBatch(C, B, G, 38, 38)
-        t = time_ms(lambda: tb.run(gt_d, bg_d, cnt_d, wh_d))
         nbytes = B * (G * 32 + 10 * 9 * 38 * 38 * 8)
-        res["rpn_targets_B%d" % B] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
-                                          frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk,
-                                          note="2 memsets + rpn_targets_kernel + finalize kernel, pre-allocated outputs")
-        del tb
+        for tag, kw in (("", {}), ("_nhwc", dict(layout=1, regr_scale=4.0))):
+            tb = RpnTargetBatch(C, B, G, 38, 38, **kw)
+            t = time_ms(lambda: tb.run(gt_d, bg_d, cnt_d, wh_d))
+            res["rpn_targets%s_B%d" % (tag, B)] = dict(
+                t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
+                frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk,
+                note="one launch (fill team + compute team + last-CTA finalize), pre-allocated outputs, L2 flushed")
+            del tb
+
+    # ---- a4, batched: 64 panels x 300 RoIs x 20 figures straight from the detection records ----
+    from rock_art_radnet_b200.rpn import RoiTargetBatch, gt_feature_cells
+    B = 64
+    cls, regr = tile_maps(B)
+    pipe = ProposalPipeline(C, B, 38, 38, alloc_pooled=False)
+    pipe.decode(cls, regr)
+    pipe.sort_nms()
+    gtc = np.zeros((B, G, 4)); gcl = np.zeros((B, G), np.int32)
+    for b in range(B):
+        a_, c_ = gt_feature_cells(S.gt_figures(b, G, classes=("boat", "human")), C, C.class_mapping)
+        gtc[b], gcl[b] = a_, c_
+    rt = RoiTargetBatch(C, C.class_mapping, B, 300, G)
+    gtc_d, gcl_d = torch.from_numpy(gtc).cuda(), torch.from_numpy(gcl).cuda()
+    cnt_d = torch.full((B,), G, dtype=torch.int32, device="cuda")
+    res["roi_targets_batch_B64"] = dict(time_ms(lambda: rt.run(gtc_d, gcl_d, cnt_d, det=pipe.records)),
+                                        note="radnet_roi_targets_batch, one CTA per panel, L2 flushed")
+    res["roi_targets_batch_B64_graph"] = time_graph_ms(lambda: rt.run(gtc_d, gcl_d, cnt_d, det=pipe.records))
+    del pipe, rt
 
     # ---- a4 ----------------------------------------------------------------------------
     import rock_art_radnet_b200 as R

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Stress of the cluster form of sort+NMS: thousands of launches over random panels, batch sizes and NMS
-settings; every result must equal the one-CTA form (RADNET_NMS_CLUSTER=0 is read per launch)."""
+settings; every result must equal the one-CTA form (the nms_cluster option is read per launch)."""
 import os
 import sys
 import time
@@ -11,6 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rock_art_radnet_b200 import synthetic as S  # noqa: E402
+from rock_art_radnet_b200 import _lib  # noqa: E402
 from rock_art_radnet_b200.pipeline import ProposalPipeline  # noqa: E402
 
 torch.cuda.set_device(0)
@@ -39,10 +40,10 @@ for trial in range(60):
             cls = ((perm.float() + 0.5) / N).reshape(B, H, W, A).contiguous()
         spread = [0.5, 1.5, 0.1][rep % 3]       # 0.1: heavy overlap, the slice may run out (second round)
         regr = (spread * torch.randn((B, H, W, 4 * A), device="cuda", generator=g)).contiguous()
-        os.environ["RADNET_NMS_CLUSTER"] = "1"
+        _lib.set_option("nms_cluster", 1)
         pipe.decode(cls, regr)
         pipe.sort_nms()
-        os.environ["RADNET_NMS_CLUSTER"] = "0"
+        _lib.set_option("nms_cluster", 0)
         ref.decode(cls, regr)
         ref.sort_nms()
         torch.cuda.synchronize()

@@ -81,14 +81,41 @@ int device_smem_optin(int dev) { return cached_attr(g_smem_optin, cudaDevAttrMax
 int device_sm_count(int dev) { return cached_attr(g_sm_count, cudaDevAttrMultiProcessorCount, dev); }
 
 static std::mutex g_attr_mutex;
-int SmemAttrCache::ensure(const void *func, int dev, size_t bytes) {
+struct AttrEntry {
+    const void *func;
+    int dev;
+    size_t smem;
+    bool nonportable;
+};
+static AttrEntry g_attr[256];
+static int g_attr_n = 0;
+
+static AttrEntry *attr_entry(const void *func, int dev) {       // caller holds g_attr_mutex
+    for (int i = 0; i < g_attr_n; ++i)
+        if (g_attr[i].func == func && g_attr[i].dev == dev) return &g_attr[i];
+    if (g_attr_n >= 256) return nullptr;                        // table full: fall back to setting every time
+    g_attr[g_attr_n] = AttrEntry{func, dev, 0, false};
+    return &g_attr[g_attr_n++];
+}
+
+int ensure_dynamic_smem(const void *func, int dev, size_t bytes) {
     if (bytes <= 48 * 1024) return RADNET_OK;
-    const int d = (dev >= 0 && dev < 64) ? dev : 0;
     std::lock_guard<std::mutex> lock(g_attr_mutex);
-    if ((size_t)granted[d] >= bytes && dev == d) return RADNET_OK;
-    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    if (dev == d) granted[d] = (int)bytes;
+    AttrEntry *e = attr_entry(func, dev);
+    if (e && e->smem >= bytes) return RADNET_OK;
+    cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    if (e) e->smem = bytes;
+    return RADNET_OK;
+}
+
+int ensure_nonportable_clusters(const void *func, int dev) {
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    AttrEntry *e = attr_entry(func, dev);
+    if (e && e->nonportable) return RADNET_OK;
+    cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)");
+    if (e) e->nonportable = true;
     return RADNET_OK;
 }
 

@@ -63,12 +63,11 @@ int device_smem_optin(int dev);
 // SM count of device `dev`, cached per device
 int device_sm_count(int dev);
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch needs more than was already
-// granted on that device (one instance per kernel, function-local static)
-struct SmemAttrCache {
-    int granted[64] = {};
-    int ensure(const void *func, int dev, size_t bytes);
-};
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch of `func` on device `dev` needs more
+// than was already granted (a process-wide table keyed by kernel and device, mutex-protected)
+int ensure_dynamic_smem(const void *func, int dev, size_t bytes);
+// cudaFuncSetAttribute(NonPortableClusterSizeAllowed) once per kernel and device
+int ensure_nonportable_clusters(const void *func, int dev);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

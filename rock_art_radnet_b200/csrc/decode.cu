@@ -256,14 +256,14 @@ static int decode_common(bool f64, const float *cls, const float *regr, int B, i
     dim3 grid((HW + kDecodeCells - 1) / kDecodeCells, B);
     size_t per = f64 ? (sizeof(double4) + sizeof(uint32_t) + 1) : (sizeof(int4) + sizeof(uint32_t));
     size_t smem = (size_t)A * (kDecodeCells + 1) * per + 16;
+    int dev = 0;
+    RADNET_CUDA(cudaGetDevice(&dev));
     if (f64) {
-        RADNET_CUDA(cudaFuncSetAttribute(decode_clip_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(decode_clip_kernel<true>), dev, smem)) return rc;
         decode_clip_kernel<true><<<grid, kDecodeThreads, smem, st>>>(
             cls, regr, H, W, A, magic_a, magic_w, tab, std_scaling, use_regr, nullptr, nullptr, boxes_f64, scores, valid, stats);
     } else {
-        RADNET_CUDA(cudaFuncSetAttribute(decode_clip_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(decode_clip_kernel<false>), dev, smem)) return rc;
         decode_clip_kernel<false><<<grid, kDecodeThreads, smem, st>>>(
             cls, regr, H, W, A, magic_a, magic_w, tab, std_scaling, use_regr, boxes_i32, keys, nullptr, nullptr, nullptr, stats);
     }

@@ -890,9 +890,10 @@ __global__ void real_coordinates_kernel(const int32_t *__restrict__ v, long long
 }
 
 static int optin_smem() {
-    int dev = 0, v = 232448;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    return v;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 232448;
+    const int v = device_smem_optin(dev);
+    return v > 0 ? v : 232448;
 }
 
 static size_t matrix_smem_bytes(int cap, int words) {
@@ -918,7 +919,11 @@ static int launch_class_nms(ClassNmsParams &p, int S, int cap, cudaStream_t st) 
         set_error("class_nms: %d entries need %zu B of shared memory", p.cap, smem);
         return RADNET_E_UNSUPPORTED;
     }
-    RADNET_CUDA(cudaFuncSetAttribute(class_nms_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        int dev = 0;
+        RADNET_CUDA(cudaGetDevice(&dev));
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(class_nms_kernel<kMode>), dev, smem)) return rc;
+    }
     class_nms_kernel<kMode><<<S, kDetThreads, smem, st>>>(p);
     return check_launch("class_nms_kernel");
 }
@@ -982,7 +987,11 @@ static int launch_cluster(const void *rec_in, int in_max_det, int S, int n_in, c
         set_error("%s: %zu B of shared memory needed", who, smem);
         return RADNET_E_UNSUPPORTED;
     }
-    RADNET_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        int dev = 0;
+        RADNET_CUDA(cudaGetDevice(&dev));
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(cluster_kernel), dev, smem)) return rc;
+    }
     // segment counters start at zero (the packing CTA also resets its own)
     RADNET_CUDA(cudaMemsetAsync(p.ws, 0, p.ws_counters, st));
     cluster_kernel<<<dim3(n_cls, S), kDetThreads, smem, st>>>(p);

@@ -286,10 +286,9 @@ __global__ void __launch_bounds__(256) roi_pool_direct_kernel(RoiPoolParams p) {
 
 template <int LANES>
 static int launch_slice(const RoiPoolParams &p, int B, size_t smem, cudaStream_t st) {
-    static SmemAttrCache smem_cache;        // one per LANES instantiation
     int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
-    if (int rc = smem_cache.ensure(reinterpret_cast<const void *>(roi_pool_slice_kernel<LANES>), dev, smem)) return rc;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(roi_pool_slice_kernel<LANES>), dev, smem)) return rc;
     roi_pool_slice_kernel<LANES><<<B * p.n_slices, kPoolThreads, smem, st>>>(p);
     return check_launch("roi_pool_slice_kernel");
 }

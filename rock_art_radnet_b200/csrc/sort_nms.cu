@@ -1249,22 +1249,12 @@ static int forced_cluster_size() {
     return (q == 2 || q == 4 || q == 8 || q == 16) ? (int)q : 0;
 }
 
-// per-kernel, per-device record of the function attributes already set (dynamic shared memory, non-portable
-// cluster size), so that a launch does not call cudaFuncSetAttribute again
+// function attributes (dynamic shared memory, non-portable cluster size) are set once per kernel and device
 template <typename K>
 static int ensure_attrs(K kernel, size_t smem_bytes, bool nonportable) {
-    static SmemAttrCache smem_cache;
-    static std::atomic<unsigned long long> np_done{0};
     const int dev = current_device();
-    int rc = smem_cache.ensure(reinterpret_cast<const void *>(kernel), dev, smem_bytes);
-    if (rc) return rc;
-    if (nonportable) {
-        const unsigned long long bit = 1ull << (dev & 63);
-        if (!(np_done.load(std::memory_order_relaxed) & bit)) {
-            RADNET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            np_done.fetch_or(bit, std::memory_order_relaxed);
-        }
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), dev, smem_bytes)) return rc;
+    if (nonportable) return ensure_nonportable_clusters(reinterpret_cast<const void *>(kernel), dev);
     return RADNET_OK;
 }
 
@@ -1315,8 +1305,9 @@ static int max_active_clusters(const NmsPlan &pl, int cs) {
         ? (const void *)sort_nms_kernel<BoxI32, uint32_t, uint32_t, false, true, true, true>
         : (const void *)sort_nms_kernel<BoxI32, uint32_t, uint16_t, true, true, true>;
     int n = 0;
-    bool ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes) == cudaSuccess;
-    if (ok && cs > 8) ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    // through the shared table, so that the granted shared-memory size of a kernel never shrinks
+    bool ok = ensure_dynamic_smem(kernel, current_device(), pl.smem_bytes) == RADNET_OK;
+    if (ok && cs > 8) ok = ensure_nonportable_clusters(kernel, current_device()) == RADNET_OK;
     if (ok) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)cs);

@@ -35,7 +35,6 @@ constexpr int kTgtThreads = 256;
 constexpr int kFillWarps = 2;
 constexpr int kFillThreads = 32 * kFillWarps;
 constexpr int kCompThreads = kTgtThreads - kFillThreads;
-constexpr int kCompWarps = kCompThreads / 32;
 
 struct RpnTargetParams {
     const double *gt;          // [B][Gmax][4] x1,x2,y1,y2
@@ -169,43 +168,62 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     float *s_area32 = reinterpret_cast<float *>(s_best + p.Gmax);
     unsigned *s_floor = reinterpret_cast<unsigned *>(s_area32 + p.Gmax);                // [G] lower bound of the best IoU (f32 bits)
     int *s_hits = reinterpret_cast<int *>(s_floor + p.Gmax);
-    uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_hits + p.Gmax);                     // bit0: bg/degenerate, bit1: no filter
+    int *s_cstart = s_hits + p.Gmax;                                                    // [G+1] first 32-cell chunk of figure g
+    uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_cstart + p.Gmax + 1);               // bit0: bg/degenerate, bit1: no filter
 
     const int b = blockIdx.y, a = blockIdx.x;
     const int HW = p.H * p.W;
-    const int G = min(max(p.gt_count[b], 0), p.Gmax);
     const double aw = p.anchors.wh[a][0], ah = p.anchors.wh[a][1];
-    const double img_w = p.img_wh[2 * b], img_h = p.img_wh[2 * b + 1];
     double *cls_b = p.y_cls + (size_t)b * 2 * p.A * HW;
     double *regr_b = p.y_regr + (size_t)b * 8 * p.A * HW;
     const int lane = threadIdx.x & 31;
 
     // per-cell state of this anchor plane
-    double *s_lb = reinterpret_cast<double *>(smem + p.sm_off_cells);                    // [HW] (replay path; winner list)
-    double2 *s_ax = reinterpret_cast<double2 *>(s_lb + ((HW + 1) & ~1));                 // [W] anchor x1,x2 of column ix
+    unsigned long long *s_cell = reinterpret_cast<unsigned long long *>(smem + p.sm_off_cells);  // [HW] best IoU bits
+    double2 *s_ax = reinterpret_cast<double2 *>(s_cell + ((HW + 1) & ~1));               // [W] anchor x1,x2 of column ix
     double2 *s_ay = s_ax + p.W;                                                          // [H] anchor y1,y2 of row jy
     float4 *s_axf = reinterpret_cast<float4 *>(s_ay + p.H);                              // [W] x1,x2,width (f32), in-image flag
     float4 *s_ayf = s_axf + p.W;                                                         // [H]
     TargetHit *s_hit = reinterpret_cast<TargetHit *>(s_ayf + p.H);                       // [hit_cap]
     const int hit_cap = p.hit_cap;
-    int *s_nhit = reinterpret_cast<int *>(s_hit + hit_cap);                              // {hits, winners, patch base, last flag}
+    int *s_nhit = reinterpret_cast<int *>(s_hit + hit_cap);                              // {hits, next chunk, -, last flag}
     int *s_use = s_nhit + 4;                                                             // ix_lo, ix_hi, jy_lo, jy_hi in-image
-    short *s_lg = reinterpret_cast<short *>(s_nhit + 8);                                 // [HW]
-    uint8_t *s_inx = reinterpret_cast<uint8_t *>(s_lg + ((HW + 7) & ~7));                // [A][W] column of shape c inside the image
+    int *s_lg = s_nhit + 8;                                                              // [HW] winning figure of a cell
+    uint8_t *s_inx = reinterpret_cast<uint8_t *>(s_lg + ((HW + 3) & ~3));                // [A][W] column of shape c inside the image
     uint8_t *s_iny = s_inx + p.A * p.W;                                                  // [A][H]
     TGT_STAMP(0);
+
+    // ---- every input of the panel is fetched BEFORE the fill team starts: a load issued behind the store
+    //      stream of the same SM waits for the whole backlog ---------------------------------------------
+    const int G = min(max(p.gt_count[b], 0), p.Gmax);
+    const double img_w = p.img_wh[2 * b], img_h = p.img_wh[2 * b + 1];
+    const bool coords_small = img_w <= 8192.0 && img_h <= 8192.0 && aw <= 8192.0 && ah <= 8192.0;
+    for (int i = threadIdx.x; i < p.Gmax; i += kTgtThreads) {
+        const double2 *q = reinterpret_cast<const double2 *>(p.gt + ((size_t)b * p.Gmax + i) * 4);
+        const double2 qx = q[0], qy = q[1];
+        const uint8_t isbg = p.gt_is_bg[(size_t)b * p.Gmax + i];
+        const double x1 = qx.x, x2 = qx.y, y1 = qy.x, y2 = qy.y;
+        s_gt[4 * i + 0] = x1; s_gt[4 * i + 1] = x2; s_gt[4 * i + 2] = y1; s_gt[4 * i + 3] = y2;
+        s_gt32[i] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
+        s_area32[i] = (float)((x2 - x1) * (y2 - y1));
+        s_best[i] = 0ull;
+        s_hits[i] = 0;
+        s_floor[i] = 0u;
+        // 'bg' figures never produce labels (utils.py:690); degenerate ones have IoU 0 (utils.py:103)
+        uint8_t f = ((isbg != 0) || (x1 >= x2) || (y1 >= y2)) ? 1 : 0;
+        // the float32 estimate is only trusted for pixel-scale coordinates
+        if (!coords_small || !(fabs(x1) <= 8192.0 && fabs(x2) <= 8192.0 && fabs(y1) <= 8192.0 && fabs(y2) <= 8192.0)) f |= 2;
+        s_skip[i] = f;
+    }
+    if (threadIdx.x == 0) {
+        s_nhit[0] = 0; s_nhit[1] = 0;
+        s_use[0] = p.W; s_use[1] = -1; s_use[2] = p.H; s_use[3] = -1;
+    }
+    __syncthreads();
 
     if (threadIdx.x >= kCompThreads) {
         // ================================================================= fill team
         const int tf = threadIdx.x - kCompThreads;
-        // regression tensor: zero wherever no anchor is positive
-        {
-            double2 *dst = reinterpret_cast<double2 *>(regr_b + (size_t)a * 8 * HW);
-            const double2 z = make_double2(0.0, 0.0);
-            const int n2 = 4 * HW;
-#pragma unroll 4
-            for (int i = tf; i < n2; i += kFillThreads) dst[i] = z;
-        }
         // label tensor: [valid | overlap]; valid = anchor inside the image on both axes (utils.py:629, 638), and
         // labels are only ever written inside the GT loop: no GT, no labels (utils.py:722-738)
         for (int i = tf; i < p.A * (p.W + p.H); i += kFillThreads) {
@@ -217,6 +235,14 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
             const double v1 = __dsub_rn(ctr, __dmul_rn(side, 0.5)), v2 = __dadd_rn(ctr, __dmul_rn(side, 0.5));
             const bool ok = !(v1 < 0.0 || v2 > lim_px) && v1 < v2 && G > 0;
             (isx ? s_inx + c * p.W : s_iny + c * p.H)[k] = ok ? 1 : 0;
+        }
+        // regression tensor: zero wherever no anchor is positive
+        {
+            double2 *dst = reinterpret_cast<double2 *>(regr_b + (size_t)a * 8 * HW);
+            const double2 z = make_double2(0.0, 0.0);
+            const int n2 = 4 * HW;
+#pragma unroll 8
+            for (int i = tf; i < n2; i += kFillThreads) dst[i] = z;
         }
         bar_team(2, kFillThreads);
         {
@@ -242,29 +268,12 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
         }
         TGT_STAMP(9);
     } else {
-        // ============================================================== compute team
-        const bool coords_small = img_w <= 8192.0 && img_h <= 8192.0 && aw <= 8192.0 && ah <= 8192.0;
-        for (int i = threadIdx.x; i < G; i += kCompThreads) {
-            const double *q = p.gt + ((size_t)b * p.Gmax + i) * 4;
-            const double x1 = q[0], x2 = q[1], y1 = q[2], y2 = q[3];
-            s_gt[4 * i + 0] = x1; s_gt[4 * i + 1] = x2; s_gt[4 * i + 2] = y1; s_gt[4 * i + 3] = y2;
-            s_gt32[i] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
-            s_area32[i] = (float)((x2 - x1) * (y2 - y1));
-            s_best[i] = 0ull;
-            s_hits[i] = 0;
-            s_floor[i] = 0u;
-            // 'bg' figures never produce labels (utils.py:690); degenerate ones have IoU 0 (utils.py:103)
-            uint8_t f = ((p.gt_is_bg[(size_t)b * p.Gmax + i] != 0) || (x1 >= x2) || (y1 >= y2)) ? 1 : 0;
-            // the float32 estimate is only trusted for pixel-scale coordinates
-            if (!coords_small || !(fabs(x1) <= 8192.0 && fabs(x2) <= 8192.0 && fabs(y1) <= 8192.0 && fabs(y2) <= 8192.0)) f |= 2;
-            s_skip[i] = f;
+        // ============================================================== compute team (shared memory only
+        // until its results go to the workspace)
+        for (int cell = threadIdx.x; cell < HW; cell += kCompThreads) {
+            s_lg[cell] = 0x7fffffff;
+            s_cell[cell] = 0ull;
         }
-        if (threadIdx.x == 0) {
-            s_nhit[0] = 0; s_nhit[1] = 0;
-            s_use[0] = p.W; s_use[1] = -1; s_use[2] = p.H; s_use[3] = -1;
-        }
-        for (int cell = threadIdx.x; cell < HW; cell += kCompThreads) s_lg[cell] = -1;
-        bar_team(1, kCompThreads);
         // A LOWER bound of every figure's best float32 IoU, from the exact IoU with the A anchors of
         // the cell under the figure's centre (all anchor shapes, not only this CTA's).  Pairs whose
         // float32 estimate is below it by more than the margin cannot be (or tie with) the best anchor.
@@ -330,93 +339,121 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
                 }
             }
             s_range[g] = r;
+            const int n = (r.x > r.y || r.z > r.w) ? 0 : (r.y - r.x + 1) * (r.w - r.z + 1);
+            s_cstart[g + 1] = (n + 31) >> 5;                                     // chunks of this figure, prefix below
+        }
+        bar_team(1, kCompThreads);
+        if (threadIdx.x < 32) {            // inclusive prefix over the figures' chunk counts, 32 at a time
+            int carry = 0;
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                const int v = g < G ? s_cstart[g + 1] : 0;
+                int inc = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += n;
+                }
+                if (g < G) s_cstart[g + 1] = carry + inc;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_cstart[0] = 0;
         }
         bar_team(1, kCompThreads);
         TGT_STAMP(2);
 
-        // Phase 1 - one WARP per figure.  The warp enumerates the cells of the figure's window 32 at a
-        // time; every lane keeps its own running best key and appends its own hits, so the loop body has
-        // no warp-wide operation and iterations overlap.  Cells whose IoU exceeds rpn_max_overlap go to a
-        // hit list; which figure wins a cell is settled in phase 2, so the figure order of the reference
-        // ("first figure wins ties", utils.py:710-713) does not serialise the warps.
-        const int w = threadIdx.x >> 5;
+        // Phase 1 - the windows of all figures are cut into chunks of 32 cells and the warps of the team pull
+        // chunks from a shared counter (the windows differ a lot in size).  Cells whose IoU exceeds
+        // rpn_max_overlap go to a hit list; which figure wins a cell is settled in phase 2, so the figure
+        // order of the reference ("first figure wins ties", utils.py:710-713) does not serialise the warps.
+        const int n_chunks = s_cstart[G];
 #pragma unroll 1
-        for (int g = w; g < G; g += kCompWarps) {
+        while (true) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&s_nhit[1], 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= n_chunks) break;
+            int g = 0;                                                            // last g with s_cstart[g] <= c
+            for (int hi = G - 1; g < hi;) {
+                const int mid = (g + hi + 1) >> 1;
+                if (s_cstart[mid] <= c) g = mid; else hi = mid - 1;
+            }
             const int4 rg = s_range[g];
-            if (rg.x > rg.y || rg.z > rg.w) continue;                             // warp-uniform (also bg / degenerate)
             const int ww = rg.y - rg.x + 1, n = ww * (rg.w - rg.z + 1);
+            const int t = (c - s_cstart[g]) * 32 + lane;
+            const bool act = t < n;
+            const int dy = act ? t / ww : 0;
+            const int ix = rg.x + (act ? t - dy * ww : 0), jy = rg.z + dy;
             const uint8_t gflag = s_skip[g];
             const double gx1 = s_gt[4 * g + 0], gx2 = s_gt[4 * g + 1], gy1 = s_gt[4 * g + 2], gy2 = s_gt[4 * g + 3];
             const float4 gf = s_gt32[g];
-            const float ga32 = s_area32[g];
             const float lim = fminf(__uint_as_float(s_floor[g]), thr32);
-            unsigned long long best = 0ull;
-            int nhit = 0;
-#pragma unroll 2
-            for (int t = lane; t < n; t += 32) {
-                const int dy = t / ww;
-                const int ix = rg.x + t - dy * ww, jy = rg.z + dy;
-                const float4 XF = s_axf[ix], YF = s_ayf[jy];
-                // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
-                if (XF.w == 0.f || YF.w == 0.f) continue;
-                const double2 X = s_ax[ix], Y = s_ay[jy];
-                // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
-                if (!(gx2 > X.x && X.y > gx1 && gy2 > Y.x && Y.y > gy1)) continue;
-                // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
+            const double2 X = s_ax[ix], Y = s_ay[jy];
+            const float4 XF = s_axf[ix], YF = s_ayf[jy];
+            // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
+            const bool usable = act && XF.w != 0.f && YF.w != 0.f;
+            // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
+            const bool isect = usable && gx2 > X.x && X.y > gx1 && gy2 > Y.x && Y.y > gy1;
+            // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
+            bool need = false;
+            if (isect) {
                 const float wi = fminf(gf.z, XF.y) - fmaxf(gf.x, XF.x);
                 const float hi = fminf(gf.w, YF.y) - fmaxf(gf.y, YF.x);
                 const float it = fmaxf(wi, 0.f) * fmaxf(hi, 0.f);
-                const float q = __fdividef(it, ga32 + XF.z * YF.z - it);
-                // could be the best anchor, or exceed rpn_max_overlap; estimate not trusted -> always exact
-                if (!((q + kIouMargin >= lim) || (gflag & 2))) continue;
+                const float q = __fdividef(it, s_area32[g] + XF.z * YF.z - it);
+                need = (q + kIouMargin >= lim) ||           // could be the best anchor, or exceed rpn_max_overlap
+                       (gflag & 2);                         // estimate not trusted: always exact
+            }
+            if (!__any_sync(0xffffffffu, need)) continue;                         // warp-uniform
+            unsigned bits = 0;
+            bool hit = false;
+            if (need) {
                 const double iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
                 const float iou32 = (float)iou;                                   // float32 accumulator (utils.py:603)
-                if (iou32 > 0.f) {
-                    // best anchor of this figure: max float32 IoU, then first in loop order size->ratio->ix->jy
-                    const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);
-                    const unsigned long long key =
-                        ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order);
-                    best = key > best ? key : best;
-                }
-                if (iou > p.max_overlap) {                                        // utils.py:704
+                if (iou32 > 0.f) bits = __float_as_uint(iou32);
+                hit = iou > p.max_overlap;                                        // utils.py:704
+                if (hit) {
                     const int pos = atomicAdd(&s_nhit[0], 1);
                     if (pos < hit_cap) s_hit[pos] = TargetHit{iou, jy * p.W + ix, g};
-                    ++nhit;
                 }
             }
-            // warp max of the 64-bit key (high word first), warp sum of the hits
-            const unsigned hi_max = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
-            const unsigned lo_max =
-                __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32) == hi_max ? (unsigned)best : 0u);
-            nhit = __reduce_add_sync(0xffffffffu, nhit);
-            if (lane == 0) {              // this warp is the only writer of figure g in this CTA
-                s_best[g] = hi_max ? (((unsigned long long)hi_max << 32) | lo_max) : 0ull;
-                s_hits[g] = nhit;
+            // best anchor of this figure: max float32 IoU, then first in loop order size->ratio->ix->jy
+            const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);
+            const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+            const unsigned hm = __ballot_sync(0xffffffffu, hit);
+            if (wmax) {
+                const unsigned omin = __reduce_min_sync(0xffffffffu, bits == wmax ? order : 0xFFFFFFFFu);
+                if (lane == 0) atomicMax(&s_best[g], ((unsigned long long)wmax << 32) | (0xFFFFFFFFu - omin));
             }
+            if (hm && lane == 0) atomicAdd(&s_hits[g], __popc(hm));
         }
         bar_team(1, kCompThreads);
         TGT_STAMP(3);
 
         // Phase 2 - settle every hit cell: highest IoU wins, equal IoU -> the earlier figure (strict '>'
-        // in figure order, utils.py:710-713).  Winners go to the panel's patch list.
+        // in figure order, utils.py:710-713).  Winners go to the panel's patch list in the workspace.
         const int n_hit = s_nhit[0];
-        uint2 *s_win = reinterpret_cast<uint2 *>(s_lb);                           // [<= HW] {a*HW + cell, g}
+        uint2 *patch_b = p.patch + (size_t)b * p.A * HW;
         if (n_hit <= hit_cap) {
+            for (int e = threadIdx.x; e < n_hit; e += kCompThreads)               // positive doubles order like their bits
+                atomicMax(&s_cell[s_hit[e].cell], (unsigned long long)__double_as_longlong(s_hit[e].iou));
+            bar_team(1, kCompThreads);
             for (int e = threadIdx.x; e < n_hit; e += kCompThreads) {
                 const TargetHit h = s_hit[e];
-                bool win = true;
-                for (int j = 0; j < n_hit; ++j) {
-                    const TargetHit o = s_hit[j];
-                    // identical (cell, figure) entries cannot occur: a window visits a cell once
-                    if (o.cell == h.cell && (o.iou > h.iou || (o.iou == h.iou && o.g < h.g))) win = false;
+                if ((unsigned long long)__double_as_longlong(h.iou) == s_cell[h.cell]) atomicMin(&s_lg[h.cell], h.g);
+            }
+            bar_team(1, kCompThreads);
+            for (int e = threadIdx.x; e < n_hit; e += kCompThreads) {
+                const TargetHit h = s_hit[e];
+                if ((unsigned long long)__double_as_longlong(h.iou) == s_cell[h.cell] && s_lg[h.cell] == h.g) {
+                    const int pos = atomicAdd(&p.panel_ctr[2 * b + 1], 1);
+                    patch_b[pos] = make_uint2((unsigned)(a * HW + h.cell), (unsigned)h.g);
                 }
-                if (win) s_win[atomicAdd(&s_nhit[1], 1)] = make_uint2((unsigned)(a * HW + h.cell), (unsigned)h.g);
             }
         } else {
             // more positives than the list holds (never seen in practice): replay figure by figure with
             // in-place per-cell state, the whole team on one figure at a time
-            for (int cell = threadIdx.x; cell < HW; cell += kCompThreads) s_lb[cell] = 0.0;
-            bar_team(1, kCompThreads);
+            double *s_lb = reinterpret_cast<double *>(s_cell);
 #pragma unroll 1
             for (int g = 0; g < G; ++g) {
                 const int4 rg = s_range[g];
@@ -429,26 +466,17 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
                     const double2 X = s_ax[ix], Y = s_ay[jy];
                     const double iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
                     const int cell = jy * p.W + ix;
-                    if (iou > p.max_overlap && iou > s_lb[cell]) { s_lb[cell] = iou; s_lg[cell] = (short)g; }
+                    if (iou > p.max_overlap && iou > s_lb[cell]) { s_lb[cell] = iou; s_lg[cell] = g; }
                 }
                 bar_team(1, kCompThreads);
             }
-            // the per-cell winners go straight to the global list (s_lb is still in use as state)
             for (int cell = threadIdx.x; cell < HW; cell += kCompThreads) {
                 const int lg = s_lg[cell];
-                if (lg >= 0) {
+                if (lg != 0x7fffffff) {
                     const int pos = atomicAdd(&p.panel_ctr[2 * b + 1], 1);
-                    p.patch[(size_t)b * p.A * HW + pos] = make_uint2((unsigned)(a * HW + cell), (unsigned)lg);
+                    patch_b[pos] = make_uint2((unsigned)(a * HW + cell), (unsigned)lg);
                 }
             }
-        }
-        bar_team(1, kCompThreads);
-        const int n_win = s_nhit[1];
-        if (n_win > 0) {
-            if (threadIdx.x == 0) s_nhit[2] = atomicAdd(&p.panel_ctr[2 * b + 1], n_win);
-            bar_team(1, kCompThreads);
-            uint2 *dst = p.patch + (size_t)b * p.A * HW + s_nhit[2];
-            for (int e = threadIdx.x; e < n_win; e += kCompThreads) dst[e] = s_win[e];
         }
         for (int g = threadIdx.x; g < G; g += kCompThreads) {
             if (s_best[g]) atomicMax(&p.best_key[(size_t)b * p.Gmax + g], s_best[g]);
@@ -469,45 +497,58 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
     __threadfence();
     TGT_STAMP(5);
 
-    // regular positives of all anchor shapes (utils.py:728-738)
+    // all loads of the finish are issued together: patch count, per-figure accumulators, then the patches
     const int n_patch = __ldcg(&p.panel_ctr[2 * b + 1]);
+    unsigned long long my_key = 0ull;
+    int my_hits = 0;
+    if ((int)threadIdx.x < G) {           // figures beyond kTgtThreads are handled in the loop below
+        my_key = __ldcg(&p.best_key[(size_t)b * p.Gmax + threadIdx.x]);
+        my_hits = __ldcg(&p.hits_acc[(size_t)b * p.Gmax + threadIdx.x]);
+    }
+    // regular positives of all anchor shapes (utils.py:728-738)
     for (int e = threadIdx.x; e < n_patch; e += kTgtThreads) {
         const uint2 u = __ldcg(p.patch + (size_t)b * p.A * HW + e);
         const int a2 = (int)(u.x / (unsigned)HW), cell = (int)(u.x - (unsigned)a2 * HW);
-        write_positive(p, cls_b, regr_b, a2, cell, p.gt + ((size_t)b * p.Gmax + u.y) * 4, false);
+        write_positive(p, cls_b, regr_b, a2, cell, s_gt + 4 * u.y, false);
     }
     // forced positives + best_anchor table (utils.py:741-766).  The reference applies them in GT order,
     // so when several GT share the same best anchor the LAST one wins: a thread only writes if no later
     // forced GT targets its anchor.
-    unsigned *s_order = reinterpret_cast<unsigned *>(smem);                       // [Gmax] loop-order id or ~0
-    __syncthreads();                                                              // patches before forced writes
+    unsigned *s_order = reinterpret_cast<unsigned *>(s_range);                    // [Gmax] loop-order id or ~0
     for (int g = threadIdx.x; g < p.Gmax; g += kTgtThreads) {
         int32_t *ba = p.best_anchor + ((size_t)b * p.Gmax + g) * 4;
-        const unsigned long long key = (g < G) ? __ldcg(&p.best_key[(size_t)b * p.Gmax + g]) : 0ull;
-        const int nh = __ldcg(&p.hits_acc[(size_t)b * p.Gmax + g]);
+        unsigned long long key = my_key;
+        int nh = my_hits;
+        if (g >= kTgtThreads && g < G) {
+            key = __ldcg(&p.best_key[(size_t)b * p.Gmax + g]);
+            nh = __ldcg(&p.hits_acc[(size_t)b * p.Gmax + g]);
+        }
+        if (g >= G) { key = 0ull; nh = 0; }
         unsigned order = 0xFFFFFFFFu;
-        if (!key) {
-            ba[0] = ba[1] = ba[2] = ba[3] = -1;
-        } else {
+        int4 out = make_int4(-1, -1, -1, -1);
+        if (key) {
             const unsigned o = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
             const int jy = (int)(o % (unsigned)p.H);
             const unsigned rest = o / (unsigned)p.H;
             const int ix = (int)(rest % (unsigned)p.W);
             const int a2 = (int)(rest / (unsigned)p.W);
-            ba[0] = jy; ba[1] = ix; ba[2] = a2 % p.n_ratios; ba[3] = a2 / p.n_ratios;   // utils.py:697
+            out = make_int4(jy, ix, a2 % p.n_ratios, a2 / p.n_ratios);            // utils.py:697
             if (nh == 0) order = o;
         }
+        *reinterpret_cast<int4 *>(ba) = out;
         p.n_hits[(size_t)b * p.Gmax + g] = nh;
         s_order[g] = order;
         // leave the workspace state as the next launch expects it
-        p.best_key[(size_t)b * p.Gmax + g] = 0ull;
-        p.hits_acc[(size_t)b * p.Gmax + g] = 0;
+        if (g < G) {
+            if (key) p.best_key[(size_t)b * p.Gmax + g] = 0ull;
+            if (nh) p.hits_acc[(size_t)b * p.Gmax + g] = 0;
+        }
     }
     if (threadIdx.x == 0) {
         p.panel_ctr[2 * b] = 0;
         p.panel_ctr[2 * b + 1] = 0;
     }
-    __syncthreads();
+    __syncthreads();                                                              // patches before forced writes
     for (int g = threadIdx.x; g < G; g += kTgtThreads) {
         const unsigned o = s_order[g];
         if (o == 0xFFFFFFFFu) continue;
@@ -518,7 +559,7 @@ __global__ void __launch_bounds__(kTgtThreads, 4) rpn_targets_kernel(RpnTargetPa
         const unsigned rest = o / (unsigned)p.H;
         const int ix = (int)(rest % (unsigned)p.W);
         const int a2 = (int)(rest / (unsigned)p.W);
-        write_positive(p, cls_b, regr_b, a2, jy * p.W + ix, p.gt + ((size_t)b * p.Gmax + g) * 4, true);
+        write_positive(p, cls_b, regr_b, a2, jy * p.W + ix, s_gt + 4 * g, true);
     }
     TGT_STAMP(6);
 }
@@ -706,14 +747,15 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     RADNET_CHECK_ARG((long long)A * H * W < 0x7fffffffLL, "rpn_targets: anchor count overflows the loop-order key");
     RADNET_CHECK_ARG(layout == RADNET_TARGETS_CHANNEL_FIRST || layout == RADNET_TARGETS_NHWC, "rpn_targets: bad layout %d",
                      layout);
-    RADNET_CHECK_ARG(((uintptr_t)y_rpn_cls & 15) == 0 && ((uintptr_t)y_rpn_regr & 15) == 0,
-                     "rpn_targets: output tensors must be 16-byte aligned");
+    RADNET_CHECK_ARG(((uintptr_t)y_rpn_cls & 15) == 0 && ((uintptr_t)y_rpn_regr & 15) == 0 &&
+                         ((uintptr_t)gt & 15) == 0 && ((uintptr_t)best_anchor & 15) == 0,
+                     "rpn_targets: gt, best_anchor and the output tensors must be 16-byte aligned");
     const TgtWsLayout wl = tgt_ws_layout(B, Gmax, H, W, A);
     if (ws_bytes < wl.total) {
         set_error("rpn_targets: workspace %zu < %zu", ws_bytes, wl.total);
         return RADNET_E_WORKSPACE;
     }
-    size_t gt_bytes = align_up((size_t)Gmax * (4 * 8 + 16 + 16 + 8 + 4 + 4 + 4 + 1) + 16, 16);
+    size_t gt_bytes = align_up((size_t)Gmax * (4 * 8 + 16 + 16 + 8 + 4 + 4 + 4 + 4 + 1) + 32, 16);
     int hit_cap = H * W < 4096 ? H * W : 4096;
     {   // tests shrink the list to exercise the replay path
         const long long v = get_option(kOptTargetsHitCap);
@@ -721,7 +763,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     }
     const size_t HW = (size_t)H * W;
     size_t smem = gt_bytes + ((HW + 1) & ~(size_t)1) * sizeof(double) + (size_t)(H + W) * 32 +
-                  (size_t)hit_cap * sizeof(TargetHit) + 32 + ((HW + 7) & ~(size_t)7) * sizeof(short) +
+                  (size_t)hit_cap * sizeof(TargetHit) + 32 + ((HW + 3) & ~(size_t)3) * sizeof(int) +
                   (size_t)A * (H + W) + 16;
     int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
@@ -754,9 +796,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     p.stamps = g_tgt_stamps;
 #endif
     cudaStream_t st = (cudaStream_t)stream;
-    static SmemAttrCache smem_cache;
-    int rc = smem_cache.ensure(reinterpret_cast<const void *>(rpn_targets_kernel), dev, smem);
-    if (rc) return rc;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(rpn_targets_kernel), dev, smem)) return rc;
     dim3 grid(A, B);
     rpn_targets_kernel<<<grid, kTgtThreads, smem, st>>>(p);
     return check_launch("rpn_targets_kernel");

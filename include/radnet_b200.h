@@ -66,7 +66,9 @@ int radnet_device_info(int *h_out3);
  * same results; the options choose between equivalent code paths (tests use them to exercise all of
  * them):  nms_cluster (-1 auto, 0 one CTA per panel), nms_cluster_size (0 auto | 2 | 4 | 8 | 16),
  * nms_cluster_ranks, nms_sel_target, nms_lookahead (0 = default), roipool_force_direct (0 | 1),
- * roipool_form (0 auto | 1 whole-map slices | 2 row bands), targets_hit_cap (0 = default). */
+ * roipool_form (0 auto | 1 whole-map slices | 2 row bands), targets_hit_cap (0 = default),
+ * targets_compute_ctas (0 = 43 % of the SMs), targets_two_launches (0 | 1: fill and panels as two
+ * launches, no co-residency assumed), sampler_force_exact (0 | 1). */
 int radnet_set_option(const char *h_name, long long value);
 int radnet_get_option(const char *h_name, long long *h_value);
 
@@ -170,10 +172,11 @@ int radnet_roi_pool(const float *feat, int B, int H, int W, int C, const void *d
  *   regr_scale             factor applied to the regr half (1.0, or C.std_scaling: utils.py:475)
  *   best_anchor [B][Gmax][4] int32 {jy, ix, ratio_idx, size_idx} or -1 (utils.py:697)
  *   n_hits      [B][Gmax]    int32 positives per GT before forcing    (utils.py:707)
- *   ws          scratch of radnet_rpn_targets_workspace_bytes(B,Gmax,H,W,A) bytes.  Its first part is
- *               per-panel state that every successful launch leaves zeroed: call
- *               radnet_rpn_targets_workspace_init once after allocating it (and after a failed launch).
- * Both output tensors must be 16-byte aligned. */
+ *               A panel whose fill never completed (co-residency lost for 4 s) has n_hits = -1.
+ *   ws          radnet_rpn_targets_workspace_bytes(B,Gmax,H,W,A) bytes of counters that every successful
+ *               launch leaves zeroed: call radnet_rpn_targets_workspace_init once after allocating it
+ *               (and after a failed launch).  One workspace serves one launch at a time.
+ * gt, best_anchor and both output tensors must be 16-byte aligned. */
 enum { RADNET_TARGETS_CHANNEL_FIRST = 0, RADNET_TARGETS_NHWC = 1 };
 size_t radnet_rpn_targets_workspace_bytes(int B, int Gmax, int H, int W, int A);
 int radnet_rpn_targets_workspace_init(void *ws, size_t ws_bytes, int B, int Gmax, void *stream);
@@ -211,6 +214,40 @@ int radnet_roi_targets_batch(const void *det, int det_max_boxes, const int32_t *
                              const double *h_regr_std4, int32_t *x_roi, int32_t *y_class,
                              double *y_regr, double *ious, int32_t *best_gt, int32_t *count,
                              void *stream);
+
+/* ------------------------------------------------ f3: training-side sampling
+ * The reference samples with NumPy's legacy global generator (np.random.seed, train.py:134-135).  A
+ * generator state here is uint32[625] = key[624] + pos, the layout of np.random.get_state()[1:3]; every
+ * entry point reads the state of panel b at rng_states + 625*b, consumes exactly the words NumPy would
+ * and writes the advanced state back, so a host can pass np.random's own state in and out.
+ *
+ * radnet_mt19937_seed: np.random.seed(seeds[b]) for 32-bit integer seeds (init_genrand). */
+int radnet_mt19937_seed(const uint32_t *seeds, int B, uint32_t *rng_states, void *stream);
+
+/* The 256-region balancing at the end of calc_region_props (reference faster_rcnn/utils.py:777-813), in
+ * place on the label tensor written by radnet_rpn_targets (same layout argument): if more than
+ * max_regions/2 anchors are positive, np.random.choice(n_pos, n_pos - max_regions/2, replace=False, p)
+ * of them are switched off (valid = 0); then, if positives + negatives exceed max_regions,
+ * np.random.choice(n_neg, n_neg - n_pos, replace=False, p) negatives.  p is the reference's per-channel
+ * weight, looked up in a table keyed by the channels of the NEGATIVES in both branches (utils.py:789,804).
+ *   out [B][8] int32 {n_pos returned by calc_region_props, positives found, negatives found,
+ *                     status (0 ok, 1 = the reference raises KeyError: a positive's channel has no
+ *                     negative; nothing is drawn or changed), rounds redone with the serial cumsum,
+ *                     draws, 0, 0}
+ *   ws  radnet_rpn_subsample_workspace_bytes(B,H,W,A) bytes. */
+size_t radnet_rpn_subsample_workspace_bytes(int B, int H, int W, int A);
+int radnet_rpn_subsample(double *y_rpn_cls, int B, int H, int W, int A, int layout, int max_regions,
+                         uint32_t *rng_states, int32_t *out, void *ws, size_t ws_bytes, void *stream);
+
+/* get_selected_samples (reference train.py:93-129) for B panels: from the one-hot rows of calc_iou
+ * (y_class [B][R][n_cls] int32, count [B] rows used or NULL = R; 'bg' is the last class) pick n_rois rows,
+ * positives first: all positives if fewer than n_rois/2, else np.random.choice(pos, n_rois/2,
+ * replace=False); then np.random.choice(neg, rest, replace=False) (replace=True when there are too few);
+ * without any negative the reference's second branch (train.py:122-127).
+ *   sel [B][n_rois] int32 selected row indices;  out [B][4] int32 {rows selected, n_pos, n_neg, status
+ *   (0 ok, 2 = the reference raises ValueError: nothing to sample from)}.  R <= 2048. */
+int radnet_select_samples(const int32_t *y_class, const int32_t *count, int B, int R, int n_cls,
+                          int n_rois, uint32_t *rng_states, int32_t *sel, int32_t *out, void *stream);
 
 /* utils.iou(a, b) (reference faster_rcnn/utils.py:77-109) for n box pairs: a, b [n][4] float64
  * (x1,y1,x2,y2) -> out [n] float64; 0.0 for degenerate boxes, else inter/(union+1e-6). */

@@ -27,8 +27,9 @@ int cuda_fail(cudaError_t e, const char *what) {
 // ---- options ---------------------------------------------------------------------------------------
 static const char *const kOptionNames[kOptCount] = {
     "nms_cluster", "nms_cluster_size", "nms_cluster_ranks", "nms_sel_target",
-    "nms_lookahead", "roipool_force_direct", "targets_hit_cap", "roipool_form"};
-static const long long kOptionDefaults[kOptCount] = {-1, 0, 0, 0, 0, 0, 0, 0};
+    "nms_lookahead", "roipool_force_direct", "targets_hit_cap", "roipool_form", "sampler_force_exact",
+    "targets_compute_ctas", "targets_two_launches"};
+static const long long kOptionDefaults[kOptCount] = {-1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 struct OptionTable {
     std::atomic<long long> v[kOptCount];

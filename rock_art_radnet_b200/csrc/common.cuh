@@ -53,7 +53,10 @@ enum Option {
     kOptNmsLookahead,        // nms_lookahead: 0 auto
     kOptRoipoolForceDirect,  // roipool_force_direct: 0/1
     kOptTargetsHitCap,       // targets_hit_cap: 0 auto
-    kOptRoipoolForm,         // roipool_form: 0 auto, 1 whole-map slices, 2 cluster halves
+    kOptRoipoolForm,         // roipool_form: 0 auto, 1 whole-map slices, 2 row bands
+    kOptSamplerForceExact,   // sampler_force_exact: 0/1 (always the serial cumsum chain)
+    kOptTargetsComputeCtas,  // targets_compute_ctas: 0 auto (43 % of the SMs)
+    kOptTargetsTwoLaunches,  // targets_two_launches: 0/1 (fill and panels as two launches)
     kOptCount
 };
 long long get_option(int opt);

@@ -34,7 +34,6 @@ namespace radnet {
 
 constexpr int kTgtThreads = 1024;
 constexpr int kTgtWarps = kTgtThreads / 32;
-constexpr int kFillSlices = 32;            // fill units per panel
 
 struct RpnTargetParams {
     const double *gt;          // [B][Gmax][4] x1,x2,y1,y2
@@ -52,12 +51,12 @@ struct RpnTargetParams {
     int layout;
     double regr_scale;
     // workspace (all zero between launches)
-    int32_t *panel_done;       // [B] slices of the panel filled so far
-    int32_t *ctl;              // {next fill unit, CTAs finished, fault}
+    int32_t *panel_done;       // [B] double2 items of the panel filled so far
     int n_fill_ctas;           // block indices below this fill only
     int role;                  // 0 both roles in one launch, 1 fill only, 2 compute only (fill already done)
     // shared-memory layout of a compute CTA (byte offsets)
-    int sm_off_tables, sm_off_items, sm_off_hits, sm_off_hash, hit_cap, hash_slots, n_items_max;
+    int sm_off_tables, sm_off_items, sm_off_hits, sm_off_hash, sm_off_win, hit_cap, hash_slots, n_items_max;
+    int group;                 // panels per fill round (= number of compute CTAs)
     long long *stamps;         // profiling build only
 };
 
@@ -139,42 +138,53 @@ struct TgtAddr {
     }
 };
 
-// positive anchor (a, cell) matched to figure g: overlap label, np.repeat(overlap, 4) and the four
-// regression targets (utils.py:728-738, 815-816); `f32` = forced positive (utils.py:605, 766)
-__device__ __forceinline__ void write_positive(const RpnTargetParams &p, double *cls_b, double *regr_b, int a,
-                                               int cell, const double *gt4, bool forced) {
-    const int HW = p.H * p.W;
-    const TgtAddr ad{p.layout, p.A, HW};
+// positive anchor (a, cell) matched to figure g: the four regression targets as they are stored
+// (utils.py:669-687, 736; `forced` = forced positive, float32-rounded: utils.py:605, 766), times regr_scale
+__device__ __forceinline__ void positive_values(const RpnTargetParams &p, int a, int cell, const double *gt4,
+                                                bool forced, double v[4]) {
     const int jy = cell / p.W, ix = cell - jy * p.W;
     const AnchorPx an = anchor_px(p.stride, ix, jy, p.anchors.wh[a][0], p.anchors.wh[a][1]);
     double t[4];
     regr_targets(an, gt4[0], gt4[1], gt4[2], gt4[3], t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __dmul_rn(forced ? (double)(float)t[k] : t[k], p.regr_scale);
+}
+
+// overlap label, np.repeat(overlap, 4) and the regression targets of a positive anchor (utils.py:728-738,
+// 815-816); a forced positive also sets the valid label (utils.py:758-759)
+__device__ __forceinline__ void store_positive(const RpnTargetParams &p, double *cls_b, double *regr_b, int a,
+                                               int cell, const double v[4], bool forced) {
+    const TgtAddr ad{p.layout, p.A, p.H * p.W};
     if (forced) cls_b[ad.cls(a, cell)] = 1.0;
     cls_b[ad.cls(p.A + a, cell)] = 1.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         regr_b[ad.regr(4 * a + k, cell)] = 1.0;
-        const double v = forced ? (double)(float)t[k] : t[k];
-        regr_b[ad.regr(4 * p.A + 4 * a + k, cell)] = __dmul_rn(v, p.regr_scale);
+        regr_b[ad.regr(4 * p.A + 4 * a + k, cell)] = v[k];
     }
 }
 
-// ---- fill role: one unit = slice `s` of panel `b` (both tensors of the panel seen as one array of
-//      5*A*H*W double2 items: the label tensor first, then the regression tensor) ------------------------
-__device__ void fill_unit(const RpnTargetParams &p, int unit, uint8_t *s_inx, uint8_t *s_iny) {
-    const int b = unit / kFillSlices, s = unit - b * kFillSlices;
+// ---- fill role.  Both tensors of a panel are seen as ONE array of 5*A*H*W double2 items (label tensor
+//      first, then the regression tensor).  Panels are filled in groups of `group` consecutive panels (one
+//      round of the compute CTAs); inside a group fill CTA k streams the k-th contiguous share of the group's
+//      items.  Per panel segment: stores, a CTA barrier, then thread 0 alone fences and adds the segment's
+//      item count to the panel's counter (the pattern of a grid barrier: the fence is cumulative over the
+//      writes ordered before it by the barrier) while the other warps already store the next segment. ------
+__device__ void fill_segment(const RpnTargetParams &p, int b, int lo, int hi, uint8_t *s_inx, uint8_t *s_iny) {
     const int HW = p.H * p.W, AHW = p.A * HW;
-    const int n_items = 5 * AHW;                                  // double2 items of the panel
-    const int per = (n_items + kFillSlices - 1) / kFillSlices;
-    const int lo = s * per, hi = min(lo + per, n_items);
     double2 *cls2 = reinterpret_cast<double2 *>(p.y_cls + (size_t)b * 2 * AHW);
     double2 *regr2 = reinterpret_cast<double2 *>(p.y_regr + (size_t)b * 8 * AHW);
+    {   // regression tensor: zero wherever no anchor is positive
+        const double2 z = make_double2(0.0, 0.0);
+        const int r_lo = max(lo, AHW) - AHW, r_hi = hi - AHW;
+#pragma unroll 4
+        for (int i = r_lo + threadIdx.x; i < r_hi; i += kTgtThreads) regr2[i] = z;
+    }
     if (lo < AHW) {
         // label tensor: [valid | overlap]; valid = anchor inside the image on both axes (utils.py:629, 638), and
         // labels are only ever written inside the GT loop: no GT, no labels (utils.py:722-738)
         const int G = min(max(p.gt_count[b], 0), p.Gmax);
         const double img_w = p.img_wh[2 * b], img_h = p.img_wh[2 * b + 1];
-        __syncthreads();                                          // tables of the previous unit are no longer read
         for (int i = threadIdx.x; i < p.A * (p.W + p.H); i += kTgtThreads) {
             const int c = i / (p.W + p.H), r = i - c * (p.W + p.H);
             const bool isx = r < p.W;
@@ -205,27 +215,31 @@ __device__ void fill_unit(const RpnTargetParams &p, int unit, uint8_t *s_inx, ui
             cls2[i] = make_double2(v[0], v[1]);
         }
     }
-    {   // regression tensor: zero wherever no anchor is positive
-        const double2 z = make_double2(0.0, 0.0);
-        const int r_lo = max(lo, AHW) - AHW, r_hi = hi - AHW;
-#pragma unroll 4
-        for (int i = r_lo + threadIdx.x; i < r_hi; i += kTgtThreads) regr2[i] = z;
+    __syncthreads();                                              // all stores of the segment issued; tables free
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&p.panel_done[b], hi - lo);
     }
-    // publish: the slice is complete once every thread's stores are visible device-wide
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(&p.panel_done[b], 1);
 }
 
-// one fill unit from the shared counter; false when none is left
-__device__ bool fill_next_unit(const RpnTargetParams &p, int *s_unit, uint8_t *s_inx, uint8_t *s_iny) {
-    __syncthreads();
-    if (threadIdx.x == 0) *s_unit = atomicAdd(&p.ctl[0], 1);
-    __syncthreads();
-    const int u = *s_unit;
-    if (u >= p.B * kFillSlices) return false;
-    fill_unit(p, u, s_inx, s_iny);
-    return true;
+__device__ void fill_role(const RpnTargetParams &p, int k, int n_fill, int group, uint8_t *s_inx, uint8_t *s_iny) {
+    const long long per_panel = 5LL * p.A * p.H * p.W;
+#pragma unroll 1
+    for (int b0 = 0; b0 < p.B; b0 += group) {
+        const int nb = min(group, p.B - b0);
+        const long long total = per_panel * nb;
+        // shares are multiples of 64 items (1 KB) so that every CTA writes whole, aligned lines
+        const long long share = ((total + n_fill - 1) / n_fill + 63) & ~63LL;
+        long long lo = share * k, hi = lo + share;
+        if (hi > total) hi = total;
+        while (lo < hi) {
+            const int b = (int)(lo / per_panel);
+            const long long base = (long long)b * per_panel;
+            const long long seg_hi = (hi < base + per_panel) ? hi : base + per_panel;
+            fill_segment(p, b0 + b, (int)(lo - base), (int)(seg_hi - base), s_inx, s_iny);
+            lo = seg_hi;
+        }
+    }
 }
 
 __device__ __forceinline__ int ld_acquire(const int *ptr) {
@@ -238,7 +252,7 @@ __device__ __forceinline__ uint32_t hash_key(uint32_t k) { return (k * 265443576
 
 __global__ void __launch_bounds__(kTgtThreads, 1) rpn_targets_kernel(RpnTargetParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_ctl[8];              // 0 fill unit, 1 ready flag, 2 hits, 3 fault, 4 item count
+    __shared__ int s_ctl[8];              // 1 ready flag, 2 hits, 3 regular winners, 4 forced positives
     const int HW = p.H * p.W, AHW = p.A * HW;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
@@ -268,11 +282,15 @@ __global__ void __launch_bounds__(kTgtThreads, 1) rpn_targets_kernel(RpnTargetPa
     int *s_tg = reinterpret_cast<int *>(s_tkey + p.hash_slots);                          // [slots] winning figure
     const int hit_cap = p.hit_cap;
     const uint32_t hmask = (uint32_t)p.hash_slots - 1;
+    // positives ready to be stored once the panel is filled: regular winners, then forced ones
+    double *s_wv = reinterpret_cast<double *>(smem + p.sm_off_win);                      // [hit_cap + Gmax][4]
+    int *s_wkey = reinterpret_cast<int *>(s_wv + 4 * (size_t)(hit_cap + p.Gmax));        // [hit_cap + Gmax] a*HW + cell
 
     const bool fill_only = p.role == 1 || (p.role == 0 && (int)blockIdx.x < p.n_fill_ctas);
     if (fill_only) {
         TGT_STAMP(0);
-        while (fill_next_unit(p, &s_ctl[0], s_inx, s_iny)) {}
+        if (p.role == 1) fill_role(p, (int)blockIdx.x, (int)gridDim.x, p.B, s_inx, s_iny);
+        else fill_role(p, (int)blockIdx.x, p.n_fill_ctas, p.group, s_inx, s_iny);
         TGT_STAMP(9);
     } else {
         const int n_comp = p.role == 2 ? (int)gridDim.x : (int)gridDim.x - p.n_fill_ctas;
@@ -309,7 +327,7 @@ __global__ void __launch_bounds__(kTgtThreads, 1) rpn_targets_kernel(RpnTargetPa
                 s_tmax[i] = 0ull;
                 s_tg[i] = 0x7fffffff;
             }
-            if (threadIdx.x == 0) { s_ctl[2] = 0; s_ctl[1] = 0; }
+            if (threadIdx.x == 0) { s_ctl[2] = 0; s_ctl[1] = 0; s_ctl[3] = 0; s_ctl[4] = 0; }
             __syncthreads();
             // A LOWER bound of every figure's best float32 IoU, from the exact IoU with the A anchors of
             // the cell under the figure's centre.  Pairs whose float32 estimate is below it by more than
@@ -470,7 +488,9 @@ __global__ void __launch_bounds__(kTgtThreads, 1) rpn_targets_kernel(RpnTargetPa
             TGT_STAMP(3);
 
             // Phase 2 - settle every hit anchor: highest IoU wins, equal IoU -> the earlier figure (strict '>'
-            // in figure order, utils.py:710-713).  Open-addressing table keyed by the anchor; three passes.
+            // in figure order, utils.py:710-713).  Open-addressing table keyed by the anchor; three passes.  The
+            // winners and their regression targets are parked in shared memory: once the panel is filled only
+            // stores are left.
             const int n_hit = s_ctl[2];
             const bool replay = n_hit > hit_cap;
             if (!replay) {
@@ -491,9 +511,19 @@ __global__ void __launch_bounds__(kTgtThreads, 1) rpn_targets_kernel(RpnTargetPa
                     while (s_tkey[slot] != (uint32_t)h.key) slot = (slot + 1) & hmask;
                     if ((unsigned long long)__double_as_longlong(h.iou) == s_tmax[slot]) atomicMin(&s_tg[slot], h.g);
                 }
+                __syncthreads();
+                for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
+                    const TargetHit h = s_hit[e];
+                    uint32_t slot = hash_key((uint32_t)h.key) & hmask;
+                    while (s_tkey[slot] != (uint32_t)h.key) slot = (slot + 1) & hmask;
+                    if ((unsigned long long)__double_as_longlong(h.iou) == s_tmax[slot] && s_tg[slot] == h.g) {
+                        const int a2 = h.key / HW, pos = atomicAdd(&s_ctl[3], 1);
+                        s_wkey[pos] = h.key;
+                        positive_values(p, a2, h.key - a2 * HW, s_gt + 4 * h.g, false, s_wv + 4 * pos);
+                    }
+                }
             }
             // forced positives + best_anchor table (utils.py:741-766): decode the best anchor of every figure
-            __syncthreads();
             for (int g = threadIdx.x; g < p.Gmax; g += kTgtThreads) {
                 const unsigned long long key = g < G ? s_best[g] : 0ull;
                 const int nh = g < G ? s_hits[g] : 0;
@@ -512,39 +542,53 @@ __global__ void __launch_bounds__(kTgtThreads, 1) rpn_targets_kernel(RpnTargetPa
                 p.n_hits[(size_t)b * p.Gmax + g] = nh;
                 s_order[g] = order;
             }
+            __syncthreads();
+            // The reference applies the forced positives in GT order, so when several GT share the same best
+            // anchor the LAST one wins: a figure is only kept if no later forced figure targets its anchor.
+            const int n_win = s_ctl[3];
+            for (int g = threadIdx.x; g < G; g += kTgtThreads) {
+                const unsigned o = s_order[g];
+                if (o == 0xFFFFFFFFu) continue;
+                bool last = true;
+                for (int g2 = g + 1; g2 < G; ++g2) last = last && (s_order[g2] != o);
+                if (!last) continue;
+                const int jy = (int)(o % (unsigned)p.H);
+                const unsigned rest = o / (unsigned)p.H;
+                const int ix = (int)(rest % (unsigned)p.W);
+                const int a2 = (int)(rest / (unsigned)p.W);
+                const int pos = hit_cap + atomicAdd(&s_ctl[4], 1);
+                s_wkey[pos] = a2 * HW + jy * p.W + ix;
+                positive_values(p, a2, jy * p.W + ix, s_gt + 4 * g, true, s_wv + 4 * pos);
+            }
             TGT_STAMP(4);
 
-            // ---- wait until every slice of this panel has been filled; fill slices meanwhile -----------
+            // ---- wait until every item of this panel has been filled -----------------------------------
             if (p.role == 0) {
+                const int want = 5 * AHW;
                 const long long t_start = global_ns();
                 while (true) {
                     __syncthreads();
                     if (threadIdx.x == 0) {
                         const int done = ld_acquire(&p.panel_done[b]);
-                        s_ctl[1] = done >= kFillSlices;
-                        if (!s_ctl[1] && global_ns() - t_start > 4000000000LL) { s_ctl[1] = 2; atomicExch(&p.ctl[2], 1); }
+                        s_ctl[1] = done >= want;
+                        if (!s_ctl[1] && global_ns() - t_start > 4000000000LL) s_ctl[1] = 2;
                     }
                     __syncthreads();
                     if (s_ctl[1]) break;
-                    fill_next_unit(p, &s_ctl[0], s_inx, s_iny);
                 }
-                __threadfence();
                 if (s_ctl[1] == 2)         // the fill never completed (4 s): results invalid, reported through n_hits
                     for (int g = threadIdx.x; g < p.Gmax; g += kTgtThreads) p.n_hits[(size_t)b * p.Gmax + g] = -1;
+            } else {
+                __syncthreads();
             }
             TGT_STAMP(5);
             if (threadIdx.x == 0) p.panel_done[b] = 0;            // leave the workspace clean
 
             // regular positives (utils.py:728-738)
             if (!replay) {
-                for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
-                    const TargetHit h = s_hit[e];
-                    uint32_t slot = hash_key((uint32_t)h.key) & hmask;
-                    while (s_tkey[slot] != (uint32_t)h.key) slot = (slot + 1) & hmask;
-                    if ((unsigned long long)__double_as_longlong(h.iou) == s_tmax[slot] && s_tg[slot] == h.g) {
-                        const int a2 = h.key / HW;
-                        write_positive(p, cls_b, regr_b, a2, h.key - a2 * HW, s_gt + 4 * h.g, false);
-                    }
+                for (int e = threadIdx.x; e < n_win; e += kTgtThreads) {
+                    const int key = s_wkey[e], a2 = key / HW;
+                    store_positive(p, cls_b, regr_b, a2, key - a2 * HW, s_wv + 4 * e, false);
                 }
             } else {
                 // more positives than the list holds (never seen in practice): shape by shape, figure by figure
@@ -574,40 +618,29 @@ __global__ void __launch_bounds__(kTgtThreads, 1) rpn_targets_kernel(RpnTargetPa
                     }
                     for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) {
                         const int lg = s_lg[cell];
-                        if (lg >= 0) write_positive(p, cls_b, regr_b, a, cell, s_gt + 4 * lg, false);
+                        if (lg >= 0) {
+                            double v[4];
+                            positive_values(p, a, cell, s_gt + 4 * lg, false, v);
+                            store_positive(p, cls_b, regr_b, a, cell, v, false);
+                        }
                     }
                 }
             }
             __syncthreads();                                                          // regular before forced writes
-            // The reference applies the forced positives in GT order, so when several GT share the same best
-            // anchor the LAST one wins: a thread only writes if no later forced GT targets its anchor.
-            for (int g = threadIdx.x; g < G; g += kTgtThreads) {
-                const unsigned o = s_order[g];
-                if (o == 0xFFFFFFFFu) continue;
-                bool last = true;
-                for (int g2 = g + 1; g2 < G; ++g2) last = last && (s_order[g2] != o);
-                if (!last) continue;
-                const int jy = (int)(o % (unsigned)p.H);
-                const unsigned rest = o / (unsigned)p.H;
-                const int ix = (int)(rest % (unsigned)p.W);
-                const int a2 = (int)(rest / (unsigned)p.W);
-                write_positive(p, cls_b, regr_b, a2, jy * p.W + ix, s_gt + 4 * g, true);
+            const int n_forced = s_ctl[4];
+            for (int e = threadIdx.x; e < n_forced; e += kTgtThreads) {
+                const int key = s_wkey[hit_cap + e], a2 = key / HW;
+                store_positive(p, cls_b, regr_b, a2, key - a2 * HW, s_wv + 4 * (hit_cap + e), true);
             }
+#ifdef RADNET_TGT_PROFILE
+            if (p.stamps && threadIdx.x == 0) {
+                p.stamps[(size_t)blockIdx.x * 16 + 10] = n_chunks;
+                p.stamps[(size_t)blockIdx.x * 16 + 11] = n_hit;
+                p.stamps[(size_t)blockIdx.x * 16 + 12] = n_win;
+                p.stamps[(size_t)blockIdx.x * 16 + 13] = n_forced;
+            }
+#endif
             TGT_STAMP(6);
-        }
-        // panels done: help with whatever is left of the fill
-        if (p.role == 0) while (fill_next_unit(p, &s_ctl[0], s_inx, s_iny)) {}
-    }
-    // ---- the last CTA out resets the launch-wide counters --------------------------------------------
-    if (p.role != 2) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const int prev = atomicAdd(&p.ctl[1], 1);
-            if (prev == (int)gridDim.x - 1) {
-                p.ctl[0] = 0;
-                p.ctl[1] = 0;
-            }
         }
     }
 }
@@ -745,7 +778,7 @@ using namespace radnet;
 
 namespace {
 struct TgtSmemLayout {
-    size_t off_tables, off_items, off_hits, off_hash, total;
+    size_t off_tables, off_items, off_hits, off_hash, off_win, total;
     int hit_cap, hash_slots, n_items_max;
 };
 TgtSmemLayout tgt_smem_layout(int Gmax, int H, int W, int A, int hit_cap) {
@@ -767,7 +800,8 @@ TgtSmemLayout tgt_smem_layout(int Gmax, int H, int W, int A, int hit_cap) {
     // the replay path reuses both regions as {double iou[HW]; int figure[HW]}
     if (hits_bytes + hash_bytes < 12 * HW + 16) hits_bytes = align_up(12 * HW + 16 - hash_bytes, 16);
     l.off_hash = off + hits_bytes;
-    l.total = l.off_hash + hash_bytes;
+    l.off_win = l.off_hash + hash_bytes;
+    l.total = l.off_win + ((size_t)hit_cap + gm) * (4 * sizeof(double) + sizeof(int)) + 16;
     return l;
 }
 size_t tgt_ws_bytes(int B) { return align_up((size_t)B * sizeof(int32_t) + 16, 256); }
@@ -816,7 +850,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
         set_error("rpn_targets: workspace %zu < %zu", ws_bytes, tgt_ws_bytes(B));
         return RADNET_E_WORKSPACE;
     }
-    int hit_cap = 2048;
+    int hit_cap = 1024;
     {   // tests shrink the list to exercise the replay path
         const long long v = get_option(kOptTargetsHitCap);
         if (v >= 1 && v < hit_cap) hit_cap = (int)v;
@@ -842,9 +876,8 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     p.y_cls = y_rpn_cls; p.y_regr = y_rpn_regr; p.best_anchor = best_anchor; p.n_hits = n_hits;
     p.layout = layout; p.regr_scale = regr_scale;
     p.panel_done = reinterpret_cast<int32_t *>(ws);
-    p.ctl = p.panel_done + B;
     p.sm_off_tables = (int)sl.off_tables; p.sm_off_items = (int)sl.off_items; p.sm_off_hits = (int)sl.off_hits;
-    p.sm_off_hash = (int)sl.off_hash; p.hit_cap = sl.hit_cap; p.hash_slots = sl.hash_slots; p.n_items_max = sl.n_items_max;
+    p.sm_off_hash = (int)sl.off_hash; p.sm_off_win = (int)sl.off_win; p.hit_cap = sl.hit_cap; p.hash_slots = sl.hash_slots; p.n_items_max = sl.n_items_max;
 #ifdef RADNET_TGT_PROFILE
     p.stamps = g_tgt_stamps;
 #endif
@@ -856,15 +889,12 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     if (n_comp < 1) n_comp = (n_sm * 43 + 99) / 100;
     if (n_comp > B) n_comp = B;
     if (n_comp > n_sm - 1) n_comp = n_sm > 1 ? n_sm - 1 : 1;
-    const long long n_units = (long long)B * kFillSlices;
     long long n_fill = n_sm - n_comp;
     if (n_fill < 1) n_fill = 1;
-    if (n_fill > n_units) n_fill = n_units;
     if (get_option(kOptTargetsTwoLaunches) == 1) {
         // no co-residency assumed: the fill as its own launch, then the panels (stream order replaces the wait)
-        p.role = 1; p.n_fill_ctas = 0;
-        const long long g1 = n_units < n_sm ? n_units : n_sm;
-        rpn_targets_kernel<<<(unsigned)g1, kTgtThreads, sl.total, st>>>(p);
+        p.role = 1; p.n_fill_ctas = 0; p.group = B;
+        rpn_targets_kernel<<<(unsigned)n_sm, kTgtThreads, sl.total, st>>>(p);
         if (int rc = check_launch("rpn_targets_kernel (fill)")) return rc;
         p.role = 2;
         const long long g2 = B < n_sm ? B : n_sm;
@@ -873,6 +903,7 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     }
     p.role = 0;
     p.n_fill_ctas = (int)n_fill;
+    p.group = (int)n_comp;
     rpn_targets_kernel<<<(unsigned)(n_fill + n_comp), kTgtThreads, sl.total, st>>>(p);
     return check_launch("rpn_targets_kernel");
 }

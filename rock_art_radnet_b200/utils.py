@@ -2,9 +2,12 @@
 `calc_region_props` (upstream keras-frcnn name `calc_rpn`), `get_new_img_size`, `iou`.
 
 The anchor x GT IoU / label / regression-target computation runs in
-libradnet_b200.so (`radnet_rpn_targets`); the host keeps what the reference also
-does on the host with the global NumPy RNG: the 256-region subsampling.
+libradnet_b200.so (`radnet_rpn_targets`), and so does the 256-region subsampling the
+reference draws from the global NumPy generator (`radnet_rpn_subsample` replays the
+legacy MT19937 `np.random.choice` stream; the host only hands the generator state over).
 """
+import threading
+
 import numpy as np
 import torch
 
@@ -114,61 +117,121 @@ def rpn_targets_device(C, gt_boxes, gt_is_bg, gt_count, H, W, img_wh, device=Non
     return batch.run(gt_dev, bg_dev, gt_count, wh_dev)
 
 
-def _subsample_regions(y_is_box_valid, y_rpn_overlap, max_n_regions=256):
-    """Host half of calc_region_props: random balancing to 256 regions with the legacy global
-    NumPy RNG, in place on the (1,A,H,W) arrays (reference utils.py:777-813).  Returns n_pos."""
-    where_pos = np.where(np.logical_and(y_rpn_overlap[0] == 1, y_is_box_valid[0] == 1))
-    where_neg = np.where(np.logical_and(y_rpn_overlap[0] == 0, y_is_box_valid[0] == 1))
-    n_pos, n_neg = len(where_pos[0]), len(where_neg[0])
-    half = int(max_n_regions / 2)
+class _RegionPropsContext:
+    """Everything one `calc_region_props` call needs, allocated once per (config, map size, figure capacity)
+    and reused: K3 for one panel, the device sampler, ONE packed device buffer for the small inputs and
+    outputs with a pinned host mirror, pinned landing buffers for the two target tensors.
 
-    def channel_weights(channels, total):
-        # per-candidate probability = (share of its anchor channel) / (size of that channel);
-        # the table is keyed by the NEGATIVE channel ids in both branches, as in utils.py:789,804
-        ids, counts = np.unique(where_neg[0], return_counts=True)
-        share = dict(zip(ids, counts / total))
-        size = dict(zip(ids, counts))
-        return [share[c] / size[c] for c in channels]
+    Packed buffer (bytes): [gt Gcap*32 | img_wh 16 | count 4 (+12) | is_bg Gcap (padded) | rng state 2512 |
+    best_anchor Gcap*16 | n_hits Gcap*4 (padded) | sampler report 32].  One H2D copy ships everything up to
+    and including the rng state, one D2H copy brings back everything from the rng state on."""
 
-    if n_pos > max_n_regions / 2:
-        drop = np.random.choice(n_pos, n_pos - half, replace=False, p=channel_weights(where_pos[0], n_pos))
-        y_is_box_valid[0, where_pos[0][drop], where_pos[1][drop], where_pos[2][drop]] = 0
-        n_pos = half
-    if n_neg + n_pos > max_n_regions:
-        drop = np.random.choice(n_neg, n_neg - n_pos, replace=False, p=channel_weights(where_neg[0], n_neg))
-        y_is_box_valid[0, where_neg[0][drop], where_neg[1][drop], where_neg[2][drop]] = 0
-    return n_pos
+    def __init__(self, C, H, W, Gcap, dev):
+        from .sampling import RpnSubsampler
+        self.C, self.H, self.W, self.Gcap, self.dev = C, H, W, Gcap, dev
+        self.batch = RpnTargetBatch(C, 1, Gcap, H, W, device=dev)
+        self.A = self.batch.A
+        self.sampler = RpnSubsampler(1, H, W, self.A, device=dev)
+        pad16 = lambda v: (v + 15) // 16 * 16
+        self.o_gt = 0
+        self.o_wh = Gcap * 32
+        self.o_cnt = self.o_wh + 16
+        self.o_bg = self.o_cnt + 16
+        self.o_state = self.o_bg + pad16(Gcap)
+        self.o_best = self.o_state + pad16(625 * 4)
+        self.o_hits = self.o_best + Gcap * 16
+        self.o_rep = self.o_hits + pad16(Gcap * 4)
+        self.n_bytes = self.o_rep + 32
+        self.dev_buf = torch.zeros((self.n_bytes,), dtype=torch.uint8, device=dev)
+        self.host_buf = torch.zeros((self.n_bytes,), dtype=torch.uint8).pin_memory()
+        hb = self.host_buf.numpy()
+        self.h_gt = hb[self.o_gt:self.o_wh].view(np.float64).reshape(Gcap, 4)
+        self.h_wh = hb[self.o_wh:self.o_wh + 16].view(np.float64)
+        self.h_cnt = hb[self.o_cnt:self.o_cnt + 4].view(np.int32)
+        self.h_bg = hb[self.o_bg:self.o_bg + Gcap]
+        self.h_state = hb[self.o_state:self.o_state + 2500].view(np.uint32)
+        self.h_best = hb[self.o_best:self.o_hits].view(np.int32).reshape(Gcap, 4)
+        self.h_hits = hb[self.o_hits:self.o_hits + 4 * Gcap].view(np.int32)
+        self.h_rep = hb[self.o_rep:self.o_rep + 32].view(np.int32)
+        db = self.dev_buf
+        self.d_gt = db[self.o_gt:self.o_wh]
+        self.d_wh = db[self.o_wh:self.o_wh + 16]
+        self.d_cnt = db[self.o_cnt:self.o_cnt + 4]
+        self.d_bg = db[self.o_bg:self.o_bg + Gcap]
+        self.d_state = db[self.o_state:self.o_state + 2500]
+        self.d_rep = db[self.o_rep:self.o_rep + 32]
+        # K3 writes best_anchor / n_hits straight into the packed buffer
+        self.batch.best = db[self.o_best:self.o_hits].view(torch.int32).view(1, Gcap, 4)
+        self.batch.hits = db[self.o_hits:self.o_hits + 4 * Gcap].view(torch.int32).view(1, Gcap)
+        self.h_cls = torch.empty(tuple(self.batch.y_cls.shape), dtype=torch.float64).pin_memory()
+        self.h_regr = torch.empty(tuple(self.batch.y_regr.shape), dtype=torch.float64).pin_memory()
+
+
+_CONTEXTS = {}
+_CONTEXT_LOCK = threading.Lock()
+
+
+def _region_props_context(C, H, W, G, dev):
+    Gcap = max(32, (G + 31) // 32 * 32)
+    key = (tuple(C.anchor_box_scales), tuple(map(tuple, C.anchor_box_ratios)), float(C.rpn_stride),
+           float(C.rpn_max_overlap), H, W, Gcap, dev.index)
+    ctx = _CONTEXTS.get(key)
+    if ctx is None:
+        if len(_CONTEXTS) > 16:
+            _CONTEXTS.clear()
+        ctx = _RegionPropsContext(C, H, W, Gcap, dev)
+        _CONTEXTS[key] = ctx
+    return ctx
 
 
 def calc_region_props(C, img_data, width, height, width_resized, height_resized, get_feat_map_size,
                       verbose=False):
-    """RPN anchor targets for one image (reference utils.py:554-821).
+    """RPN anchor targets for one image (reference utils.py:554-821), including the random balancing to 256
+    regions with NumPy's global legacy generator (utils.py:777-813; `np.random`'s state is read, replayed on
+    the device and advanced exactly as the reference advances it).
 
     Returns (y_rpn_cls (1,2A,fh,fw) float64 = [valid | overlap],
              y_rpn_regr (1,8A,fh,fw) float64 = [repeat(overlap,4) | regr],
-             best_anchor_for_bbox (G,4) int64, n_pos)."""
+             best_anchor_for_bbox (G,4) int64, n_pos).
+    KeyError, like the reference, when more than 128 anchors are positive and one of them sits in an anchor
+    channel without any negative (utils.py:789-795)."""
+    from .sampling import numpy_state_words, set_numpy_state
+    D.require_cuda()
+    dev = torch.device("cuda:%d" % torch.cuda.current_device())
     fw, fh = get_feat_map_size(width_resized, height_resized)                 # utils.py:592
     bboxes = img_data['bboxes']
     G = len(bboxes)
-    gt = np.zeros((1, max(G, 1), 4))
-    is_bg = np.zeros((1, max(G, 1)), dtype=np.uint8)
-    for k, bb in enumerate(bboxes):                                           # utils.py:608-613
-        gt[0, k, 0] = bb['x1'] * (width_resized / float(width))
-        gt[0, k, 1] = bb['x2'] * (width_resized / float(width))
-        gt[0, k, 2] = bb['y1'] * (height_resized / float(height))
-        gt[0, k, 3] = bb['y2'] * (height_resized / float(height))
-        is_bg[0, k] = 1 if bb['class'] == 'bg' else 0
-    y_cls_d, y_regr_d, best_d, _ = rpn_targets_device(
-        C, gt if G else None, is_bg if G else None, np.array([G], dtype=np.int32), int(fh), int(fw),
-        np.array([[float(width_resized), float(height_resized)]]))
-    A = y_cls_d.shape[1] // 2
-    y_cls = y_cls_d.cpu().numpy()
-    y_rpn_regr = y_regr_d.cpu().numpy()
-    y_is_box_valid = y_cls[:, :A]
-    y_rpn_overlap = y_cls[:, A:]
-    n_pos = _subsample_regions(y_is_box_valid, y_rpn_overlap)
-    best_anchor_for_bbox = best_d[0].cpu().numpy().astype(np.int64).reshape(G, 4)
-    return np.copy(y_cls), np.copy(y_rpn_regr), best_anchor_for_bbox, n_pos
+    with _CONTEXT_LOCK:
+        ctx = _region_props_context(C, int(fh), int(fw), G, dev)
+        sx, sy = width_resized / float(width), height_resized / float(height)
+        for k, bb in enumerate(bboxes):                                       # utils.py:608-613
+            ctx.h_gt[k, 0] = bb['x1'] * sx
+            ctx.h_gt[k, 1] = bb['x2'] * sx
+            ctx.h_gt[k, 2] = bb['y1'] * sy
+            ctx.h_gt[k, 3] = bb['y2'] * sy
+            ctx.h_bg[k] = 1 if bb['class'] == 'bg' else 0
+        ctx.h_wh[0], ctx.h_wh[1] = float(width_resized), float(height_resized)
+        ctx.h_cnt[0] = G
+        ctx.h_state[:625] = numpy_state_words()
+        ctx.dev_buf[:ctx.o_best].copy_(ctx.host_buf[:ctx.o_best], non_blocking=True)
+        y_cls_d, y_regr_d, _, _ = ctx.batch.run(ctx.d_gt, ctx.d_bg, ctx.d_cnt, ctx.d_wh)
+        ctx.sampler.run(y_cls_d, ctx.d_state, out=ctx.d_rep)
+        ctx.h_cls.copy_(y_cls_d, non_blocking=True)
+        ctx.h_regr.copy_(y_regr_d, non_blocking=True)
+        ctx.host_buf[ctx.o_state:].copy_(ctx.dev_buf[ctx.o_state:], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        rep = ctx.h_rep
+        if G and (ctx.h_hits[:G] < 0).any():
+            raise RuntimeError("radnet_rpn_targets: the fill of the panel never completed; results invalid")
+        if rep[3] == 1:
+            raise KeyError("anchor channel without negatives (pos_probs[l], reference utils.py:795)")
+        if rep[5] > 0:
+            set_numpy_state(ctx.h_state[:625])
+        y_cls = ctx.h_cls.numpy().copy()
+        y_rpn_regr = ctx.h_regr.numpy().copy()
+        best_anchor_for_bbox = ctx.h_best[:G].astype(np.int64).reshape(G, 4)
+        n_pos = int(rep[0])
+    return y_cls, y_rpn_regr, best_anchor_for_bbox, n_pos
 
 
 calc_rpn = calc_region_props

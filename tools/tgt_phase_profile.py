@@ -55,3 +55,6 @@ for it in range(4):
         v = v[v > 0] - t0
         if len(v):
             print("   %-18s n=%4d  min %7.2f  median %7.2f  max %7.2f us" % (names[k], len(v), v.min() / 1e3, np.median(v) / 1e3, v.max() / 1e3))
+    comp = st[st[:, 6] > 0]
+    for k, nm in ((10, "chunks"), (11, "hits"), (12, "winners"), (13, "forced")):
+        print("   per panel %-8s min %5d  median %5d  max %5d" % (nm, comp[:, k].min(), np.median(comp[:, k]), comp[:, k].max()))

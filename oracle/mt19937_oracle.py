@@ -127,7 +127,9 @@ def choice_noreplace(rng, pop, size):
 def choice_replace(rng, pop, size):
     """RandomState.choice(pop, size, replace=True) = pop[randint(0, len(pop), size)]."""
     pop = np.arange(pop) if np.isscalar(pop) else np.asarray(pop)
-    if len(pop) == 0:
+    if size < 0:
+        raise ValueError("negative dimensions are not allowed")
+    if len(pop) == 0 and size > 0:
         raise ValueError("'a' cannot be empty unless no samples are taken")
     idx = np.array([rng.interval(len(pop) - 1) for _ in range(size)], dtype=np.int64)
     return pop[idx]

@@ -97,6 +97,8 @@ def get_selected_samples(Y1, C):
     dev = torch.device("cuda:%d" % torch.cuda.current_device())
     Y1 = np.asarray(Y1)
     R, n_cls = int(Y1.shape[1]), int(Y1.shape[2])
+    if R == 0:       # np.random.choice([], n_rois, replace=True) (train.py:125)
+        raise ValueError("'a' cannot be empty unless no samples are taken")
     y = torch.from_numpy(np.ascontiguousarray(Y1[0], dtype=np.int32)).to(dev).unsqueeze(0)
     states = torch.from_numpy(numpy_state_words().view(np.int32)).to(dev).unsqueeze(0)
     selr = SampleSelector(1, R, n_cls, int(C.n_rois), device=dev)

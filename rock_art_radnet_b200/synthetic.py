@@ -318,3 +318,16 @@ def tiled_panel_head_outputs(C, panel_seed, tile, rois_xywh, n_slots=300, n_obj=
     P_regr = np.zeros((n_slots, r.shape[2]), dtype=np.float32)
     P_cls[:n], P_regr[:n] = a[0], r[0]
     return P_cls, P_regr
+
+
+def one_hot_rows(seed, n_pos, n_neg, n_cls=7):
+    """Y1 of calc_iou, (1, n_pos+n_neg, n_cls) int64: n_neg 'bg' rows (last class) and n_pos rows of random
+    foreground classes, interleaved at random - the input of get_selected_samples (reference train.py:93)."""
+    rng = np.random.default_rng(seed)
+    n = n_pos + n_neg
+    cls = np.full((n,), n_cls - 1, dtype=np.int64)
+    where = rng.permutation(n)[:n_pos]
+    cls[where] = rng.integers(0, n_cls - 1, n_pos)
+    Y1 = np.zeros((1, n, n_cls), dtype=np.int64)
+    Y1[0, np.arange(n), cls] = 1
+    return Y1

@@ -8,7 +8,7 @@ from oracle import radnet_oracle as O
 from rock_art_radnet_b200 import sharding
 from rock_art_radnet_b200 import synthetic as S
 from rock_art_radnet_b200.pipeline import DetectionRecords, anchor_cells, anchor_pixels
-from rock_art_radnet_b200.utils import _subsample_regions, get_new_img_size, iou
+from rock_art_radnet_b200.utils import get_new_img_size, iou
 
 
 def test_anchor_tables_follow_reference_order():
@@ -39,32 +39,6 @@ def test_scalar_arithmetic_helpers_have_no_cpu_path():
     net = RADNet(S.HotPathConfig(), None, None, None)
     with pytest.raises(RuntimeError):
         net.get_real_coordinates(0.75, 1, 2, 3, 4)
-
-
-@pytest.mark.parametrize("n_pos,n_neg", [(40, 3000), (200, 3000), (150, 60), (10, 100), (0, 500)])
-def test_subsampling_replays_the_reference_rng_stream(n_pos, n_neg):
-    rng = np.random.default_rng(n_pos * 7 + n_neg)
-    A, H, W = 9, 20, 20
-    flat = rng.permutation(A * H * W)
-    valid = np.zeros(A * H * W); overlap = np.zeros(A * H * W)
-    valid[flat[:n_pos + n_neg]] = 1
-    overlap[flat[:n_pos]] = 1
-    v1 = valid.reshape(1, A, H, W).copy(); o1 = overlap.reshape(1, A, H, W).copy()
-    v2, o2 = v1.copy(), o1.copy()
-    np.random.seed(123)
-    try:
-        ref = O.subsample_regions(v1, o1)
-        err = None
-    except (KeyError, ValueError) as e:       # the reference's own failure modes (utils.py:789-797)
-        ref, err = None, type(e)
-    np.random.seed(123)
-    if err is not None:
-        with pytest.raises(err):
-            _subsample_regions(v2, o2)
-        return
-    got = _subsample_regions(v2, o2)
-    assert got == ref and np.array_equal(v1, v2) and np.array_equal(o1, o2)
-    assert int((v2 * (1 - o2)).sum() + (v2 * o2).sum()) <= max(256, n_pos + n_neg if n_pos + n_neg <= 256 else 256)
 
 
 def test_detection_record_views_on_cpu():

@@ -3,9 +3,9 @@
 
     RADNET_B200_LIB=rock_art_radnet_b200/_C/libradnet_b200_prof.so python tools/tgt_phase_profile.py [B]
 
-Every CTA stamps %globaltimer (ns): fill CTAs at 0 start and 9 no unit left; compute CTAs (last panel they
-handled) at 0 start, 1 figures + floors + anchor tables, 2 windows, 3 phase 1 (IoU over the windows),
-4 phase 2 + best anchors, 5 panel filled (wait over), 6 positives written.  Relative to the earliest start."""
+Every CTA stamps %globaltimer (ns): 8 CTA start, 9 no fill unit left (CTAs that fill first); per panel (the last
+one a CTA handled) 0 start, 1 figures + floors + anchor tables, 2 windows, 3 phase 1 (IoU over the windows),
+4 phase 2 + positives parked, 5 panel filled (wait over), 6 positives written.  Relative to the earliest start."""
 import ctypes
 import os
 import sys
@@ -24,7 +24,7 @@ G, H, W = 20, 38, 38
 C = S.HotPathConfig()
 lib = _lib.load()
 A = 9
-stamps = torch.zeros((256 * 16,), dtype=torch.int64, device="cuda")
+stamps = torch.zeros((320 * 16,), dtype=torch.int64, device="cuda")
 lib.radnet_debug_set_tgt_stamps.argtypes = [ctypes.c_void_p]
 lib.radnet_debug_set_tgt_stamps(ctypes.c_void_p(stamps.data_ptr()))
 gt = np.zeros((B, G, 4))
@@ -45,16 +45,16 @@ for it in range(4):
     tb.run(gt_d, bg_d, cnt_d, wh_d)
     e.record()
     torch.cuda.synchronize()
-    st = stamps.cpu().numpy().reshape(256, 16).astype(np.float64)
-    st = st[st[:, 0] > 0]
-    t0 = st[:, 0].min()
-    names = {0: "start", 1: "setup", 2: "windows", 3: "phase1", 4: "phase2+best", 9: "fill: no unit left", 5: "panel filled", 6: "positives written"}
+    st = stamps.cpu().numpy().reshape(320, 16).astype(np.float64)
+    st = st[st[:, 8] > 0]
+    t0 = st[:, 8].min()
+    names = {8: "CTA start", 9: "fill: no unit left", 0: "panel start", 1: "setup", 2: "windows", 3: "phase1", 4: "phase2+parked", 5: "panel filled", 6: "positives written"}
     print("launch %d: event time %.1f us" % (it, a.elapsed_time(e) * 1e3))
-    for k in (0, 1, 2, 3, 4, 9, 5, 6):
+    for k in (8, 9, 0, 1, 2, 3, 4, 5, 6):
         v = st[:, k]
         v = v[v > 0] - t0
         if len(v):
             print("   %-18s n=%4d  min %7.2f  median %7.2f  max %7.2f us" % (names[k], len(v), v.min() / 1e3, np.median(v) / 1e3, v.max() / 1e3))
     comp = st[st[:, 6] > 0]
-    for k, nm in ((10, "chunks"), (11, "hits"), (12, "winners"), (13, "forced")):
+    for k, nm in ((10, "pairs"), (11, "hits"), (12, "winners"), (13, "forced")):
         print("   per panel %-8s min %5d  median %5d  max %5d" % (nm, comp[:, k].min(), np.median(comp[:, k]), comp[:, k].max()))

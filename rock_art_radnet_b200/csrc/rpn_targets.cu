@@ -36,7 +36,7 @@
 namespace radnet {
 
 constexpr int kTgtThreads = 512;
-constexpr int kUnitsPerPanel = 4;
+constexpr int kUnitsPerPanel = 16;
 
 struct RpnTargetParams {
     const double *gt;          // [B][Gmax][4] x1,x2,y1,y2
@@ -56,7 +56,7 @@ struct RpnTargetParams {
     // workspace (all zero between launches)
     int32_t *panel_done;       // [B] double2 items of the panel filled so far
     int32_t *ctl;              // {next fill unit, next panel, CTAs finished}
-    int first_compute_sm;      // SMs with %smid >= this take panels first
+    int n_compute_sm, n_sm;    // this many SMs, spread evenly over %smid, take panels first
     int role;                  // 0 both kinds of work in one launch, 1 fill only, 2 panels only (fill already done)
     // shared-memory layout (byte offsets)
     int sm_off_tables, sm_off_items, sm_off_hits, sm_off_hash, sm_off_win, hit_cap, hash_slots, n_items_max;
@@ -154,7 +154,8 @@ struct TgtShared {
     int *tg;                    // [slots] winning figure
     double *wv;                 // [hit_cap + G][4] values of the positives to store
     int *wkey;                  // [hit_cap + G]
-    int *ctl;                   // static: 0 pulled index, 1 ready flag, 2 hits, 3 winners, 4 forced, 5 scan carry
+    int *ctl;                   // static: 0 pulled index, 1 ready flag, 2 hits, 3 winners, 4 forced, 5 scan carry,
+                                //         6 prefetched fill unit
     int *warp;                  // static [17] scan scratch
 };
 
@@ -248,14 +249,22 @@ __device__ void fill_unit(const RpnTargetParams &p, const TgtShared &s, int unit
     }
 }
 
-// next fill unit from the shared counter; false when none is left
+// next fill unit from the shared counter; false when none is left.  The index of the unit after this one is
+// requested before the stores of this one are issued (s.ctl[6] holds a prefetched index, -1 = none), so the
+// round trip of the atomic is hidden behind the store stream.
 __device__ bool pull_fill(const RpnTargetParams &p, const TgtShared &s) {
     __syncthreads();
-    if (threadIdx.x == 0) s.ctl[0] = atomicAdd(&p.ctl[0], 1);
+    if (threadIdx.x == 0) {
+        s.ctl[0] = s.ctl[6] >= 0 ? s.ctl[6] : atomicAdd(&p.ctl[0], 1);
+        s.ctl[6] = -1;
+    }
     __syncthreads();
     const int u = s.ctl[0];
     if (u >= p.B * kUnitsPerPanel) return false;
+    int next = -1;
+    if (threadIdx.x == 0) next = atomicAdd(&p.ctl[0], 1);        // consumed after the stores below
     fill_unit(p, s, u);
+    if (threadIdx.x == 0) s.ctl[6] = next;
     return true;
 }
 
@@ -411,47 +420,55 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     // rpn_max_overlap go to a hit list; which figure wins a cell is settled in phase 2, so the figure order of the
     // reference ("first figure wins ties", utils.py:710-713) does not serialise anything.
     const int n_pairs = n_items ? s.pstart[n_items] : 0;
-#pragma unroll 1
-    for (int q = threadIdx.x; q < n_pairs; q += kTgtThreads) {
+    {
+        const int per_thread = (n_pairs + kTgtThreads - 1) / kTgtThreads;
+        int q = min((int)threadIdx.x * per_thread, n_pairs);
+        const int q_end = min(q + per_thread, n_pairs);
         int it = 0;                                                           // last item with pstart[it] <= q
-        for (int hi = n_items - 1; it < hi;) {
-            const int mid = (it + hi + 1) >> 1;
-            if (s.pstart[mid] <= q) it = mid; else hi = mid - 1;
-        }
-        const int a = it / G, g = it - a * G;
-        const int4 rg = s.range[it];
-        const int ww = rg.y - rg.x + 1;
-        const int t = q - s.pstart[it];
-        const int dy = t / ww;
-        const int ix = rg.x + t - dy * ww, jy = rg.z + dy;
-        const float4 XF = s.axf[a * p.W + ix], YF = s.ayf[a * p.H + jy];
-        // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
-        if (XF.w == 0.f || YF.w == 0.f) continue;
-        const double gx1 = s.gt[4 * g + 0], gx2 = s.gt[4 * g + 1], gy1 = s.gt[4 * g + 2], gy2 = s.gt[4 * g + 3];
-        const double2 X = s.ax[a * p.W + ix], Y = s.ay[a * p.H + jy];
-        // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
-        if (!(gx2 > X.x && X.y > gx1 && gy2 > Y.x && Y.y > gy1)) continue;
-        // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
-        const float4 gf = s.gt32[g];
-        const float wi = fminf(gf.z, XF.y) - fmaxf(gf.x, XF.x);
-        const float hi32 = fminf(gf.w, YF.y) - fmaxf(gf.y, YF.x);
-        const float itf = fmaxf(wi, 0.f) * fmaxf(hi32, 0.f);
-        const float est = __fdividef(itf, s.area32[g] + XF.z * YF.z - itf);
-        const float lim = fminf(__uint_as_float(s.floor[g]), thr32);
-        const bool need = (est + kIouMargin >= lim) ||      // could be the best anchor, or exceed rpn_max_overlap
-                          (s.skip[g] & 2) || !(XF.z <= 8192.f && YF.z <= 8192.f);   // estimate not trusted: exact
-        if (!need) continue;
-        const double iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
-        const float iou32 = (float)iou;                                       // float32 accumulator (utils.py:603)
-        if (iou32 > 0.f) {
-            // best anchor of this figure: max float32 IoU, then first in loop order size->ratio->ix->jy
-            const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);
-            atomicMax(&s.best[g], ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order));
-        }
-        if (iou > p.max_overlap) {                                            // utils.py:704
-            atomicAdd(&s.hits[g], 1);
-            const int pos = atomicAdd(&s.ctl[2], 1);
-            if (pos < hit_cap) s.hit[pos] = TargetHit{iou, a * HW + jy * p.W + ix, g};
+        if (q < q_end)
+            for (int hi = n_items - 1; it < hi;) {
+                const int mid = (it + hi + 1) >> 1;
+                if (s.pstart[mid] <= q) it = mid; else hi = mid - 1;
+            }
+        int it_end = q < q_end ? s.pstart[it + 1] : 0;
+#pragma unroll 1
+        for (; q < q_end; ++q) {
+            while (q >= it_end) { ++it; it_end = s.pstart[it + 1]; }          // next non-empty item
+            const int a = it / G, g = it - a * G;
+            const int4 rg = s.range[it];
+            const int ww = rg.y - rg.x + 1;
+            const int t = q - s.pstart[it];
+            const int dy = t / ww;
+            const int ix = rg.x + t - dy * ww, jy = rg.z + dy;
+            const float4 XF = s.axf[a * p.W + ix], YF = s.ayf[a * p.H + jy];
+            // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
+            if (XF.w == 0.f || YF.w == 0.f) continue;
+            const double gx1 = s.gt[4 * g + 0], gx2 = s.gt[4 * g + 1], gy1 = s.gt[4 * g + 2], gy2 = s.gt[4 * g + 3];
+            const double2 X = s.ax[a * p.W + ix], Y = s.ay[a * p.H + jy];
+            // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
+            if (!(gx2 > X.x && X.y > gx1 && gy2 > Y.x && Y.y > gy1)) continue;
+            // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
+            const float4 gf = s.gt32[g];
+            const float wi = fminf(gf.z, XF.y) - fmaxf(gf.x, XF.x);
+            const float hi32 = fminf(gf.w, YF.y) - fmaxf(gf.y, YF.x);
+            const float itf = fmaxf(wi, 0.f) * fmaxf(hi32, 0.f);
+            const float est = __fdividef(itf, s.area32[g] + XF.z * YF.z - itf);
+            const float lim = fminf(__uint_as_float(s.floor[g]), thr32);
+            const bool need = (est + kIouMargin >= lim) ||      // could be the best anchor, or exceed rpn_max_overlap
+                              (s.skip[g] & 2) || !(XF.z <= 8192.f && YF.z <= 8192.f);   // estimate not trusted: exact
+            if (!need) continue;
+            const double iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
+            const float iou32 = (float)iou;                                       // float32 accumulator (utils.py:603)
+            if (iou32 > 0.f) {
+                // best anchor of this figure: max float32 IoU, then first in loop order size->ratio->ix->jy
+                const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);
+                atomicMax(&s.best[g], ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order));
+            }
+            if (iou > p.max_overlap) {                                            // utils.py:704
+                atomicAdd(&s.hits[g], 1);
+                const int pos = atomicAdd(&s.ctl[2], 1);
+                if (pos < hit_cap) s.hit[pos] = TargetHit{iou, a * HW + jy * p.W + ix, g};
+            }
         }
     }
     __syncthreads();
@@ -514,8 +531,9 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
         }
     }
     // The reference applies the forced positives in GT order, so when several GT share the same best anchor the
-    // LAST one wins: a figure is only kept if no later forced figure targets its anchor.
-    for (int g = threadIdx.x; g < G; g += kTgtThreads) {
+    // LAST one wins: a figure is only kept if no later forced figure targets its anchor.  (Threads are taken from
+    // the top so that this float64 work runs next to the winners' above, not after it.)
+    for (int g = kTgtThreads - 1 - (int)threadIdx.x; g < G; g += kTgtThreads) {
         const unsigned o = s.order[g];
         if (o == 0xFFFFFFFFu) continue;
         bool last = true;
@@ -632,6 +650,7 @@ __global__ void __launch_bounds__(kTgtThreads, 2) rpn_targets_kernel(RpnTargetPa
     __shared__ int s_ctl[8];
     __shared__ int s_warp[17];
     const TgtShared s = carve(p, smem, s_ctl, s_warp);
+    if (threadIdx.x == 0) s_ctl[6] = -1;
 #ifdef RADNET_TGT_PROFILE
     if (p.stamps && threadIdx.x == 0) p.stamps[(size_t)blockIdx.x * 16 + 8] = global_ns();
 #endif
@@ -639,7 +658,7 @@ __global__ void __launch_bounds__(kTgtThreads, 2) rpn_targets_kernel(RpnTargetPa
         while (pull_fill(p, s)) {}
     } else if (p.role == 2) {
         while (pull_panel(p, s)) {}
-    } else if (sm_id() >= p.first_compute_sm) {
+    } else if (((long long)sm_id() * p.n_compute_sm) % p.n_sm < p.n_compute_sm) {     // n_compute_sm SMs, evenly spread
         while (pull_panel(p, s)) {}
         while (pull_fill(p, s)) {}
     } else {
@@ -796,7 +815,8 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     if (n_comp_sm > (B + per_sm - 1) / per_sm) n_comp_sm = (B + per_sm - 1) / per_sm;
     if (n_comp_sm > n_sm - 1) n_comp_sm = n_sm > 1 ? n_sm - 1 : 1;
     p.role = 0;
-    p.first_compute_sm = (int)(n_sm - n_comp_sm);
+    p.n_compute_sm = (int)n_comp_sm;
+    p.n_sm = n_sm;
     rpn_targets_kernel<<<(unsigned)grid, kTgtThreads, sl.total, st>>>(p);
     return check_launch("rpn_targets_kernel");
 }

@@ -37,6 +37,7 @@ namespace radnet {
 
 constexpr int kTgtThreads = 512;
 constexpr int kUnitsPerPanel = 16;
+constexpr int kGroupPanels = 64;          // fill completion is published and awaited per group of panels
 
 struct RpnTargetParams {
     const double *gt;          // [B][Gmax][4] x1,x2,y1,y2
@@ -54,7 +55,7 @@ struct RpnTargetParams {
     int layout;
     double regr_scale;
     // workspace (all zero between launches)
-    int32_t *panel_done;       // [B] double2 items of the panel filled so far
+    int32_t *group_done;       // [n_groups] double2 items filled so far in each group of kGroupPanels panels
     int32_t *ctl;              // {next fill unit, next panel, CTAs finished}
     int n_compute_sm, n_sm;    // this many SMs, spread evenly over %smid, take panels first
     int role;                  // 0 both kinds of work in one launch, 1 fill only, 2 panels only (fill already done)
@@ -155,7 +156,7 @@ struct TgtShared {
     double *wv;                 // [hit_cap + G][4] values of the positives to store
     int *wkey;                  // [hit_cap + G]
     int *ctl;                   // static: 0 pulled index, 1 ready flag, 2 hits, 3 winners, 4 forced, 5 scan carry,
-                                //         6 prefetched fill unit
+                                //         6 prefetched fill unit, 7 group of the unpublished items, 8 their count
     int *warp;                  // static [17] scan scratch
 };
 
@@ -189,10 +190,18 @@ __device__ __forceinline__ TgtShared carve(const RpnTargetParams &p, unsigned ch
     return s;
 }
 
+// thread 0: make the items this CTA filled since its last publication visible and count them for their group.
+// The fence is cumulative over the stores of all threads ordered before it by a CTA barrier.
+__device__ __forceinline__ void publish_fill(const RpnTargetParams &p, const TgtShared &s) {
+    if (s.ctl[8] > 0) {
+        __threadfence();
+        atomicAdd(&p.group_done[s.ctl[7]], s.ctl[8]);
+        s.ctl[8] = 0;
+    }
+}
+
 // ---- fill.  Both tensors of a panel are seen as ONE array of 5*A*H*W double2 items (label tensor first, then the
-//      regression tensor); unit u = quarter (u % 4) of panel u / 4.  Stores, a CTA barrier, then thread 0 alone
-//      fences and adds the unit's item count to the panel's counter (the pattern of a grid barrier: the fence is
-//      cumulative over the writes ordered before it by the barrier) while the other warps go on. -------------------
+//      regression tensor); unit u = sixteenth (u % 16) of panel u / 16. ---------------------------------------
 __device__ void fill_unit(const RpnTargetParams &p, const TgtShared &s, int unit) {
     const int b = unit / kUnitsPerPanel, q = unit - b * kUnitsPerPanel;
     const int HW = p.H * p.W, AHW = p.A * HW;
@@ -243,9 +252,13 @@ __device__ void fill_unit(const RpnTargetParams &p, const TgtShared &s, int unit
         }
     }
     __syncthreads();                                              // all stores of the unit issued; tables free
-    if (threadIdx.x == 0 && hi > lo) {
-        __threadfence();
-        atomicAdd(&p.panel_done[b], hi - lo);
+    if (threadIdx.x == 0) {
+        // completion is published per group of panels: one fence when this CTA leaves a group (or on demand),
+        // not one per unit - a fence per unit stalls the CTA at its next barrier for the whole drain time
+        const int gr = b / kGroupPanels;
+        if (s.ctl[7] != gr) publish_fill(p, s);
+        s.ctl[7] = gr;
+        s.ctl[8] += hi - lo;
     }
 }
 
@@ -260,7 +273,10 @@ __device__ bool pull_fill(const RpnTargetParams &p, const TgtShared &s) {
     }
     __syncthreads();
     const int u = s.ctl[0];
-    if (u >= p.B * kUnitsPerPanel) return false;
+    if (u >= p.B * kUnitsPerPanel) {
+        if (threadIdx.x == 0) publish_fill(p, s);                 // nothing left to pull: hand in what is pending
+        return false;
+    }
     int next = -1;
     if (threadIdx.x == 0) next = atomicAdd(&p.ctl[0], 1);        // consumed after the stores below
     fill_unit(p, s, u);
@@ -379,6 +395,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     TGT_STAMP(1);
 
     const float thr32 = (float)p.max_overlap;
+    const double inv_stride = 1.0 / p.stride;
     const int n_items = p.A * G;
     // Cell window of anchor shape a that can matter for figure g.  IoU >= L needs, on each axis, an overlap of at
     // least L*max(figure side, anchor side) (because union >= the larger area and the other overlap <= the smaller
@@ -400,8 +417,8 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
             const bool feasible = imax >= (L - 1e-9) * (wg * hg + aw * ah - imax);
             const double mx = L * fmax(wg, aw), my = L * fmax(hg, ah);
             // centre c = stride*(i+0.5) must satisfy  g1 + m - side/2 <= c <= g2 - m + side/2
-            const double xl = (gx1 + mx - aw * 0.5) / p.stride - 0.5, xh = (gx2 - mx + aw * 0.5) / p.stride - 0.5;
-            const double yl = (gy1 + my - ah * 0.5) / p.stride - 0.5, yh = (gy2 - my + ah * 0.5) / p.stride - 0.5;
+            const double xl = (gx1 + mx - aw * 0.5) * inv_stride - 0.5, xh = (gx2 - mx + aw * 0.5) * inv_stride - 0.5;
+            const double yl = (gy1 + my - ah * 0.5) * inv_stride - 0.5, yh = (gy2 - my + ah * 0.5) * inv_stride - 0.5;
             if (feasible && xl <= xh + 2.0 && yl <= yh + 2.0) {
                 r.x = max((int)fmax(floor(xl) - 1.0, 0.0), use[0]);
                 r.y = min((int)fmin(ceil(xh) + 1.0, (double)(p.W - 1)), use[1]);
@@ -460,9 +477,11 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
             const double iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
             const float iou32 = (float)iou;                                       // float32 accumulator (utils.py:603)
             if (iou32 > 0.f) {
-                // best anchor of this figure: max float32 IoU, then first in loop order size->ratio->ix->jy
+                // best anchor of this figure: max float32 IoU, then first in loop order size->ratio->ix->jy.  The
+                // 64-bit shared-memory max is a compare-and-swap loop: only candidates that beat the value seen go in.
                 const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);
-                atomicMax(&s.best[g], ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order));
+                const unsigned long long key = ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order);
+                if (key > *reinterpret_cast<volatile unsigned long long *>(&s.best[g])) atomicMax(&s.best[g], key);
             }
             if (iou > p.max_overlap) {                                            // utils.py:704
                 atomicAdd(&s.hits[g], 1);
@@ -551,13 +570,15 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
 
     // ---- wait until every item of this panel has been filled; fill meanwhile if there is anything left ---------
     if (p.role == 0) {
-        const int want = 5 * AHW;
+        const int gr = b / kGroupPanels;
+        const int want = 5 * AHW * min(kGroupPanels, p.B - gr * kGroupPanels);
         const long long t_start = global_ns();
         bool more = true;
         while (true) {
             __syncthreads();
             if (threadIdx.x == 0) {
-                const int done = ld_acquire(&p.panel_done[b]);
+                publish_fill(p, s);                               // never wait on items this CTA still holds back
+                const int done = ld_acquire(&p.group_done[gr]);
                 s.ctl[1] = done >= want;
                 if (!s.ctl[1] && global_ns() - t_start > 4000000000LL) s.ctl[1] = 2;
             }
@@ -572,7 +593,6 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
         __syncthreads();
     }
     TGT_STAMP(5);
-    if (threadIdx.x == 0) p.panel_done[b] = 0;            // leave the workspace clean
 
     // regular positives (utils.py:728-738)
     const int n_win = s.ctl[3];
@@ -647,10 +667,10 @@ __device__ bool pull_panel(const RpnTargetParams &p, const TgtShared &s) {
 
 __global__ void __launch_bounds__(kTgtThreads, 2) rpn_targets_kernel(RpnTargetParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_ctl[8];
+    __shared__ int s_ctl[12];
     __shared__ int s_warp[17];
     const TgtShared s = carve(p, smem, s_ctl, s_warp);
-    if (threadIdx.x == 0) s_ctl[6] = -1;
+    if (threadIdx.x == 0) { s_ctl[6] = -1; s_ctl[7] = -1; s_ctl[8] = 0; }
 #ifdef RADNET_TGT_PROFILE
     if (p.stamps && threadIdx.x == 0) p.stamps[(size_t)blockIdx.x * 16 + 8] = global_ns();
 #endif
@@ -677,6 +697,8 @@ __global__ void __launch_bounds__(kTgtThreads, 2) rpn_targets_kernel(RpnTargetPa
             p.ctl[0] = 0;
             p.ctl[1] = 0;
             p.ctl[2] = 0;
+            if (p.role != 1)
+                for (int g = 0; g < (p.B + kGroupPanels - 1) / kGroupPanels; ++g) p.group_done[g] = 0;
         }
     }
 }
@@ -713,7 +735,8 @@ TgtSmemLayout tgt_smem_layout(int Gmax, int H, int W, int A, int hit_cap) {
     l.total = l.off_win + ((size_t)hit_cap + gm) * (4 * sizeof(double) + sizeof(int)) + 16;
     return l;
 }
-size_t tgt_ws_bytes(int B) { return align_up(((size_t)B + 4) * sizeof(int32_t), 256); }
+int tgt_groups(int B) { return (B + kGroupPanels - 1) / kGroupPanels; }
+size_t tgt_ws_bytes(int B) { return align_up(((size_t)tgt_groups(B) + 4) * sizeof(int32_t), 256); }
 }  // namespace
 
 extern "C" size_t radnet_rpn_targets_workspace_bytes(int B, int Gmax, int H, int W, int A) {
@@ -784,8 +807,8 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     p.stride = rpn_stride; p.img_wh = img_wh; p.max_overlap = max_overlap;
     p.y_cls = y_rpn_cls; p.y_regr = y_rpn_regr; p.best_anchor = best_anchor; p.n_hits = n_hits;
     p.layout = layout; p.regr_scale = regr_scale;
-    p.panel_done = reinterpret_cast<int32_t *>(ws);
-    p.ctl = p.panel_done + B;
+    p.group_done = reinterpret_cast<int32_t *>(ws);
+    p.ctl = p.group_done + tgt_groups(B);
     p.sm_off_tables = (int)sl.off_tables; p.sm_off_items = (int)sl.off_items; p.sm_off_hits = (int)sl.off_hits;
     p.sm_off_hash = (int)sl.off_hash; p.sm_off_win = (int)sl.off_win; p.hit_cap = sl.hit_cap;
     p.hash_slots = sl.hash_slots; p.n_items_max = sl.n_items_max;

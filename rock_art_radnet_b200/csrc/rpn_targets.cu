@@ -66,9 +66,12 @@ struct RpnTargetParams {
 
 struct TargetHit {
     double iou;
+    double v[4];   // regression targets as stored (times regr_scale)
     int key;       // a*H*W + cell
-    int g;
+    int g;         // figure; set to -1 - g when the entry loses its anchor to another figure
 };
+
+constexpr int kNeedCap = 4096;            // candidate pairs queued for the exact float64 pass
 
 __device__ __forceinline__ long long global_ns() {
     long long t;
@@ -150,13 +153,15 @@ struct TgtShared {
     int4 *range;                // [A*G] cell window of (shape, figure)
     int *pstart;                // [A*G + 1] first candidate pair of the item
     TargetHit *hit;             // [hit_cap]
+    int *need;                  // [kNeedCap] candidate pairs whose exact IoU is needed
     unsigned long long *tmax;   // [slots] best IoU bits of an anchor
     uint32_t *tkey;             // [slots] a*HW + cell or ~0
     int *tg;                    // [slots] winning figure
-    double *wv;                 // [hit_cap + G][4] values of the positives to store
-    int *wkey;                  // [hit_cap + G]
+    double *wv;                 // [G][4] values of the forced positives
+    int *wkey;                  // [G] their anchors
     int *ctl;                   // static: 0 pulled index, 1 ready flag, 2 hits, 3 winners, 4 forced, 5 scan carry,
-                                //         6 prefetched fill unit, 7 group of the unpublished items, 8 their count
+                                //         6 prefetched fill unit, 7 group of the unpublished items, 8 their count,
+                                //         9 queued pairs
     int *warp;                  // static [17] scan scratch
 };
 
@@ -184,7 +189,8 @@ __device__ __forceinline__ TgtShared carve(const RpnTargetParams &p, unsigned ch
     s.tkey = reinterpret_cast<uint32_t *>(s.tmax + p.hash_slots);
     s.tg = reinterpret_cast<int *>(s.tkey + p.hash_slots);
     s.wv = reinterpret_cast<double *>(smem + p.sm_off_win);
-    s.wkey = reinterpret_cast<int *>(s.wv + 4 * (size_t)(p.hit_cap + p.Gmax));
+    s.wkey = reinterpret_cast<int *>(s.wv + 4 * (size_t)p.Gmax);
+    s.need = s.wkey + p.Gmax;
     s.ctl = s_ctl;
     s.warp = s_warp;
     return s;
@@ -355,7 +361,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
         s.tmax[i] = 0ull;
         s.tg[i] = 0x7fffffff;
     }
-    if (threadIdx.x == 0) { s.ctl[1] = 0; s.ctl[2] = 0; s.ctl[3] = 0; s.ctl[4] = 0; }
+    if (threadIdx.x == 0) { s.ctl[1] = 0; s.ctl[2] = 0; s.ctl[3] = 0; s.ctl[4] = 0; s.ctl[9] = 0; }
     __syncthreads();
     // A LOWER bound of every figure's best float32 IoU, from the exact IoU with the A anchors of the cell under
     // the figure's centre.  Pairs whose float32 estimate is below it by more than the margin cannot be (or tie
@@ -433,10 +439,41 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     scan_items(s, n_items);
     TGT_STAMP(2);
 
-    // Phase 1 - every candidate pair (anchor of a window, figure) gets a thread.  Cells whose IoU exceeds
-    // rpn_max_overlap go to a hit list; which figure wins a cell is settled in phase 2, so the figure order of the
-    // reference ("first figure wins ties", utils.py:710-713) does not serialise anything.
+    // Phase 1 - two passes over the candidate pairs (anchor of a window, figure).  Pass A, every pair, float32 only:
+    // a cheap estimate of the IoU decides whether the exact value can matter at all; the pairs where it can are
+    // queued.  Pass B, dense over the queue: exact float64 IoU, the figure's best anchor, and for IoU above
+    // rpn_max_overlap a hit with its regression targets.  (One divergent pass costs every warp the float64 path
+    // on every step.)  Which figure wins an anchor is settled in phase 2, so the figure order of the reference
+    // ("first figure wins ties", utils.py:710-713) does not serialise anything.
     const int n_pairs = n_items ? s.pstart[n_items] : 0;
+    auto exact_pair = [&](int it, int t) {
+        const int a = it / G, g = it - a * G;
+        const int4 rg = s.range[it];
+        const int ww = rg.y - rg.x + 1;
+        const int dy = t / ww;
+        const int ix = rg.x + t - dy * ww, jy = rg.z + dy;
+        const double gx1 = s.gt[4 * g + 0], gx2 = s.gt[4 * g + 1], gy1 = s.gt[4 * g + 2], gy2 = s.gt[4 * g + 3];
+        const double2 X = s.ax[a * p.W + ix], Y = s.ay[a * p.H + jy];
+        const double iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
+        const float iou32 = (float)iou;                                       // float32 accumulator (utils.py:603)
+        if (iou32 > 0.f) {
+            // best anchor of this figure: max float32 IoU, then first in loop order size->ratio->ix->jy.  The
+            // 64-bit shared-memory max is a compare-and-swap loop: only candidates that beat the value seen go in.
+            const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order);
+            if (key > *reinterpret_cast<volatile unsigned long long *>(&s.best[g])) atomicMax(&s.best[g], key);
+        }
+        if (iou > p.max_overlap) {                                            // utils.py:704
+            atomicAdd(&s.hits[g], 1);
+            const int pos = atomicAdd(&s.ctl[2], 1);
+            if (pos < hit_cap) {
+                TargetHit h;
+                h.iou = iou; h.key = a * HW + jy * p.W + ix; h.g = g;
+                positive_values(p, a, jy * p.W + ix, s.gt + 4 * g, false, h.v);
+                s.hit[pos] = h;
+            }
+        }
+    };
     {
         const int per_thread = (n_pairs + kTgtThreads - 1) / kTgtThreads;
         int q = min((int)threadIdx.x * per_thread, n_pairs);
@@ -460,65 +497,59 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
             const float4 XF = s.axf[a * p.W + ix], YF = s.ayf[a * p.H + jy];
             // anchors crossing the image are skipped entirely (utils.py:629,638); a degenerate anchor has IoU 0
             if (XF.w == 0.f || YF.w == 0.f) continue;
-            const double gx1 = s.gt[4 * g + 0], gx2 = s.gt[4 * g + 1], gy1 = s.gt[4 * g + 2], gy2 = s.gt[4 * g + 3];
-            const double2 X = s.ax[a * p.W + ix], Y = s.ay[a * p.H + jy];
-            // IoU > 0  <=>  the open intervals meet on both axes (exact, float64 compares only)
-            if (!(gx2 > X.x && X.y > gx1 && gy2 > Y.x && Y.y > gy1)) continue;
-            // float32 estimate of the IoU: decides whether the exact float64 value can matter at all
             const float4 gf = s.gt32[g];
-            const float wi = fminf(gf.z, XF.y) - fmaxf(gf.x, XF.x);
-            const float hi32 = fminf(gf.w, YF.y) - fmaxf(gf.y, YF.x);
-            const float itf = fmaxf(wi, 0.f) * fmaxf(hi32, 0.f);
-            const float est = __fdividef(itf, s.area32[g] + XF.z * YF.z - itf);
-            const float lim = fminf(__uint_as_float(s.floor[g]), thr32);
-            const bool need = (est + kIouMargin >= lim) ||      // could be the best anchor, or exceed rpn_max_overlap
-                              (s.skip[g] & 2) || !(XF.z <= 8192.f && YF.z <= 8192.f);   // estimate not trusted: exact
-            if (!need) continue;
-            const double iou = ref_iou(gx1, gy1, gx2, gy2, X.x, Y.x, X.y, Y.y);
-            const float iou32 = (float)iou;                                       // float32 accumulator (utils.py:603)
-            if (iou32 > 0.f) {
-                // best anchor of this figure: max float32 IoU, then first in loop order size->ratio->ix->jy.  The
-                // 64-bit shared-memory max is a compare-and-swap loop: only candidates that beat the value seen go in.
-                const unsigned order = (unsigned)((a * p.W + ix) * p.H + jy);
-                const unsigned long long key = ((unsigned long long)__float_as_uint(iou32) << 32) | (0xFFFFFFFFu - order);
-                if (key > *reinterpret_cast<volatile unsigned long long *>(&s.best[g])) atomicMax(&s.best[g], key);
+            const bool trusted = !(s.skip[g] & 2) && XF.z <= 8192.f && YF.z <= 8192.f;
+            if (trusted) {
+                // float32 estimate of the IoU (error < 3e-4 at pixel scale, margin 2e-3): pairs that cannot be the
+                // figure's best anchor nor exceed rpn_max_overlap are dropped, including the disjoint ones (est = 0)
+                const float wi = fminf(gf.z, XF.y) - fmaxf(gf.x, XF.x);
+                const float hi32 = fminf(gf.w, YF.y) - fmaxf(gf.y, YF.x);
+                const float itf = fmaxf(wi, 0.f) * fmaxf(hi32, 0.f);
+                const float est = __fdividef(itf, s.area32[g] + XF.z * YF.z - itf);
+                const float lim = fminf(__uint_as_float(s.floor[g]), thr32);
+                if (!(est + kIouMargin >= lim)) continue;
             }
-            if (iou > p.max_overlap) {                                            // utils.py:704
-                atomicAdd(&s.hits[g], 1);
-                const int pos = atomicAdd(&s.ctl[2], 1);
-                if (pos < hit_cap) s.hit[pos] = TargetHit{iou, a * HW + jy * p.W + ix, g};
+            const int slot = atomicAdd(&s.ctl[9], 1);
+            if (slot < kNeedCap) s.need[slot] = q;
+            else exact_pair(it, t);                                           // queue full: resolve in place
+        }
+    }
+    __syncthreads();
+    {
+        const int n_need = min(s.ctl[9], kNeedCap);
+#pragma unroll 1
+        for (int e = threadIdx.x; e < n_need; e += kTgtThreads) {
+            const int q = s.need[e];
+            int it = 0;
+            for (int hi = n_items - 1; it < hi;) {
+                const int mid = (it + hi + 1) >> 1;
+                if (s.pstart[mid] <= q) it = mid; else hi = mid - 1;
             }
+            exact_pair(it, q - s.pstart[it]);
         }
     }
     __syncthreads();
     TGT_STAMP(3);
 
     // Phase 2 - settle every hit anchor: highest IoU wins, equal IoU -> the earlier figure (strict '>' in figure
-    // order, utils.py:710-713).  Open-addressing table keyed by the anchor; three passes.  The winners and their
-    // regression targets are parked in shared memory: once the panel is filled only stores are left.
+    // order, utils.py:710-713).  Open-addressing table keyed by the anchor; three passes; losers are flagged in
+    // place.  The hits carry their regression targets already: once the panel is filled only stores are left.
     const int n_hit = s.ctl[2];
     const bool replay = n_hit > hit_cap;
     if (!replay) {
         for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
-            const TargetHit h = s.hit[e];
-            uint32_t slot = hash_key((uint32_t)h.key) & hmask;
+            const int key = s.hit[e].key;
+            uint32_t slot = hash_key((uint32_t)key) & hmask;
             while (true) {
-                const uint32_t prev = atomicCAS(&s.tkey[slot], 0xFFFFFFFFu, (uint32_t)h.key);
-                if (prev == 0xFFFFFFFFu || prev == (uint32_t)h.key) break;
+                const uint32_t prev = atomicCAS(&s.tkey[slot], 0xFFFFFFFFu, (uint32_t)key);
+                if (prev == 0xFFFFFFFFu || prev == (uint32_t)key) break;
                 slot = (slot + 1) & hmask;
             }
-            atomicMax(&s.tmax[slot], (unsigned long long)__double_as_longlong(h.iou));   // positive doubles order like their bits
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
-            const TargetHit h = s.hit[e];
-            uint32_t slot = hash_key((uint32_t)h.key) & hmask;
-            while (s.tkey[slot] != (uint32_t)h.key) slot = (slot + 1) & hmask;
-            if ((unsigned long long)__double_as_longlong(h.iou) == s.tmax[slot]) atomicMin(&s.tg[slot], h.g);
+            atomicMax(&s.tmax[slot], (unsigned long long)__double_as_longlong(s.hit[e].iou));   // positive doubles order like their bits
         }
     }
     // forced positives + best_anchor table (utils.py:741-766): decode the best anchor of every figure
-    for (int g = threadIdx.x; g < p.Gmax; g += kTgtThreads) {
+    for (int g = kTgtThreads - 1 - (int)threadIdx.x; g < p.Gmax; g += kTgtThreads) {
         const unsigned long long key = g < G ? s.best[g] : 0ull;
         const int nh = g < G ? s.hits[g] : 0;
         unsigned order = 0xFFFFFFFFu;
@@ -539,19 +570,15 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     __syncthreads();
     if (!replay) {
         for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
-            const TargetHit h = s.hit[e];
-            uint32_t slot = hash_key((uint32_t)h.key) & hmask;
-            while (s.tkey[slot] != (uint32_t)h.key) slot = (slot + 1) & hmask;
-            if ((unsigned long long)__double_as_longlong(h.iou) == s.tmax[slot] && s.tg[slot] == h.g) {
-                const int a2 = h.key / HW, pos = atomicAdd(&s.ctl[3], 1);
-                s.wkey[pos] = h.key;
-                positive_values(p, a2, h.key - a2 * HW, s.gt + 4 * h.g, false, s.wv + 4 * pos);
-            }
+            const int key = s.hit[e].key;
+            uint32_t slot = hash_key((uint32_t)key) & hmask;
+            while (s.tkey[slot] != (uint32_t)key) slot = (slot + 1) & hmask;
+            if ((unsigned long long)__double_as_longlong(s.hit[e].iou) == s.tmax[slot]) atomicMin(&s.tg[slot], s.hit[e].g);
         }
     }
     // The reference applies the forced positives in GT order, so when several GT share the same best anchor the
     // LAST one wins: a figure is only kept if no later forced figure targets its anchor.  (Threads are taken from
-    // the top so that this float64 work runs next to the winners' above, not after it.)
+    // the top so that this float64 work runs next to the table passes, not after them.)
     for (int g = kTgtThreads - 1 - (int)threadIdx.x; g < G; g += kTgtThreads) {
         const unsigned o = s.order[g];
         if (o == 0xFFFFFFFFu) continue;
@@ -562,9 +589,19 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
         const unsigned rest = o / (unsigned)p.H;
         const int ix = (int)(rest % (unsigned)p.W);
         const int a2 = (int)(rest / (unsigned)p.W);
-        const int pos = hit_cap + atomicAdd(&s.ctl[4], 1);
+        const int pos = atomicAdd(&s.ctl[4], 1);
         s.wkey[pos] = a2 * HW + jy * p.W + ix;
         positive_values(p, a2, jy * p.W + ix, s.gt + 4 * g, true, s.wv + 4 * pos);
+    }
+    __syncthreads();
+    if (!replay) {
+        for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
+            const int key = s.hit[e].key, g = s.hit[e].g;
+            uint32_t slot = hash_key((uint32_t)key) & hmask;
+            while (s.tkey[slot] != (uint32_t)key) slot = (slot + 1) & hmask;
+            const bool win = (unsigned long long)__double_as_longlong(s.hit[e].iou) == s.tmax[slot] && s.tg[slot] == g;
+            if (!win) s.hit[e].g = -1 - g;
+        }
     }
     TGT_STAMP(4);
 
@@ -595,11 +632,14 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     TGT_STAMP(5);
 
     // regular positives (utils.py:728-738)
-    const int n_win = s.ctl[3];
+    int n_win = 0;
     if (!replay) {
-        for (int e = threadIdx.x; e < n_win; e += kTgtThreads) {
-            const int key = s.wkey[e], a2 = key / HW;
-            store_positive(p, cls_b, regr_b, a2, key - a2 * HW, s.wv + 4 * e, false);
+        for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
+            const TargetHit &h = s.hit[e];
+            if (h.g < 0) continue;
+            const int a2 = h.key / HW;
+            store_positive(p, cls_b, regr_b, a2, h.key - a2 * HW, h.v, false);
+            ++n_win;
         }
     } else {
         // more positives than the list holds (never seen in practice): shape by shape, figure by figure with
@@ -640,8 +680,8 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     __syncthreads();                                                          // regular before forced writes
     const int n_forced = s.ctl[4];
     for (int e = threadIdx.x; e < n_forced; e += kTgtThreads) {
-        const int key = s.wkey[hit_cap + e], a2 = key / HW;
-        store_positive(p, cls_b, regr_b, a2, key - a2 * HW, s.wv + 4 * (hit_cap + e), true);
+        const int key = s.wkey[e], a2 = key / HW;
+        store_positive(p, cls_b, regr_b, a2, key - a2 * HW, s.wv + 4 * e, true);
     }
 #ifdef RADNET_TGT_PROFILE
     if (p.stamps && threadIdx.x == 0) {
@@ -732,7 +772,7 @@ TgtSmemLayout tgt_smem_layout(int Gmax, int H, int W, int A, int hit_cap) {
     if (hits_bytes + hash_bytes < 12 * HW + 16) hits_bytes = align_up(12 * HW + 16 - hash_bytes, 16);
     l.off_hash = off + hits_bytes;
     l.off_win = l.off_hash + hash_bytes;
-    l.total = l.off_win + ((size_t)hit_cap + gm) * (4 * sizeof(double) + sizeof(int)) + 16;
+    l.total = l.off_win + gm * (4 * sizeof(double) + sizeof(int)) + (size_t)kNeedCap * sizeof(int) + 16;
     return l;
 }
 int tgt_groups(int B) { return (B + kGroupPanels - 1) / kGroupPanels; }

@@ -116,3 +116,81 @@ class TiledPanelSharder:
     def finish(self, gathered, work):
         work.wait()
         return gathered_to_global(gathered, self.n_tiles)
+
+
+class OwnerRoutedTiles:
+    """Tiles of tiled panels with the merge sharded too: tile g = p*T + t is processed on rank g % world
+    (as `TiledPanelSharder`), and the tile records of panel p are routed to ONE rank, its owner p % world,
+    which alone runs the merge (K7 final_nms + per-class NMS) for that panel.  Per rank the exchange moves
+    only its own tiles' records (one `all_to_all_single` with per-destination split sizes over NVLink) and
+    the merge work is n_panels / world panels - the all-gather-to-everyone of `TiledPanelSharder` costs
+    world times the bytes and merges every panel on every rank.  `gather_final` then collects the final
+    records (one per panel) on every rank in global panel order.
+
+    The schedule (who sends which slots to whom, in which order they arrive) is a pure function of
+    (n_panels, T, world) and is built once on the host.  world == 1 needs no process group."""
+
+    def __init__(self, n_panels, tiles_per_panel, rank=None, world=None, group=None, device=None):
+        self.group = group
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rank, self.world = int(rank), int(world)
+        self.n_panels, self.T = int(n_panels), int(tiles_per_panel)
+        self.n_tiles = self.n_panels * self.T
+        self.local_ids = shard_indices(self.n_tiles, self.rank, self.world)
+        self.owned = shard_indices(self.n_panels, self.rank, self.world)          # panels merged here
+        self.max_owned = max(shard_sizes(self.n_panels, self.world))
+        T, w = self.T, self.world
+        # send side: my slots ordered by (destination, global tile id)
+        dest = (self.local_ids // T) % w
+        send_perm = np.argsort(dest, kind="stable")
+        self.in_splits = [int((dest == d).sum()) for d in range(w)]
+        # receive side: from source s arrive, ascending, the tiles g with g % w == s whose panel I own
+        recv_ids = []
+        self.out_splits = []
+        for s in range(w):
+            ids = shard_indices(self.n_tiles, s, w)
+            mine = ids[(ids // T) % w == self.rank]
+            recv_ids.append(mine)
+            self.out_splits.append(len(mine))
+        recv_ids = np.concatenate(recv_ids) if recv_ids else np.zeros((0,), dtype=np.int64)
+        assert len(recv_ids) == len(self.owned) * T
+        # position of every arrived record in (owned panel, tile) order
+        key = (recv_ids // T // w) * T + recv_ids % T
+        to_panel_order = np.argsort(key, kind="stable")
+        self._send_perm = torch.from_numpy(send_perm.astype(np.int64))
+        self._to_panel_order = torch.from_numpy(to_panel_order.astype(np.int64))
+        self._final_order = torch.from_numpy(global_order(self.n_panels, w, self.max_owned))
+        if device is not None:
+            self.to(device)
+
+    def to(self, device):
+        self._send_perm = self._send_perm.to(device)
+        self._to_panel_order = self._to_panel_order.to(device)
+        self._final_order = self._final_order.to(device)
+        return self
+
+    def exchange(self, tile_records):
+        """tile_records: (len(local_ids), stride) uint8, the records of this rank's tiles in local slot order.
+        Returns (len(owned) * T, stride): the tile records of the panels this rank owns, in (panel, tile)
+        order - the input layout of `DetectionPipeline.merge`."""
+        if self.world == 1:
+            return tile_records
+        send = tile_records.index_select(0, self._send_perm)
+        recv = torch.empty((sum(self.out_splits), tile_records.shape[1]), dtype=tile_records.dtype,
+                           device=tile_records.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=self.out_splits, input_split_sizes=self.in_splits,
+                               group=self.group)
+        return recv.index_select(0, self._to_panel_order)
+
+    def gather_final(self, final_records):
+        """final_records: (len(owned), stride) uint8, one merged record per owned panel, ascending panel id.
+        Returns (n_panels, stride) in global panel order on every rank (one all-gather of max_owned records)."""
+        if self.world == 1:
+            return final_records
+        pad = self.max_owned - int(final_records.shape[0])
+        if pad:
+            final_records = torch.cat([final_records, final_records.new_zeros((pad, final_records.shape[1]))])
+        gathered, _ = gather_detections(final_records, group=self.group)
+        return gathered.reshape(self.world * self.max_owned, -1).index_select(0, self._final_order)

@@ -99,3 +99,51 @@ def test_tiled_panel_sharder_world2_gloo(tmp_path, n_panels, tiles_per_panel):
     mp.spawn(_tile_worker, args=(2, port, n_panels, tiles_per_panel, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert np.load(tmp_path / ("tile_ok_%d.npy" % r))[0] == 1
+
+
+def _owner_worker(rank, world, port, n_panels, T, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rock_art_radnet_b200 import sharding
+    router = sharding.OwnerRoutedTiles(n_panels, T)
+    stride = 32
+    raw = torch.zeros((len(router.local_ids), stride), dtype=torch.uint8)
+    for slot, g in enumerate(router.local_ids):
+        raw[slot, 0] = int(g) // T            # panel
+        raw[slot, 1] = int(g) % T             # tile
+        raw[slot, 2] = rank
+    got = router.exchange(raw)
+    ok = tuple(got.shape) == (len(router.owned) * T, stride)
+    want = [(int(p), t) for p in router.owned for t in range(T)]
+    ok &= [(int(r[0]), int(r[1])) for r in got] == want                     # (owned panel, tile) order
+    ok &= all(int(r[2]) == (int(r[0]) * T + int(r[1])) % world for r in got)   # each came from the rank that held it
+    final = torch.zeros((len(router.owned), stride), dtype=torch.uint8)
+    for i, p in enumerate(router.owned):
+        final[i, 0] = int(p)
+        final[i, 1] = 100 + rank
+    glob = router.gather_final(final)
+    ok &= tuple(glob.shape) == (n_panels, stride) and glob[:, 0].tolist() == list(range(n_panels))
+    ok &= glob[:, 1].tolist() == [100 + p % world for p in range(n_panels)]
+    np.save(os.path.join(out_dir, "owner_ok_%d.npy" % rank), np.array([int(ok)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_panels,T", [(2, 1, 36), (2, 5, 7), (3, 4, 36), (4, 3, 5)])
+def test_owner_routed_tiles_gloo(tmp_path, world, n_panels, T):
+    """Owner routing of the tile merge: every tile record reaches exactly the rank that owns its panel
+    (p % world), in (panel, tile) order; final records come back in global panel order.  Uneven splits,
+    ranks that own no panel, more ranks than panels."""
+    port = _free_port()
+    mp.spawn(_owner_worker, args=(world, port, n_panels, T, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert np.load(tmp_path / ("owner_ok_%d.npy" % r))[0] == 1
+
+
+def test_owner_routing_without_process_group_is_identity():
+    from rock_art_radnet_b200 import sharding
+    router = sharding.OwnerRoutedTiles(2, 5, rank=0, world=1)
+    raw = torch.arange(10 * 8, dtype=torch.uint8).reshape(10, 8)
+    assert torch.equal(router.exchange(raw), raw) and torch.equal(router.gather_final(raw[:2]), raw[:2])

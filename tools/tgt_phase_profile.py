@@ -58,3 +58,23 @@ for it in range(4):
     comp = st[st[:, 6] > 0]
     for k, nm in ((10, "pairs"), (11, "hits"), (12, "winners"), (13, "forced")):
         print("   per panel %-8s min %5d  median %5d  max %5d" % (nm, comp[:, k].min(), np.median(comp[:, k]), comp[:, k].max()))
+
+# ---- steady state: back-to-back launches over rotating output sets (4 x 66.6 MB at B = 64: larger than L2) ----
+n_sets = max(2, int(np.ceil(260e6 / (B * 1040320.0))) + 1)
+sets = [RpnTargetBatch(C, B, G, H, W) for _ in range(n_sets)]
+for lay, name in ((0, "channel-first"), (1, "nhwc x std_scaling")):
+    sets = [RpnTargetBatch(C, B, G, H, W, layout=lay, regr_scale=4.0 if lay else 1.0) for _ in range(n_sets)]
+    for tb_ in sets:
+        tb_.run(gt_d, bg_d, cnt_d, wh_d)
+    torch.cuda.synchronize()
+    reps = 40
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(reps):
+        sets[i % n_sets].run(gt_d, bg_d, cnt_d, wh_d)
+    e.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(e) * 1e3 / reps
+    print("stream of %d launches over %d output sets (%s): %.1f us per launch = %.0f GB/s" % (
+        reps, n_sets, name, us, B * 1040320.0 / us / 1e3))
+    del sets

@@ -329,10 +329,10 @@ int radnet_real_coordinates(const int32_t *v, long long n, double ratio, int32_t
 /* ------------------------------------------------ bench / test utility: synthetic panels on the device
  * BASELINE configs[4] (the 10,000 panels of the archive sweep are generated on the
  * device from their seed).  Counter-based: every value is a hash of (seed, panel id, tensor, element), so panel
- * first_panel+b is the same bytes wherever and in whatever batch it is generated.
+ * first_panel + b*panel_stride is the same bytes wherever and in whatever batch it is generated.
  *   cls [B][H][W][A] uniform scores in (0,1); regr [B][H][W][4A] 0.5*N(0,1); feat [B][H][W][C] N(0,1). */
-int radnet_synth_panels(unsigned long long seed, long long first_panel, int B, int H, int W, int A, int C,
-                        float *cls, float *regr, float *feat, void *stream);
+int radnet_synth_panels(unsigned long long seed, long long first_panel, long long panel_stride, int B,
+                        int H, int W, int A, int C, float *cls, float *regr, float *feat, void *stream);
 
 #ifdef __cplusplus
 }

@@ -59,8 +59,8 @@ SIGNATURES = {
                                      c_void_p, c_size_t, c_void_p]),
     "radnet_select_samples": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
-    "radnet_synth_panels": (c_int, [ctypes.c_ulonglong, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                    c_void_p, c_void_p, c_void_p]),
+    "radnet_synth_panels": (c_int, [ctypes.c_ulonglong, c_longlong, c_longlong, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "radnet_iou_pairs": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     "radnet_real_coordinates": (c_int, [c_void_p, c_longlong, c_double, c_void_p, c_void_p]),
     "radnet_cls_record_bytes": (c_size_t, [c_int]),

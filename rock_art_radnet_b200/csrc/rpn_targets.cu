@@ -35,7 +35,6 @@
 
 namespace radnet {
 
-constexpr int kTgtThreads = 512;
 constexpr int kUnitsPerPanel = 16;
 constexpr int kGroupPanels = 64;          // fill completion is published and awaited per group of panels
 
@@ -162,7 +161,7 @@ struct TgtShared {
     int *ctl;                   // static: 0 pulled index, 1 ready flag, 2 hits, 3 winners, 4 forced, 5 scan carry,
                                 //         6 prefetched fill unit, 7 group of the unpublished items, 8 their count,
                                 //         9 queued pairs
-    int *warp;                  // static [17] scan scratch
+    int *warp;                  // static [33] scan scratch
 };
 
 __device__ __forceinline__ TgtShared carve(const RpnTargetParams &p, unsigned char *smem, int *s_ctl, int *s_warp) {
@@ -208,6 +207,7 @@ __device__ __forceinline__ void publish_fill(const RpnTargetParams &p, const Tgt
 
 // ---- fill.  Both tensors of a panel are seen as ONE array of 5*A*H*W double2 items (label tensor first, then the
 //      regression tensor); unit u = sixteenth (u % 16) of panel u / 16. ---------------------------------------
+template <int NT>
 __device__ void fill_unit(const RpnTargetParams &p, const TgtShared &s, int unit) {
     const int b = unit / kUnitsPerPanel, q = unit - b * kUnitsPerPanel;
     const int HW = p.H * p.W, AHW = p.A * HW;
@@ -220,14 +220,14 @@ __device__ void fill_unit(const RpnTargetParams &p, const TgtShared &s, int unit
         const double2 z = make_double2(0.0, 0.0);
         const int r_lo = max(lo, AHW) - AHW, r_hi = hi - AHW;
 #pragma unroll 4
-        for (int i = r_lo + threadIdx.x; i < r_hi; i += kTgtThreads) regr2[i] = z;
+        for (int i = r_lo + threadIdx.x; i < r_hi; i += NT) regr2[i] = z;
     }
     if (lo < AHW) {
         // label tensor: [valid | overlap]; valid = anchor inside the image on both axes (utils.py:629, 638), and
         // labels are only ever written inside the GT loop: no GT, no labels (utils.py:722-738)
         const int G = min(max(p.gt_count[b], 0), p.Gmax);
         const double img_w = p.img_wh[2 * b], img_h = p.img_wh[2 * b + 1];
-        for (int i = threadIdx.x; i < p.A * (p.W + p.H); i += kTgtThreads) {
+        for (int i = threadIdx.x; i < p.A * (p.W + p.H); i += NT) {
             const int c = i / (p.W + p.H), r = i - c * (p.W + p.H);
             const bool isx = r < p.W;
             const int k = isx ? r : r - p.W;
@@ -239,7 +239,7 @@ __device__ void fill_unit(const RpnTargetParams &p, const TgtShared &s, int unit
         }
         __syncthreads();
         const int twoA = 2 * p.A, top = min(hi, AHW);
-        for (int i = lo + threadIdx.x; i < top; i += kTgtThreads) {
+        for (int i = lo + threadIdx.x; i < top; i += NT) {
             double v[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -271,6 +271,7 @@ __device__ void fill_unit(const RpnTargetParams &p, const TgtShared &s, int unit
 // next fill unit from the shared counter; false when none is left.  The index of the unit after this one is
 // requested before the stores of this one are issued (s.ctl[6] holds a prefetched index, -1 = none), so the
 // round trip of the atomic is hidden behind the store stream.
+template <int NT>
 __device__ bool pull_fill(const RpnTargetParams &p, const TgtShared &s) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -285,16 +286,17 @@ __device__ bool pull_fill(const RpnTargetParams &p, const TgtShared &s) {
     }
     int next = -1;
     if (threadIdx.x == 0) next = atomicAdd(&p.ctl[0], 1);        // consumed after the stores below
-    fill_unit(p, s, u);
+    fill_unit<NT>(p, s, u);
     if (threadIdx.x == 0) s.ctl[6] = next;
     return true;
 }
 
 // CTA-wide exclusive scan of the item sizes in s.pstart[1..n] (in place: pstart[i] = first pair of item i)
+template <int NT>
 __device__ void scan_items(const TgtShared &s, int n) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) { s.ctl[5] = 0; s.pstart[0] = 0; }
-    for (int i0 = 0; i0 < n; i0 += kTgtThreads) {                 // block-uniform
+    for (int i0 = 0; i0 < n; i0 += NT) {                 // block-uniform
         const int i = i0 + threadIdx.x;
         const int v = i < n ? s.pstart[i + 1] : 0;
         int inc = v;
@@ -307,26 +309,27 @@ __device__ void scan_items(const TgtShared &s, int n) {
         if (lane == 31) s.warp[w] = inc;
         __syncthreads();
         if (w == 0) {
-            const int x = lane < kTgtThreads / 32 ? s.warp[lane] : 0;
+            const int x = lane < NT / 32 ? s.warp[lane] : 0;       // NT / 32 <= 32 warps
             int xi = x;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, xi, d);
                 if (lane >= d) xi += t;
             }
-            if (lane < kTgtThreads / 32) s.warp[lane] = xi - x;
-            if (lane == 31) s.warp[16] = xi;
+            if (lane < NT / 32) s.warp[lane] = xi - x;
+            if (lane == 31) s.warp[32] = xi;
         }
         __syncthreads();
         const int carry = s.ctl[5];
         if (i < n) s.pstart[i + 1] = carry + s.warp[w] + inc;
         __syncthreads();
-        if (threadIdx.x == 0) s.ctl[5] = carry + s.warp[16];
+        if (threadIdx.x == 0) s.ctl[5] = carry + s.warp[32];
     }
     __syncthreads();
 }
 
 // ---- one panel --------------------------------------------------------------------------------------------------
+template <int NT>
 __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     const int HW = p.H * p.W, AHW = p.A * HW;
     const int hit_cap = p.hit_cap;
@@ -337,7 +340,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     const int G = min(max(p.gt_count[b], 0), p.Gmax);
     const double img_w = p.img_wh[2 * b], img_h = p.img_wh[2 * b + 1];
     __syncthreads();                                      // previous work of this CTA fully consumed
-    for (int i = threadIdx.x; i < p.Gmax; i += kTgtThreads) {
+    for (int i = threadIdx.x; i < p.Gmax; i += NT) {
         const double2 *q = reinterpret_cast<const double2 *>(p.gt + ((size_t)b * p.Gmax + i) * 4);
         const double2 qx = q[0], qy = q[1];
         const uint8_t isbg = p.gt_is_bg[(size_t)b * p.Gmax + i];
@@ -355,8 +358,8 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
             !(fabs(x1) <= 8192.0 && fabs(x2) <= 8192.0 && fabs(y1) <= 8192.0 && fabs(y2) <= 8192.0)) f |= 2;
         s.skip[i] = f;
     }
-    for (int i = threadIdx.x; i < 4 * p.A; i += kTgtThreads) s.use[i] = (i & 1) ? -1 : ((i & 2) ? p.H : p.W);
-    for (int i = threadIdx.x; i < p.hash_slots; i += kTgtThreads) {
+    for (int i = threadIdx.x; i < 4 * p.A; i += NT) s.use[i] = (i & 1) ? -1 : ((i & 2) ? p.H : p.W);
+    for (int i = threadIdx.x; i < p.hash_slots; i += NT) {
         s.tkey[i] = 0xFFFFFFFFu;
         s.tmax[i] = 0ull;
         s.tg[i] = 0x7fffffff;
@@ -366,7 +369,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     // A LOWER bound of every figure's best float32 IoU, from the exact IoU with the A anchors of the cell under
     // the figure's centre.  Pairs whose float32 estimate is below it by more than the margin cannot be (or tie
     // with) the best anchor.
-    for (int i = threadIdx.x; i < G * p.A; i += kTgtThreads) {
+    for (int i = threadIdx.x; i < G * p.A; i += NT) {
         const int g = i / p.A, a2 = i - g * p.A;
         if (s.skip[g] & 1) continue;
         const double gx1 = s.gt[4 * g + 0], gx2 = s.gt[4 * g + 1], gy1 = s.gt[4 * g + 2], gy2 = s.gt[4 * g + 3];
@@ -382,7 +385,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     }
     // anchor coordinates per shape and column / row (utils.py:625-626, 635-636) and the per-axis in-image tests
     // (utils.py:629, 638); an anchor is used when both its column and its row pass
-    for (int i = threadIdx.x; i < p.A * (p.W + p.H); i += kTgtThreads) {
+    for (int i = threadIdx.x; i < p.A * (p.W + p.H); i += NT) {
         const int a = i / (p.W + p.H), r = i - a * (p.W + p.H);
         const bool isx = r < p.W;
         const int k = isx ? r : r - p.W;
@@ -408,7 +411,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     // side); with L = min(floor, thr) - margin this is a handful of cells around the figure.  The window is empty
     // when the two shapes cannot reach L at all (IoU <= smaller-overlap-box / union), and it is clipped to the
     // in-image rectangle of the shape.  One cell of padding absorbs the rounding of this float64 arithmetic.
-    for (int it = threadIdx.x; it < n_items; it += kTgtThreads) {
+    for (int it = threadIdx.x; it < n_items; it += NT) {
         const int a = it / G, g = it - a * G;
         const double aw = p.anchors.wh[a][0], ah = p.anchors.wh[a][1];
         const int *use = s.use + 4 * a;
@@ -436,7 +439,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
         s.pstart[it + 1] = (r.x > r.y || r.z > r.w) ? 0 : (r.y - r.x + 1) * (r.w - r.z + 1);
     }
     __syncthreads();
-    scan_items(s, n_items);
+    scan_items<NT>(s, n_items);
     TGT_STAMP(2);
 
     // Phase 1 - two passes over the candidate pairs (anchor of a window, figure).  Pass A, every pair, float32 only:
@@ -475,7 +478,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
         }
     };
     {
-        const int per_thread = (n_pairs + kTgtThreads - 1) / kTgtThreads;
+        const int per_thread = (n_pairs + NT - 1) / NT;
         int q = min((int)threadIdx.x * per_thread, n_pairs);
         const int q_end = min(q + per_thread, n_pairs);
         int it = 0;                                                           // last item with pstart[it] <= q
@@ -518,7 +521,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     {
         const int n_need = min(s.ctl[9], kNeedCap);
 #pragma unroll 1
-        for (int e = threadIdx.x; e < n_need; e += kTgtThreads) {
+        for (int e = threadIdx.x; e < n_need; e += NT) {
             const int q = s.need[e];
             int it = 0;
             for (int hi = n_items - 1; it < hi;) {
@@ -537,7 +540,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     const int n_hit = s.ctl[2];
     const bool replay = n_hit > hit_cap;
     if (!replay) {
-        for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
+        for (int e = threadIdx.x; e < n_hit; e += NT) {
             const int key = s.hit[e].key;
             uint32_t slot = hash_key((uint32_t)key) & hmask;
             while (true) {
@@ -549,7 +552,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
         }
     }
     // forced positives + best_anchor table (utils.py:741-766): decode the best anchor of every figure
-    for (int g = kTgtThreads - 1 - (int)threadIdx.x; g < p.Gmax; g += kTgtThreads) {
+    for (int g = NT - 1 - (int)threadIdx.x; g < p.Gmax; g += NT) {
         const unsigned long long key = g < G ? s.best[g] : 0ull;
         const int nh = g < G ? s.hits[g] : 0;
         unsigned order = 0xFFFFFFFFu;
@@ -569,7 +572,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     }
     __syncthreads();
     if (!replay) {
-        for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
+        for (int e = threadIdx.x; e < n_hit; e += NT) {
             const int key = s.hit[e].key;
             uint32_t slot = hash_key((uint32_t)key) & hmask;
             while (s.tkey[slot] != (uint32_t)key) slot = (slot + 1) & hmask;
@@ -579,7 +582,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     // The reference applies the forced positives in GT order, so when several GT share the same best anchor the
     // LAST one wins: a figure is only kept if no later forced figure targets its anchor.  (Threads are taken from
     // the top so that this float64 work runs next to the table passes, not after them.)
-    for (int g = kTgtThreads - 1 - (int)threadIdx.x; g < G; g += kTgtThreads) {
+    for (int g = NT - 1 - (int)threadIdx.x; g < G; g += NT) {
         const unsigned o = s.order[g];
         if (o == 0xFFFFFFFFu) continue;
         bool last = true;
@@ -595,7 +598,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     }
     __syncthreads();
     if (!replay) {
-        for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
+        for (int e = threadIdx.x; e < n_hit; e += NT) {
             const int key = s.hit[e].key, g = s.hit[e].g;
             uint32_t slot = hash_key((uint32_t)key) & hmask;
             while (s.tkey[slot] != (uint32_t)key) slot = (slot + 1) & hmask;
@@ -622,10 +625,10 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
             __syncthreads();
             if (s.ctl[1]) break;
             // the parked positives live in wv / wkey / ctl[3..4]; a fill unit only touches the in-image tables
-            if (more) more = pull_fill(p, s);
+            if (more) more = pull_fill<NT>(p, s);
         }
         if (s.ctl[1] == 2)         // the fill never completed (4 s): results invalid, reported through n_hits
-            for (int g = threadIdx.x; g < p.Gmax; g += kTgtThreads) p.n_hits[(size_t)b * p.Gmax + g] = -1;
+            for (int g = threadIdx.x; g < p.Gmax; g += NT) p.n_hits[(size_t)b * p.Gmax + g] = -1;
     } else {
         __syncthreads();
     }
@@ -634,7 +637,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     // regular positives (utils.py:728-738)
     int n_win = 0;
     if (!replay) {
-        for (int e = threadIdx.x; e < n_hit; e += kTgtThreads) {
+        for (int e = threadIdx.x; e < n_hit; e += NT) {
             const TargetHit &h = s.hit[e];
             if (h.g < 0) continue;
             const int a2 = h.key / HW;
@@ -649,7 +652,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
 #pragma unroll 1
         for (int a = 0; a < p.A; ++a) {
             __syncthreads();
-            for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) { s_lb[cell] = 0.0; s_lg[cell] = -1; }
+            for (int cell = threadIdx.x; cell < HW; cell += NT) { s_lb[cell] = 0.0; s_lg[cell] = -1; }
             __syncthreads();
 #pragma unroll 1
             for (int g = 0; g < G; ++g) {
@@ -657,7 +660,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
                 if (rg.x > rg.y || rg.z > rg.w) continue;                     // block-uniform
                 const int ww = rg.y - rg.x + 1, n = ww * (rg.w - rg.z + 1);
                 const double gx1 = s.gt[4 * g + 0], gx2 = s.gt[4 * g + 1], gy1 = s.gt[4 * g + 2], gy2 = s.gt[4 * g + 3];
-                for (int t = threadIdx.x; t < n; t += kTgtThreads) {
+                for (int t = threadIdx.x; t < n; t += NT) {
                     const int dy = t / ww, ix = rg.x + t - dy * ww, jy = rg.z + dy;
                     if (s.axf[a * p.W + ix].w == 0.f || s.ayf[a * p.H + jy].w == 0.f) continue;
                     const double2 X = s.ax[a * p.W + ix], Y = s.ay[a * p.H + jy];
@@ -667,7 +670,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
                 }
                 __syncthreads();
             }
-            for (int cell = threadIdx.x; cell < HW; cell += kTgtThreads) {
+            for (int cell = threadIdx.x; cell < HW; cell += NT) {
                 const int lg = s_lg[cell];
                 if (lg >= 0) {
                     double v[4];
@@ -679,7 +682,7 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
     }
     __syncthreads();                                                          // regular before forced writes
     const int n_forced = s.ctl[4];
-    for (int e = threadIdx.x; e < n_forced; e += kTgtThreads) {
+    for (int e = threadIdx.x; e < n_forced; e += NT) {
         const int key = s.wkey[e], a2 = key / HW;
         store_positive(p, cls_b, regr_b, a2, key - a2 * HW, s.wv + 4 * e, true);
     }
@@ -695,38 +698,40 @@ __device__ void do_panel(const RpnTargetParams &p, const TgtShared &s, int b) {
 }
 
 // next panel from the shared counter; false when none is left
+template <int NT>
 __device__ bool pull_panel(const RpnTargetParams &p, const TgtShared &s) {
     __syncthreads();
     if (threadIdx.x == 0) s.ctl[0] = atomicAdd(&p.ctl[1], 1);
     __syncthreads();
     const int b = s.ctl[0];
     if (b >= p.B) return false;
-    do_panel(p, s, b);
+    do_panel<NT>(p, s, b);
     return true;
 }
 
-__global__ void __launch_bounds__(kTgtThreads, 2) rpn_targets_kernel(RpnTargetParams p) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 2048 / NT / 2) rpn_targets_kernel(RpnTargetParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ctl[12];
-    __shared__ int s_warp[17];
+    __shared__ int s_warp[34];
     const TgtShared s = carve(p, smem, s_ctl, s_warp);
     if (threadIdx.x == 0) { s_ctl[6] = -1; s_ctl[7] = -1; s_ctl[8] = 0; }
 #ifdef RADNET_TGT_PROFILE
     if (p.stamps && threadIdx.x == 0) p.stamps[(size_t)blockIdx.x * 16 + 8] = global_ns();
 #endif
     if (p.role == 1) {
-        while (pull_fill(p, s)) {}
+        while (pull_fill<NT>(p, s)) {}
     } else if (p.role == 2) {
-        while (pull_panel(p, s)) {}
+        while (pull_panel<NT>(p, s)) {}
     } else if (((long long)sm_id() * p.n_compute_sm) % p.n_sm < p.n_compute_sm) {     // n_compute_sm SMs, evenly spread
-        while (pull_panel(p, s)) {}
-        while (pull_fill(p, s)) {}
+        while (pull_panel<NT>(p, s)) {}
+        while (pull_fill<NT>(p, s)) {}
     } else {
-        while (pull_fill(p, s)) {}
+        while (pull_fill<NT>(p, s)) {}
 #ifdef RADNET_TGT_PROFILE
         if (p.stamps && threadIdx.x == 0) p.stamps[(size_t)blockIdx.x * 16 + 9] = global_ns();
 #endif
-        while (pull_panel(p, s)) {}
+        while (pull_panel<NT>(p, s)) {}
     }
     // ---- the last CTA out resets the launch-wide counters ----------------------------------------------------
     __syncthreads();
@@ -856,30 +861,38 @@ extern "C" int radnet_rpn_targets(const double *gt, const uint8_t *gt_is_bg, con
     p.stamps = g_tgt_stamps;
 #endif
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(rpn_targets_kernel), dev, sl.total)) return rc;
-    // two CTAs per SM when the shared memory allows it (it does for the 600-px shapes), else one
-    const int per_sm = 2 * (sl.total + 1024) <= (size_t)smem_limit + 1024 ? 2 : 1;
+    // Two launch shapes.  Few panels (one round of at most ~43 % of the SMs): one CTA of 1024 threads per SM, so
+    // that a panel has a whole SM's issue slots and the round is short.  Many panels: two CTAs of 512 threads per
+    // SM - two panels per computing SM hide each other's latencies and more SMs are left for the fill.
+    const bool two_per_sm = 2 * (sl.total + 1024) <= (size_t)smem_limit + 1024;
+    long long n_comp_sm = get_option(kOptTargetsComputeCtas);
+    const bool wide = !two_per_sm || (n_comp_sm < 1 && B <= (n_sm * 43 + 99) / 100);
+    const int per_sm = wide ? 1 : 2;
+    if (n_comp_sm < 1) n_comp_sm = wide ? (n_sm * 43 + 99) / 100 : (n_sm * 22 + 99) / 100;
+    if (n_comp_sm > (B + per_sm - 1) / per_sm) n_comp_sm = (B + per_sm - 1) / per_sm;
+    if (n_comp_sm > n_sm - 1) n_comp_sm = n_sm > 1 ? n_sm - 1 : 1;
+    p.n_compute_sm = (int)n_comp_sm;
+    p.n_sm = n_sm;
     const long long n_units = (long long)B * kUnitsPerPanel;
     long long grid = (long long)n_sm * per_sm;
     if (grid > n_units + B) grid = n_units + B;
+    auto launch = [&](unsigned g) -> int {
+        if (wide) {
+            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(rpn_targets_kernel<1024>), dev, sl.total)) return rc;
+            rpn_targets_kernel<1024><<<g, 1024, sl.total, st>>>(p);
+        } else {
+            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(rpn_targets_kernel<512>), dev, sl.total)) return rc;
+            rpn_targets_kernel<512><<<g, 512, sl.total, st>>>(p);
+        }
+        return check_launch("rpn_targets_kernel");
+    };
     if (get_option(kOptTargetsTwoLaunches) == 1) {
         // no co-residency assumed: the fill as its own launch, then the panels (stream order replaces the wait)
         p.role = 1;
-        rpn_targets_kernel<<<(unsigned)(grid < n_units ? grid : n_units), kTgtThreads, sl.total, st>>>(p);
-        if (int rc = check_launch("rpn_targets_kernel (fill)")) return rc;
+        if (int rc = launch((unsigned)(grid < n_units ? grid : n_units))) return rc;
         p.role = 2;
-        rpn_targets_kernel<<<(unsigned)(grid < B ? grid : B), kTgtThreads, sl.total, st>>>(p);
-        return check_launch("rpn_targets_kernel (panels)");
+        return launch((unsigned)(grid < B ? grid : B));
     }
-    // SMs that take panels first: enough for one round of the panels at `per_sm` panels per SM, at most 22 % of
-    // the SMs (the bare fill needs >= 110 of the 148 SMs storing to reach its burst rate)
-    long long n_comp_sm = get_option(kOptTargetsComputeCtas);
-    if (n_comp_sm < 1) n_comp_sm = (n_sm * 22 + 99) / 100;
-    if (n_comp_sm > (B + per_sm - 1) / per_sm) n_comp_sm = (B + per_sm - 1) / per_sm;
-    if (n_comp_sm > n_sm - 1) n_comp_sm = n_sm > 1 ? n_sm - 1 : 1;
     p.role = 0;
-    p.n_compute_sm = (int)n_comp_sm;
-    p.n_sm = n_sm;
-    rpn_targets_kernel<<<(unsigned)grid, kTgtThreads, sl.total, st>>>(p);
-    return check_launch("rpn_targets_kernel");
+    return launch((unsigned)grid);
 }

@@ -29,7 +29,7 @@ __device__ __forceinline__ float2 normal2(uint64_t h) {
 
 struct SynthParams {
     uint64_t seed;
-    long long first_panel;
+    long long first_panel, panel_stride;
     int B;
     long long n_cls, n_regr, n_feat;       // elements per panel
     float *cls, *regr, *feat;
@@ -37,7 +37,7 @@ struct SynthParams {
 
 __global__ void __launch_bounds__(256) synth_panels_kernel(SynthParams p) {
     const int b = blockIdx.y;
-    const uint64_t key = mix64(p.seed ^ mix64((uint64_t)(p.first_panel + b)));
+    const uint64_t key = mix64(p.seed ^ mix64((uint64_t)(p.first_panel + (long long)b * p.panel_stride)));
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
     const long long t0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     // feature map and regression map: four normals per thread and step (16-byte stores; sizes are multiples of 4
@@ -66,12 +66,12 @@ __global__ void __launch_bounds__(256) synth_panels_kernel(SynthParams p) {
 
 using namespace radnet;
 
-extern "C" int radnet_synth_panels(unsigned long long seed, long long first_panel, int B, int H, int W, int A, int C,
-                                   float *cls, float *regr, float *feat, void *stream) {
+extern "C" int radnet_synth_panels(unsigned long long seed, long long first_panel, long long panel_stride, int B, int H,
+                                   int W, int A, int C, float *cls, float *regr, float *feat, void *stream) {
     RADNET_CHECK_ARG(cls && regr && feat && B >= 1 && B <= 65535 && H >= 1 && W >= 1 && A >= 1 && C >= 1,
                      "synth_panels: bad arguments");
     SynthParams p{};
-    p.seed = seed; p.first_panel = first_panel; p.B = B;
+    p.seed = seed; p.first_panel = first_panel; p.panel_stride = panel_stride; p.B = B;
     p.n_cls = (long long)H * W * A; p.n_regr = 4 * p.n_cls; p.n_feat = (long long)H * W * C;
     p.cls = cls; p.regr = regr; p.feat = feat;
     long long blocks = (p.n_feat / 4 + 255) / 256;

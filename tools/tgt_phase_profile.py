@@ -3,8 +3,8 @@
 
     RADNET_B200_LIB=rock_art_radnet_b200/_C/libradnet_b200_prof.so python tools/tgt_phase_profile.py [B]
 
-Every CTA stamps %globaltimer (ns): 8 CTA start, 9 no fill unit left (CTAs that fill first); per panel (the last
-one a CTA handled) 0 start, 1 figures + floors + anchor tables, 2 windows, 3 phase 1 (IoU over the windows),
+Every CTA stamps %globaltimer (ns): fill CTAs at 0 start and 9 share written; compute CTAs (last panel they
+handled) at 0 start, 1 figures + floors + anchor tables, 2 windows, 3 phase 1 (IoU over the windows),
 4 phase 2 + positives parked, 5 panel filled (wait over), 6 positives written.  Relative to the earliest start."""
 import ctypes
 import os
@@ -46,17 +46,17 @@ for it in range(4):
     e.record()
     torch.cuda.synchronize()
     st = stamps.cpu().numpy().reshape(320, 16).astype(np.float64)
-    st = st[st[:, 8] > 0]
-    t0 = st[:, 8].min()
-    names = {8: "CTA start", 9: "fill: no unit left", 0: "panel start", 1: "setup", 2: "windows", 3: "phase1", 4: "phase2+parked", 5: "panel filled", 6: "positives written"}
+    st = st[st[:, 0] > 0]
+    t0 = st[:, 0].min()
+    names = {0: "start", 9: "fill: share written", 1: "setup", 2: "windows", 3: "phase1", 4: "phase2+parked", 5: "panel filled", 6: "positives written"}
     print("launch %d: event time %.1f us" % (it, a.elapsed_time(e) * 1e3))
-    for k in (8, 9, 0, 1, 2, 3, 4, 5, 6):
+    for k in (0, 9, 1, 2, 3, 4, 5, 6):
         v = st[:, k]
         v = v[v > 0] - t0
         if len(v):
             print("   %-18s n=%4d  min %7.2f  median %7.2f  max %7.2f us" % (names[k], len(v), v.min() / 1e3, np.median(v) / 1e3, v.max() / 1e3))
     comp = st[st[:, 6] > 0]
-    for k, nm in ((10, "pairs"), (11, "hits"), (12, "winners"), (13, "forced")):
+    for k, nm in ((10, "chunks"), (11, "hits"), (12, "winners"), (13, "forced")):
         print("   per panel %-8s min %5d  median %5d  max %5d" % (nm, comp[:, k].min(), np.median(comp[:, k]), comp[:, k].max()))
 
 # ---- steady state: back-to-back launches over rotating output sets (4 x 66.6 MB at B = 64: larger than L2) ----

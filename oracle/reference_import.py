@@ -19,7 +19,11 @@ import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # oracle/build_ref.py
 REFERENCE_ROOT = os.environ.get("RADNET_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "faster_rcnn", "rpn.py")) and \
+        os.path.isfile(os.path.join(_STAGED, "faster_rcnn", "rpn.py")):
+    REFERENCE_ROOT = _STAGED             # the GPU box: only the staged copy of the hot-path modules exists
 
 
 def reference_available():

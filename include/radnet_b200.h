@@ -326,6 +326,46 @@ int radnet_final_nms(const void *rec_in, int in_max_det, int S, int n_in, const 
 int radnet_real_coordinates(const int32_t *v, long long n, double ratio, int32_t *out, void *stream);
 
 
+/* ------------------------------------------------ f4: losses and evaluation
+ * The four training losses of the reference (faster_rcnn/losses.py:16-95) as fused masked reductions over the
+ * NHWC target tensors radnet_rpn_targets writes (layout RADNET_TARGETS_NHWC, regr half scaled) and the rows
+ * radnet_roi_targets_batch writes.  One value per panel (the reference trains with batch size 1).  Elements are
+ * evaluated in float32 exactly as the Keras-2.2 / TF-1 backend calls of losses.py define them (including
+ * K.binary_crossentropy(y_pred, y_true[..., A:]) with the prediction in the `target` slot, losses.py:65); sums are
+ * float64 in a fixed order (deterministic).  TF's reduction order is unspecified: parity bar 1e-5 relative.
+ *   loss [B][2] float32: radnet_rpn_losses {rpn_loss_cls, rpn_loss_regr}; radnet_class_losses {class_loss_cls,
+ *   class_loss_regr}.  ws of radnet_rpn_losses: radnet_rpn_losses_workspace_bytes(B), zeroed once with
+ *   radnet_rpn_losses_workspace_init and left zeroed by every launch. */
+size_t radnet_rpn_losses_workspace_bytes(int B);
+int radnet_rpn_losses_workspace_init(void *ws, size_t ws_bytes, int B, void *stream);
+int radnet_rpn_losses(const double *y_rpn_cls, const double *y_rpn_regr, const float *p_cls,
+                      const float *p_regr, int B, int H, int W, int A, float *loss, void *ws,
+                      size_t ws_bytes, void *stream);
+/* y_class [B][R][n_cls] int32, y_regr [B][R][8(n_cls-1)] float64 (radnet_roi_targets_batch); sel [B][n_sel] row
+ * indices (radnet_select_samples) or NULL (rows 0..n_sel-1); n_sel_per_panel [B] or NULL (= n_sel);
+ * p_cls [B][n_sel][n_cls], p_regr [B][n_sel][4(n_cls-1)] float32 classifier-head outputs for those rows. */
+int radnet_class_losses(const int32_t *y_class, const double *y_regr, const int32_t *sel,
+                        const int32_t *n_sel_per_panel, int B, int R, int n_cls, int n_sel,
+                        const float *p_cls, const float *p_regr, float *loss, void *stream);
+
+/* get_objects (reference test.py:48-113): greedy matching of n_det detections, visited in descending score order
+ * (ties: higher index first), each to the first not yet matched figure of its class with utils.iou >= thr - one
+ * pool of figures, as the reference concatenates the whole test set (test.py:221-227).
+ *   det_box [n_det][4] float64 x1,y1,x2,y2, det_cls [n_det] int32, det_prob [n_det] float64; gt_box / gt_cls alike.
+ *   visit [n_det] int32: detection visited at rank r; match [n_det] int32: figure it matched or -1. */
+size_t radnet_match_detections_workspace_bytes(int n_det, int n_gt);
+int radnet_match_detections(const double *det_box, const int32_t *det_cls, const double *det_prob, int n_det,
+                            const double *gt_box, const int32_t *gt_cls, int n_gt, double thr,
+                            int32_t *visit, int32_t *match, void *ws, size_t ws_bytes, void *stream);
+
+/* calc_class_ap (reference test.py:117-173) for one class: y_true [n] int32, y_pred [n] float64 ->
+ * precision / recall / interpolated precision / interpolated recall [n] float64 in visiting order (descending
+ * score) and ap [1] float64 (the reference adds its terms left to right; here the sum is a tree: 1e-12 relative). */
+size_t radnet_class_ap_workspace_bytes(int n);
+int radnet_class_ap(const int32_t *y_true, const double *y_pred, int n, double *precision, double *recall,
+                    double *interp_precision, double *interp_recall, double *ap, void *ws, size_t ws_bytes,
+                    void *stream);
+
 /* ------------------------------------------------ bench / test utility: synthetic panels on the device
  * BASELINE configs[4] (the 10,000 panels of the archive sweep are generated on the
  * device from their seed).  Counter-based: every value is a hash of (seed, panel id, tensor, element), so panel

@@ -59,6 +59,18 @@ SIGNATURES = {
                                      c_void_p, c_size_t, c_void_p]),
     "radnet_select_samples": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
+    "radnet_rpn_losses_workspace_bytes": (c_size_t, [c_int]),
+    "radnet_rpn_losses_workspace_init": (c_int, [c_void_p, c_size_t, c_int, c_void_p]),
+    "radnet_rpn_losses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
+    "radnet_class_losses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    "radnet_match_detections_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "radnet_match_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double,
+                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "radnet_class_ap_workspace_bytes": (c_size_t, [c_int]),
+    "radnet_class_ap": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_size_t, c_void_p]),
     "radnet_synth_panels": (c_int, [ctypes.c_ulonglong, c_longlong, c_longlong, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "radnet_iou_pairs": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),

@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libradnet_b200.so")
-SOURCES = ["capi.cu", "decode.cu", "sort_nms.cu", "roipool.cu", "rpn_targets.cu", "targets.cu", "sampling.cu", "detect.cu", "synth.cu"]
+SOURCES = ["capi.cu", "decode.cu", "sort_nms.cu", "roipool.cu", "rpn_targets.cu", "targets.cu", "sampling.cu", "detect.cu", "synth.cu", "losses.cu", "evalmap.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -331,3 +331,32 @@ def one_hot_rows(seed, n_pos, n_neg, n_cls=7):
     Y1 = np.zeros((1, n, n_cls), dtype=np.int64)
     Y1[0, np.arange(n), cls] = 1
     return Y1
+
+
+def eval_set(seed, n_gt, n_det, classes=('boat', 'human', 'animal'), extent=1600, hit_rate=0.6, ties=False):
+    """A synthetic test set for the mAP evaluation (reference test.py:48-173): `n_gt` figures and `n_det` detections as
+    the lists of dicts get_objects takes.  About `hit_rate` of the detections are jittered copies of a figure (some
+    figures get several, some the wrong class), the rest are clutter.  ties=True plants equal scores."""
+    rng = np.random.default_rng(seed)
+    gt, det = [], []
+    for _ in range(n_gt):
+        w, h = int(rng.integers(40, 300)), int(rng.integers(40, 300))
+        x1, y1 = int(rng.integers(0, extent - w)), int(rng.integers(0, extent - h))
+        gt.append({'class': classes[int(rng.integers(len(classes)))], 'x1': x1, 'y1': y1, 'x2': x1 + w, 'y2': y1 + h})
+    for _ in range(n_det):
+        if n_gt and rng.random() < hit_rate:
+            g = gt[int(rng.integers(n_gt))]
+            j = rng.integers(-25, 26, 4)
+            x1, y1 = g['x1'] + int(j[0]), g['y1'] + int(j[1])
+            x2, y2 = max(x1 + 1, g['x2'] + int(j[2])), max(y1 + 1, g['y2'] + int(j[3]))
+            c = g['class'] if rng.random() < 0.85 else classes[int(rng.integers(len(classes)))]
+        else:
+            w, h = int(rng.integers(30, 300)), int(rng.integers(30, 300))
+            x1, y1 = int(rng.integers(0, extent - w)), int(rng.integers(0, extent - h))
+            x2, y2 = x1 + w, y1 + h
+            c = classes[int(rng.integers(len(classes)))]
+        p = float(np.float32(rng.uniform(0.2, 1.0)))
+        if ties:
+            p = round(p, 1)
+        det.append({'class': c, 'x1': x1, 'y1': y1, 'x2': x2, 'y2': y2, 'prob': p})
+    return det, gt

@@ -135,9 +135,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// wait with a retry bound (each try_wait sleeps in hardware up to its time limit); false = gave up
+// wait bounded by ELAPSED TIME (2 s of %globaltimer), not by a number of attempts: under time-slicing, MPS,
+// compute-sanitizer or a debugger a healthy partner can be arbitrarily slow per attempt, and a spurious give-up
+// would turn a correct run into an error.  Each try_wait suspends the warp in hardware up to its own time limit;
+// the clock is only read every 1024 failed attempts.  false = the partner never arrived (results are flagged
+// invalid by the caller, which still arrives on its own barrier so that its successors do not hang).
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
-    for (int tries = 0; tries < (1 << 16); ++tries) {
+    long long t_start = 0;
+    for (unsigned tries = 0;; ++tries) {
         uint32_t ok;
         asm volatile(
             "{\n"
@@ -149,8 +154,13 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) return true;
+        if ((tries & 1023u) == 1023u) {
+            long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > 2000000000LL) return false;
+        }
     }
-    return false;
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,

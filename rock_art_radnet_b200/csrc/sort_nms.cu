@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(SortNmsParams 
         float *rs = reinterpret_cast<float *>(rec + 16 + (size_t)p.det_max_boxes * 16);
         int32_t *ri = reinterpret_cast<int32_t *>(rec + 16 + (size_t)p.det_max_boxes * 20);
         if (threadIdx.x == 0) {
-            hdr[0] = *s_fault ? -1 : kept_n;        // -1: hand-off wait timed out (kernel bug), results invalid
+            hdr[0] = *s_fault ? -1 : kept_n;        // -1: a hand-off did not complete within 2 s, results invalid
             hdr[1] = M;
             hdr[2] = *s_ties;
             hdr[3] = S;

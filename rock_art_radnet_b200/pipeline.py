@@ -62,7 +62,7 @@ class DetectionRecords:
         """-> list of dicts with int64 boxes (k,4), float32 scores, int64 flat indices."""
         hdr = self.header.cpu().numpy()
         if (hdr[:, 0] < 0).any():
-            raise RuntimeError("radnet_sort_nms_i32: hand-off wait timed out (kernel bug); results invalid")
+            raise RuntimeError("radnet_sort_nms_i32: a row hand-off did not complete within 2 s; results invalid")
         boxes = self.boxes.cpu().numpy()
         scores = self.scores.cpu().numpy()
         index = self.index.cpu().numpy()

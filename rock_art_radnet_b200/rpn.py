@@ -92,7 +92,7 @@ def _nms_device(boxes_dev, probs_dev, valid_dev, overlap_thresh, max_boxes):
               float(overlap_thresh), mb, D.ptr(pick), D.ptr(count), D.ptr(ws), ws_bytes, D.stream_ptr(dev))
     cnt = count.cpu().numpy()
     if cnt[0] < 0:
-        raise RuntimeError("radnet_nms_f64: hand-off watchdog fired (kernel bug); results invalid")
+        raise RuntimeError("radnet_nms_f64: a row hand-off did not complete within 2 s; results invalid")
     return pick[:int(cnt[0])].cpu().numpy().astype(np.int64), int(cnt[1])
 
 

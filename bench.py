@@ -540,15 +540,20 @@ def run_b200_arm(args):
     for _ in range(2):
         stream.submit(cls_h, regr_h, feat_h)
         stream.collect()
+    # the job's K * world batches are handed out through a shared counter: a rank with a faster host link takes more
+    # of them (rate-aware streaming); the number of panels of the job is what a static split would process
+    from rock_art_radnet_b200.pipeline import SharedBatchCounter
+    queue = SharedBatchCounter(K * world, name="radnet_e2e_%d" % os.getpid() if world == 1 else "radnet_e2e")
     barrier()
     t0 = time.perf_counter()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
     inflight = 0
     checksum = 0
-    for k in range(K):
+    my_batches = 0
+    while True:
+        if queue.next() is None:
+            break
         stream.submit(cls_h, regr_h, feat_h)
+        my_batches += 1
         inflight += 1
         if inflight == 2:
             checksum += int(stream.collect()[0, 0])
@@ -557,9 +562,16 @@ def run_b200_arm(args):
         checksum += int(stream.collect()[0, 0])
         inflight -= 1
     torch.cuda.synchronize()
-    e1.record()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    batches = torch.tensor([my_batches], dtype=torch.int64, device=dev)
+    if world > 1:
+        gathered_b = [torch.zeros_like(batches) for _ in range(world)]
+        dist.all_gather(gathered_b, batches)
+        batches_per_rank = [int(t.item()) for t in gathered_b]
+    else:
+        batches_per_rank = [my_batches]
+    assert sum(batches_per_rank) == K * world, batches_per_rank
 
     # ---- the other BASELINE configs and north-star kernels ---------------------------
     peak, peak_src = measured_hbm_peak()
@@ -607,8 +619,10 @@ def run_b200_arm(args):
             "clocks": clocks,
             "e2e": {"value": panels / (e2e_ms * 1e-3), "unit": "panels/s",
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "batches_per_rank": batches_per_rank,
                     "note": "HostPanelStream: pinned host maps -> H2D -> decode+NMS+pool -> detection records D2H; "
-                            "pooled features stay in HBM for the classifier head"},
+                            "pooled features stay in HBM for the classifier head; the job's batches are handed out "
+                            "through a shared counter (a faster host link takes more)"},
             "gpu_launches": 3 * K,
             "kernels_ms_per_step": {"decode_clip": dec_ms, "sort_nms": nms_ms, "roi_pool": pool_ms},
             "nms_latency_us": {"p50": lat[len(lat) // 2], "p95": lat[int(len(lat) * 0.95) - 1], "n": len(lat),

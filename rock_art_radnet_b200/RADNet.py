@@ -132,11 +132,18 @@ class RADNet:
     # ------------------------------------------------------------------ f2
     def final_nms(self, boxes, probs, obj_avg_threshold=0.2, obj_confidence_threshold=0.8, n_obj_avg=5):
         """Cluster-and-average NMS of one class (RADNet.py:156-240): (M,4) boxes, (M,) probs ->
-        (boxes (K,4) int64, probs (K,) float32); `[]` for no boxes."""
+        (boxes (K,4) int64, probs (K,) float32); `[]` for no boxes.
+
+        Domain of the device path = what `predict` feeds it: integer pixel boxes and float32 scores.  The reference
+        sorts, thresholds and averages in the dtype it is given; scores that are not exactly float32 values (a
+        float64 array with more precision) and non-integer boxes would be silently narrowed here, so they are
+        refused with ValueError instead."""
         if len(boxes) == 0:
             return []
         boxes = np.asarray(boxes)
         probs = np.asarray(probs)
+        if probs.dtype != np.float32 and not np.array_equal(probs.astype(np.float32).astype(probs.dtype), probs):
+            raise ValueError("final_nms: the device path takes float32 scores (as RADNet.predict produces)")
         np.testing.assert_array_less(boxes[:, 0], boxes[:, 2])
         np.testing.assert_array_less(boxes[:, 1], boxes[:, 3])
         if boxes.dtype.kind != "i" and not np.array_equal(boxes, np.rint(boxes)):

@@ -11,6 +11,28 @@ from . import _device as D
 from . import _lib
 
 
+def _keras_layer_base():
+    """`keras.layers.Layer` (the reference subclasses `keras.engine.topology.Layer`, RoiPoolingConv.py:6-8) when a
+    Keras is importable, else `object`: without Keras the class is a plain callable with the same methods."""
+    for mod, attr in (("keras.engine.topology", "Layer"), ("keras.layers", "Layer"), ("tensorflow.keras.layers", "Layer")):
+        try:
+            m = __import__(mod, fromlist=[attr])
+            base = getattr(m, attr)
+            if isinstance(base, type):
+                return base
+        except Exception:
+            continue
+    return object
+
+
+_LayerBase = _keras_layer_base()
+
+
+def _is_graph_tensor(x):
+    """A symbolic / eager tensor of TensorFlow (anything from a `tensorflow` module that is neither NumPy nor torch)."""
+    return type(x).__module__.split(".")[0] in ("tensorflow", "keras") and not isinstance(x, np.ndarray)
+
+
 def roi_pool_device(feat, rois, roi_count, pool_size, out=None):
     """feat (B,H,W,C) float32 CUDA, rois (B,R,4) int32 CUDA as (x,y,w,h), roi_count (B,) int32
     CUDA or None -> (B,R,pool,pool,C) float32 CUDA.  Asynchronous."""
@@ -23,8 +45,11 @@ def roi_pool_device(feat, rois, roi_count, pool_size, out=None):
     return out
 
 
-class RoiPoolingConv:
-    """ROI pooling layer for 2D inputs (reference RoiPoolingConv.py:8-95).
+class RoiPoolingConv(_LayerBase):
+    """ROI pooling layer for 2D inputs (reference RoiPoolingConv.py:8-95).  A `keras.layers.Layer` when Keras is
+    importable (so it can sit inside the classifier graph exactly where the reference instantiates it,
+    resnet50.py:249-252 / vgg16.py:85); called on graph tensors it runs the CUDA kernel through
+    `tf.numpy_function` with the static output shape restored.
 
     # Arguments
         pool_size: int, side of the pooled output (14 for ResNet-50, 7 for VGG-16).
@@ -41,17 +66,33 @@ class RoiPoolingConv:
         self.pool_size = pool_size
         self.num_rois = num_rois
         self.nb_channels = None
+        if _LayerBase is not object:
+            super().__init__(**kwargs)                              # RoiPoolingConv.py:38
 
     def build(self, input_shape):
         self.nb_channels = input_shape[0][3]                       # RoiPoolingConv.py:42
+        if _LayerBase is not object:
+            super().build(input_shape)
 
     def compute_output_shape(self, input_shape):
         nb = self.nb_channels if self.nb_channels is not None else input_shape[0][3]
         return None, self.num_rois, self.pool_size, self.pool_size, nb   # RoiPoolingConv.py:45-46
 
+    def _call_graph(self, img, rois):
+        """Graph / eager TensorFlow tensors: the kernel runs as a `tf.numpy_function`; the static shape
+        (1, num_rois, pool, pool, channels) that `compute_output_shape` promises is set on the result."""
+        import tensorflow as tf
+        fn = getattr(tf, "numpy_function", None) or tf.py_func
+        out = fn(lambda a, b: self.call([np.asarray(a), np.asarray(b)]), [img, rois], tf.float32)
+        nb = self.nb_channels if self.nb_channels is not None else img.shape[3]
+        out.set_shape((1, self.num_rois, self.pool_size, self.pool_size, nb))
+        return out
+
     def call(self, x, mask=None):
         assert (len(x) == 2)                                       # RoiPoolingConv.py:50
         img, rois = x[0], x[1]
+        if _is_graph_tensor(img):
+            return self._call_graph(img, rois)
         D.require_cuda()
         on_device = D.is_cuda_tensor(img)
         dev = img.device if on_device else torch.device("cuda:%d" % torch.cuda.current_device())
@@ -76,7 +117,12 @@ class RoiPoolingConv:
         # (1,num_rois,pool,pool,C); the reference's final permute is the identity (RoiPoolingConv.py:86)
         return out if on_device else out.cpu().numpy()
 
-    __call__ = call
+    if _LayerBase is object:
+        __call__ = call                                            # without Keras the instance itself is the op
 
     def get_config(self):
-        return {'pool_size': self.pool_size, 'num_rois': self.num_rois}
+        config = {'pool_size': self.pool_size, 'num_rois': self.num_rois}
+        if _LayerBase is not object:
+            base_config = super().get_config()                     # RoiPoolingConv.py:90-95
+            return dict(list(base_config.items()) + list(config.items()))
+        return config

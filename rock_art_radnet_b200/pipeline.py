@@ -239,13 +239,20 @@ class HostPanelStream:
         self.uploaded = [torch.cuda.Event() for _ in range(slots)]
         self.consumed = [torch.cuda.Event() for _ in range(slots)]
         self.done = [torch.cuda.Event() for _ in range(slots)]
+        # `pipe.pooled` is ONE buffer shared by consecutive batches: a consumer on another stream waits on
+        # `pooled_ready` before reading it and hands back an event through `release_pooled` when it is done
+        self.pooled_ready = torch.cuda.Event()
+        self.pooled_consumed = None
         self._n = 0
         self._pending = []
         self.h2d_bytes_per_batch = 4 * (B * H * W * A * 5 + B * H * W * Cn)
         self.d2h_bytes_per_batch = B * pipe.records.stride
 
     def submit(self, cls_h, regr_h, feat_h):
-        """cls_h/regr_h/feat_h: float32 CPU tensors (pinned for asynchronous copies)."""
+        """cls_h/regr_h/feat_h: float32 CPU tensors (pinned for asynchronous copies).  At most `slots` batches may
+        be in flight: a further submit before `collect` would overwrite the host records of an uncollected batch."""
+        if len(self._pending) >= self.slots:
+            raise RuntimeError("HostPanelStream: %d batches in flight - collect() before submitting more" % self.slots)
         s = self._n % self.slots
         if self._n >= self.slots:
             self.copy_stream.wait_event(self.consumed[s])      # slot inputs no longer being read
@@ -256,12 +263,20 @@ class HostPanelStream:
             self.uploaded[s].record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.uploaded[s])
+            if self.pooled_consumed is not None:
+                self.compute_stream.wait_event(self.pooled_consumed)   # the head has read the previous pooled batch
             rec, _ = self.pipe(self.cls[s], self.regr[s], self.feat[s])
+            self.pooled_ready.record(self.compute_stream)
             self.consumed[s].record(self.compute_stream)
             self.rec_host[s].copy_(rec.raw, non_blocking=True)
             self.done[s].record(self.compute_stream)
         self._pending.append(s)
         self._n += 1
+
+    def release_pooled(self, event):
+        """`event`: recorded by the consumer of `pipe.pooled` (the classifier head) on its own stream once it has
+        read the current batch; the next RoI pool waits for it before overwriting the buffer."""
+        self.pooled_consumed = event
 
     def collect(self):
         """Wait for the oldest submitted batch; returns its records as a host uint8 tensor."""
@@ -303,3 +318,28 @@ class DetectionPipeline(ProposalPipeline):
         merged = DT.final_nms_records(tile_records, n_images, tiles_per_image, self.n_cls)
         final = DT.class_nms(merged, 1, n_images, self.n_cls, final_thresh, max_boxes=300)
         return merged, final
+
+
+class SharedBatchCounter:
+    """A job-wide counter of batches handed out to the ranks of one box (rate-aware host streaming): every rank pulls
+    the index of its next batch, so ranks whose host link is faster take more batches - a static equal split runs at
+    the pace of the slowest link (on the 8-GPU pool box four links move 23 GB/s and four 36 GB/s,
+    profiles/r01_topo_h2d.txt).  Backed by the process group's key-value store (`store.add` is atomic; one round
+    trip of tens of microseconds per batch of milliseconds).  Without a process group it is a local counter."""
+
+    def __init__(self, total, name="radnet_batches"):
+        import torch.distributed as dist
+        self.total, self.name = int(total), name
+        self._local = 0
+        self._store = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._store = dist.distributed_c10d._get_default_store()
+
+    def next(self):
+        """Index of the next batch, or None when all `total` batches have been handed out."""
+        if self._store is None:
+            i = self._local
+            self._local += 1
+        else:
+            i = int(self._store.add(self.name, 1)) - 1
+        return i if i < self.total else None

@@ -5,6 +5,7 @@ reference; the arithmetic runs in libradnet_b200.so on the GPU.  Host code here
 only validates arguments, stages NumPy arrays to the device and shapes results.
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -15,6 +16,7 @@ from .pipeline import ProposalPipeline, anchor_cells
 from .utils import get_new_img_size
 
 _PIPELINES = {}
+_PIPELINE_LOCK = threading.Lock()       # the cached single-panel pipelines own device buffers: one caller at a time
 
 
 def _device():
@@ -53,11 +55,12 @@ def rpn_to_roi(rpn_layer, regr_layer, C, use_regr=True, max_boxes=300, overlap_t
     cls = D.to_device(rpn_layer, np.float32, dev)
     regr = D.to_device(regr_layer, np.float32, dev)
     if use_regr and _int_table_ok(H, W):
-        pipe = _single_panel_pipeline(C, H, W, max(1, min(int(max_boxes), H * W * A)), overlap_thresh)
-        pipe.decode(cls, regr, use_regr=True)
-        pipe.sort_nms()
-        pipe.check_stats()
-        det = pipe.records.to_numpy()[0]
+        with _PIPELINE_LOCK:
+            pipe = _single_panel_pipeline(C, H, W, max(1, min(int(max_boxes), H * W * A)), overlap_thresh)
+            pipe.decode(cls, regr, use_regr=True)
+            pipe.sort_nms()
+            pipe.check_stats()
+            det = pipe.records.to_numpy()[0]
         return det["boxes"]
     # general path: float64 boxes (anchors without regression may be half-integers)
     n = H * W * A

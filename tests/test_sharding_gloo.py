@@ -147,3 +147,41 @@ def test_owner_routing_without_process_group_is_identity():
     router = sharding.OwnerRoutedTiles(2, 5, rank=0, world=1)
     raw = torch.arange(10 * 8, dtype=torch.uint8).reshape(10, 8)
     assert torch.equal(router.exchange(raw), raw) and torch.equal(router.gather_final(raw[:2]), raw[:2])
+
+
+def _counter_worker(rank, world, port, total, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rock_art_radnet_b200.pipeline import SharedBatchCounter
+    q = SharedBatchCounter(total)
+    mine = []
+    while True:
+        i = q.next()
+        if i is None:
+            break
+        mine.append(i)
+        if rank == 0:
+            import time
+            time.sleep(0.002)                 # a slow link: the other rank should take more batches
+    np.save(os.path.join(out_dir, "cnt_%d.npy" % rank), np.array(mine, dtype=np.int64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_batch_counter_hands_out_every_batch_once_gloo(tmp_path):
+    """Rate-aware streaming: every batch index is handed out exactly once across ranks, and the rank that is slower
+    per batch ends up with fewer of them."""
+    port = _free_port()
+    total = 200
+    mp.spawn(_counter_worker, args=(2, port, total, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "cnt_0.npy"), np.load(tmp_path / "cnt_1.npy")
+    assert sorted(a.tolist() + b.tolist()) == list(range(total))
+    assert len(b) > len(a)
+
+
+def test_shared_batch_counter_without_process_group():
+    from rock_art_radnet_b200.pipeline import SharedBatchCounter
+    q = SharedBatchCounter(3)
+    assert [q.next(), q.next(), q.next(), q.next()] == [0, 1, 2, None]

@@ -7,9 +7,11 @@
 // pixels, so reading the map through L2 would cost up to 4x the write traffic.  Design:
 //
 //   * channel-sliced, map-resident CTAs: a CTA owns (panel, slice of 32 channels) and
-//     copies that slice of the WHOLE map (38*38*128 B = 185 KB) into shared memory once
-//     (cp.async 16 B, coalesced 128 B per pixel).  The map is then read from HBM exactly
-//     once per panel and every bilinear tap is a conflict-free LDS.128.
+//     brings that slice of the WHOLE map (38*38*128 B = 185 KB) into shared memory with ONE
+//     TMA tensor copy (cp.async.bulk.tensor.4d over the map seen as (C, W, H, B); SASS
+//     UTMALDG) that completes on an mbarrier while the first y tables are being built.  The
+//     map is then read from HBM exactly once per panel and every bilinear tap is a
+//     conflict-free LDS.128.  (cp.async 16 B is kept for maps wider than a TMA box.)
 //   * per chunk of 32 RoIs the CTA tabulates, per axis and output index, the two source
 //     offsets and the float32 lerp weight exactly as TF's compute_interpolation_weights
 //     does (scale = in/out float divide; in = i*scale; floor/ceil; lerp = in - floor(in)).
@@ -20,6 +22,9 @@
 //
 // A direct (global-load) kernel covers maps whose slice does not fit in shared memory
 // and channel counts that are not a multiple of 4.
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace radnet {
@@ -40,7 +45,18 @@ struct RoiPoolParams {
     float *out;              // [B][R][pool][pool][C]
     int n_slices;
     int roi_chunk;           // RoIs whose y tables fit in shared memory at once
+    int map_rows_pad;        // map rows held in shared memory (>= H: whole TMA boxes)
+    int tma_rows;            // map rows per TMA box (0 = stage with cp.async)
 };
+
+// global -> shared TMA tile copy of a rank-4 tensor, completion (bytes) on an mbarrier
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
 
 // Per (RoI, output row) entry of the y table, 8 bytes = one LDS.64.
 //   bits  0..15  pixel index of the first cell of source row y+y0  ((y+y0)*W)
@@ -136,14 +152,17 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // re-sampled (2 LDS.128 each).  top/bottom of TF's formula are exactly hrow(y0)/hrow(y1), so
 // the result is bit-identical to evaluating all four taps per output.
 template <int LANES>
-__global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPoolParams p) {
+__global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPoolParams p,
+                                                                          const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar;
     constexpr int kPixBytes = LANES * 16;
     constexpr int G = kPoolThreads / LANES;          // columns in flight per CTA
     const int HW = p.H * p.W;
+    const int HWp = p.map_rows_pad * p.W;            // pixels held in shared memory (whole TMA boxes)
     const int pool = p.pool, PP = pool * pool;
-    float4 *s_map = reinterpret_cast<float4 *>(smem);                                   // [HW+1][LANES]
-    YEntry *s_ytab = reinterpret_cast<YEntry *>(smem + (size_t)(HW + 1) * kPixBytes);   // [chunk][pool]
+    float4 *s_map = reinterpret_cast<float4 *>(smem);                                   // [HWp+1][LANES]
+    YEntry *s_ytab = reinterpret_cast<YEntry *>(smem + (size_t)(HWp + 1) * kPixBytes);  // [chunk][pool]
     int2 *s_roi = reinterpret_cast<int2 *>(s_ytab + (size_t)p.roi_chunk * pool);        // [chunk] {x, cw}
     float *s_scale = reinterpret_cast<float *>(s_roi + p.roi_chunk);                    // [W+1] cw / pool (float32 divide)
 
@@ -154,13 +173,28 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
     const int g = threadIdx.x / LANES;
 
     // ---- stage the channel slice of the whole map (read from HBM exactly once) --------
-    {
+    if (p.tma_rows > 0) {
+        // one elected thread: a TMA tile copy per box of `tma_rows` map rows (one box for maps up to 256 rows),
+        // all completing on the same mbarrier; everybody else goes straight on to the first y tables
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            const int n_box = p.map_rows_pad / p.tma_rows;
+            mbar_expect_tx(&s_bar, (uint32_t)((size_t)HWp * kPixBytes));
+            for (int k = 0; k < n_box; ++k)
+                tma_load_4d(reinterpret_cast<unsigned char *>(s_map) + (size_t)k * p.tma_rows * p.W * kPixBytes, &tmap,
+                            s * LANES * 4, 0, k * p.tma_rows, b, &s_bar);
+        }
+        if (g == 0) s_map[HWp * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);     // the "zero pixel"
+        for (int i = threadIdx.x; i <= p.W; i += kPoolThreads) s_scale[i] = __fdiv_rn((float)i, (float)p.pool);
+    } else {
         const float4 *src = reinterpret_cast<const float4 *>(p.feat) + (size_t)b * HW * C4 + (size_t)s * LANES + q;
         for (int pix = g; pix < HW; pix += G) cp_async16(&s_map[pix * LANES + q], src + (size_t)pix * C4);
-        if (g == 0) s_map[HW * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);      // the "zero pixel"
+        if (g == 0) s_map[HWp * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);     // the "zero pixel"
         for (int i = threadIdx.x; i <= p.W; i += kPoolThreads) s_scale[i] = __fdiv_rn((float)i, (float)p.pool);
         cp_async_wait_all();
     }
+    bool map_ready = p.tma_rows == 0;
     const unsigned char *mapb = reinterpret_cast<const unsigned char *>(s_map) + q * 16;
     const size_t py_step = (size_t)pool * C4;
 
@@ -194,6 +228,10 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
             s_ytab[e] = en;
         }
         __syncthreads();
+        if (!map_ready) {            // the barrier above also ordered the mbarrier's initialisation before this wait
+            mbar_wait(&s_bar, 0);
+            map_ready = true;
+        }
 
         const int ncol = nr * pool;
         // (rl, px) advance incrementally by G columns: no integer division in the column loop
@@ -213,7 +251,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
                 xo0 = (rx.x + lo) * kPixBytes;
                 xo1 = (rx.x + hi) * kPixBytes;
             } else {
-                xo0 = xo1 = HW * kPixBytes;
+                xo0 = xo1 = HWp * kPixBytes;
                 lx = 0.f;
             }
             const YEntry *yt = s_ytab + rl * pool;
@@ -285,12 +323,54 @@ __global__ void __launch_bounds__(256) roi_pool_direct_kernel(RoiPoolParams p) {
 }
 
 template <int LANES>
-static int launch_slice(const RoiPoolParams &p, int B, size_t smem, cudaStream_t st) {
+static int launch_slice(const RoiPoolParams &p, const CUtensorMap &tmap, int B, size_t smem, cudaStream_t st) {
     int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(roi_pool_slice_kernel<LANES>), dev, smem)) return rc;
-    roi_pool_slice_kernel<LANES><<<B * p.n_slices, kPoolThreads, smem, st>>>(p);
+    roi_pool_slice_kernel<LANES><<<B * p.n_slices, kPoolThreads, smem, st>>>(p, tmap);
     return check_launch("roi_pool_slice_kernel");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// the feature maps as a rank-4 tensor (C, W, H, B), box = (lanes*4 channels, W, rows, 1); false when the shape
+// does not fit a TMA box (the kernel then stages with cp.async)
+static bool make_map_tensor(CUtensorMap *tmap, const float *feat, int B, int H, int W, int C, int lanes, int rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || W > 256 || rows > 256 || rows < 1 || (C * 4) % 16 != 0) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)lanes * 4, (cuuint32_t)W, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(feat), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// rows per TMA box: whole map when it has at most 256 rows, else the split with the least padding
+static int tma_box_rows(int H) {
+    if (H <= 256) return H;
+    int best = 1, best_pad = 1 << 30;
+    for (int k = 256; k >= 64; --k) {
+        const int pad = (H + k - 1) / k * k - H;
+        if (pad < best_pad) { best_pad = pad; best = k; }
+    }
+    return best;
 }
 
 }  // namespace radnet
@@ -327,9 +407,11 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
         (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const int C4 = C / 4;
         const int lanes_opts[4] = {8, 4, 2, 1};
+        const int box_rows = (W <= 256 && encode_tiled_fn()) ? tma_box_rows(H) : 0;
+        const int rows_pad = box_rows ? (H + box_rows - 1) / box_rows * box_rows : H;
         for (int li = 0; li < 4; ++li) {
             int L = lanes_opts[li];
-            size_t map_bytes = (HW + 1) * L * 16;
+            size_t map_bytes = ((size_t)rows_pad * W + 1) * L * 16;
             const size_t scale_bytes = ((size_t)W + 1) * sizeof(float) + 16;
             if (C4 % L != 0 || map_bytes + scale_bytes + 8 * per_roi > (size_t)smem_limit) continue;
             size_t chunk = ((size_t)smem_limit - map_bytes - scale_bytes) / per_roi;
@@ -338,11 +420,16 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
             p.n_slices = C4 / L;
             p.roi_chunk = (int)chunk;
             if ((long long)B * p.n_slices >= 0x7fffffffLL) continue;
+            alignas(64) CUtensorMap tmap;
+            memset(&tmap, 0, sizeof(tmap));
+            p.map_rows_pad = rows_pad;
+            p.tma_rows = (box_rows && make_map_tensor(&tmap, feat, B, H, W, C, L, box_rows)) ? box_rows : 0;
+            if (!p.tma_rows && rows_pad != H) continue;            // sized for TMA boxes but no descriptor: next option
             switch (L) {
-                case 8: return launch_slice<8>(p, B, smem, st);
-                case 4: return launch_slice<4>(p, B, smem, st);
-                case 2: return launch_slice<2>(p, B, smem, st);
-                default: return launch_slice<1>(p, B, smem, st);
+                case 8: return launch_slice<8>(p, tmap, B, smem, st);
+                case 4: return launch_slice<4>(p, tmap, B, smem, st);
+                case 2: return launch_slice<2>(p, tmap, B, smem, st);
+                default: return launch_slice<1>(p, tmap, B, smem, st);
             }
         }
     }

@@ -34,7 +34,9 @@ def test_sm100a_and_no_packed_fma_in_roi_pool():
         assert "FFMA2" not in text, name
     slice8 = "\n".join(next(v for k, v in pool.items() if "slice_kernelILi8" in k))
     assert "FMUL2" in slice8 and "FADD2" in slice8          # packed f32x2 math is in use
-    assert "LDGSTS" in slice8                               # cp.async staging of the map slice
+    assert "UTMALDG.4D" in slice8                           # TMA tensor copy of the map slice (cp.async.bulk.tensor.4d)
+    assert "SYNCS" in slice8                                # ... completing on an mbarrier
+    assert "LDGSTS" in slice8                               # cp.async staging kept for maps wider than a TMA box
     assert "STG.E.EF.128" in slice8                         # streaming 16-byte stores
 
 

@@ -281,6 +281,148 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
     }
 }
 
+// ---- pair form: a cluster of two CTAs holds one channel slice, half of the map rows each --------------------
+// For maps whose 32-channel slice does not fit one CTA's shared memory (600x800 px: 38*50*128 B = 243 KB) the
+// whole-map form had to fall back to 16-channel slices: 64-byte store segments, twice the CTAs (0.83 of the HBM
+// peak instead of 0.95).  Here CTA `rank` of a cluster of two stages rows [rank*Hh, rank*Hh + Hh) of the slice
+// (one TMA tile copy each) and the pair splits the output columns; a bilinear tap on a row of the other half is
+// a distributed-shared-memory load (ld.shared::cluster on the mapa-translated address).  Store lines stay 128
+// bytes, and when a half is small enough (38x38: 92 KB) two CTAs share an SM, so the staging of one cluster
+// overlaps the store stream of another.
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int LANES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPoolThreads, 1)
+    roi_pool_pair_kernel(RoiPoolParams p, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    constexpr int kPixBytes = LANES * 16;
+    constexpr int G = kPoolThreads / LANES;          // columns in flight per CTA
+    const int Hh = p.tma_rows;                       // map rows per half
+    const int HWh = Hh * p.W;                        // pixels of a half (whole TMA box)
+    const int pool = p.pool, PP = pool * pool;
+    float4 *s_map = reinterpret_cast<float4 *>(smem);                                   // [HWh+1][LANES]
+    YEntry *s_ytab = reinterpret_cast<YEntry *>(smem + (size_t)(HWh + 1) * kPixBytes);  // [chunk][pool]
+    int2 *s_roi = reinterpret_cast<int2 *>(s_ytab + (size_t)p.roi_chunk * pool);        // [chunk] {x, cw}
+    float *s_scale = reinterpret_cast<float *>(s_roi + p.roi_chunk);                    // [W+1] cw / pool (float32 divide)
+
+    const int rank = (int)cluster_ctarank();
+    const int pairi = blockIdx.x >> 1;
+    const int b = pairi / p.n_slices;
+    const int s = pairi - b * p.n_slices;
+    const int C4 = p.C >> 2;
+    const int q = threadIdx.x % LANES;
+    const int g = threadIdx.x / LANES;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, (uint32_t)((size_t)HWh * kPixBytes));
+        // rows beyond the map (second half of an odd H) are zero-filled by the TMA unit
+        tma_load_4d(s_map, &tmap, s * LANES * 4, 0, rank * Hh, b, &s_bar);
+    }
+    if (g == 0) s_map[HWh * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);         // the "zero pixel"
+    for (int i = threadIdx.x; i <= p.W; i += kPoolThreads) s_scale[i] = __fdiv_rn((float)i, (float)p.pool);
+    const unsigned char *mapb = reinterpret_cast<const unsigned char *>(s_map) + q * 16;
+    const uint32_t peer = cluster_map_shared(mapb, (uint32_t)(rank ^ 1));
+    const size_t py_step = (size_t)pool * C4;
+    bool map_ready = false;
+
+    // a tap: 16 bytes at `off` inside the half `owner` of the slice
+    auto tap = [&](int owner, unsigned off) -> float4 {
+        return owner == rank ? *reinterpret_cast<const float4 *>(mapb + off) : ld_dsmem_f4(peer + off);
+    };
+
+    for (int r0 = 0; r0 < p.R; r0 += p.roi_chunk) {
+        const int nr = min(p.roi_chunk, p.R - r0);
+        __syncthreads();     // previous chunk done with the tables
+        for (int e = threadIdx.x; e < nr * pool; e += kPoolThreads) {
+            int rl = e / pool, i = e - rl * pool;
+            int x, y, cw, ch;
+            YEntry en;
+            if (fetch_roi(p, b, r0 + rl, x, y, cw, ch)) {
+                int lo, hi, plo = -1, phi = -1;
+                float pl;
+                legacy_axis(i, ch, pool, lo, hi, en.lerp);
+                if (i > 0) legacy_axis(i - 1, ch, pool, plo, phi, pl);
+                unsigned act;
+                if (i == 0) act = (hi == lo) ? kActOneDup : kActBoth;
+                else if (lo == plo && hi == phi) act = kActKeep;
+                else if (lo == phi && hi != lo && phi != plo) act = kActShift;
+                else if (lo == phi && hi == lo && phi != plo) act = kActShiftDup;
+                else if (lo == plo && phi == plo && hi != lo) act = kActExtend;
+                else act = (hi == lo) ? kActOneDup : kActBoth;
+                // absolute source row y + lo; the kernel splits it into (half, row inside the half)
+                en.code = (unsigned)(y + lo) | ((hi != lo) ? 0x10000u : 0u) | (act << 28);
+                if (i == 0) s_roi[rl] = make_int2(x, cw);
+            } else {
+                en.code = (i == 0) ? (kActOneDup << 28) : (kActKeep << 28);
+                en.lerp = 0.f;
+                if (i == 0) s_roi[rl] = make_int2(0, 0);
+            }
+            s_ytab[e] = en;
+        }
+        __syncthreads();
+        if (!map_ready) {
+            mbar_wait(&s_bar, 0);        // my half has landed ...
+            cluster_sync_all();          // ... and so has the partner's
+            map_ready = true;
+        }
+
+        const int ncol = nr * pool;
+        // the pair walks the columns 2G at a time: CTA `rank` takes the rank-th group of G
+        const int g2 = g + rank * G;
+        int rl = g2 / pool, px = g2 - rl * pool;
+        const int d_rl = (2 * G) / pool, d_px = 2 * G - d_rl * pool;
+        for (int col = g2; col < ncol; col += 2 * G, rl += d_rl, px += d_px) {
+            while (px >= pool) { px -= pool; ++rl; }
+            const int2 rx = s_roi[rl];
+            const bool live = rx.y > 0;
+            unsigned xo0 = 0, xo1 = 0;
+            float lx = 0.f;
+            if (live) {
+                const float src = __fmul_rn((float)px, s_scale[rx.y]);
+                const float fl = floorf(src);
+                const int lo = max((int)fl, 0), hi = min((int)ceilf(src), rx.y - 1);
+                lx = __fsub_rn(src, fl);
+                xo0 = (unsigned)(rx.x + lo) * kPixBytes;
+                xo1 = (unsigned)(rx.x + hi) * kPixBytes;
+            }
+            const YEntry *yt = s_ytab + rl * pool;
+            float4 *dst = reinterpret_cast<float4 *>(p.out) +
+                          (((size_t)b * p.R + r0 + rl) * PP + px) * C4 + (size_t)s * LANES + q;
+            const unsigned row_bytes = (unsigned)p.W * kPixBytes;
+            float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+#pragma unroll 2
+            for (int py = 0; py < pool; ++py) {
+                const YEntry e = yt[py];
+                const unsigned act = e.code >> 28;
+                if (act != kActKeep && live) {
+                    const int ya = (int)(e.code & 0xFFFFu), yb = ya + 1;           // absolute rows y0 and y0 + 1
+                    const int oa = ya >= Hh, ob = yb >= Hh;
+                    const unsigned ra = (unsigned)(ya - oa * Hh) * row_bytes, rb = (unsigned)(yb - ob * Hh) * row_bytes;
+                    if (act == kActShift || act == kActShiftDup) h0 = h1;
+                    if (act == kActBoth || act == kActOneDup) h0 = lerp4(tap(oa, ra + xo0), tap(oa, ra + xo1), lx);
+                    if (act == kActOneDup) h1 = h0;
+                    if (act == kActShift || act == kActBoth || act == kActExtend)
+                        h1 = lerp4(tap(ob, rb + xo0), tap(ob, rb + xo1), lx);
+                }
+                st_stream_f4(dst, lerp4(h0, h1, e.lerp));
+                dst += py_step;
+            }
+        }
+    }
+    if (!map_ready) {                    // no chunk at all (R == 0 cannot happen, but never leave the partner waiting)
+        mbar_wait(&s_bar, 0);
+        cluster_sync_all();
+    }
+    cluster_sync_all();                  // the partner may still be reading this half
+}
+
 // Direct kernel: one CTA per (roi slot, output row); threads stride over px and channels.
 // VEC = 4 (C % 4 == 0, float4 path) or 1.
 template <int VEC>
@@ -320,6 +462,15 @@ __global__ void __launch_bounds__(256) roi_pool_direct_kernel(RoiPoolParams p) {
             orow[(size_t)px * p.C + c] = lerp1(lerp1(tl, tr, lx), lerp1(bl, br, lx), ly);
         }
     }
+}
+
+template <int LANES>
+static int launch_pair(const RoiPoolParams &p, const CUtensorMap &tmap, int B, size_t smem, cudaStream_t st) {
+    int dev = 0;
+    RADNET_CUDA(cudaGetDevice(&dev));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(roi_pool_pair_kernel<LANES>), dev, smem)) return rc;
+    roi_pool_pair_kernel<LANES><<<2 * B * p.n_slices, kPoolThreads, smem, st>>>(p, tmap);
+    return check_launch("roi_pool_pair_kernel");
 }
 
 template <int LANES>
@@ -403,9 +554,36 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
     if (smem_limit < 0) return RADNET_E_CUDA;
     const size_t HW = (size_t)H * W;
     const size_t per_roi = (size_t)pool * sizeof(YEntry) + sizeof(int2);
+    const long long form = get_option(kOptRoipoolForm);          // 0 auto, 1 whole-map slices, 2 cluster pairs
     if (C % 4 == 0 && !force_direct() && HW < 65536 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const int C4 = C / 4;
+        // pair form (32-channel slices, half the rows per CTA of a cluster of two): when the whole-map form cannot
+        // keep 32 channels in one CTA, or on request
+        const int Hh = (H + 1) / 2;
+        const size_t half_bytes = ((size_t)Hh * W + 1) * 8 * 16;
+        const size_t whole8 = (HW + 1) * 8 * 16 + ((size_t)W + 1) * sizeof(float) + 16 + 8 * per_roi;
+        const bool pair_fits = C4 % 8 == 0 && W <= 256 && Hh <= 256 && H >= 2 && encode_tiled_fn() &&
+                               half_bytes + ((size_t)W + 1) * sizeof(float) + 16 + 8 * per_roi <= (size_t)smem_limit &&
+                               2LL * B * (C4 / 8) < 0x7fffffffLL;
+        if (pair_fits && (form == 2 || (form == 0 && whole8 > (size_t)smem_limit))) {
+            const size_t scale_bytes = ((size_t)W + 1) * sizeof(float) + 16;
+            // two CTAs per SM when a half is small enough: cap the shared memory at half an SM
+            size_t budget = (size_t)smem_limit;
+            if (2 * (half_bytes + scale_bytes + 32 * per_roi + 1024) <= (size_t)smem_limit + 1024)
+                budget = ((size_t)smem_limit + 1024) / 2 - 1024;
+            size_t chunk = (budget - half_bytes - scale_bytes) / per_roi;
+            if (chunk > (size_t)rois_per_panel) chunk = rois_per_panel;
+            alignas(64) CUtensorMap tmap;
+            memset(&tmap, 0, sizeof(tmap));
+            if (chunk >= 1 && make_map_tensor(&tmap, feat, B, H, W, C, 8, Hh)) {
+                p.n_slices = C4 / 8;
+                p.roi_chunk = (int)chunk;
+                p.map_rows_pad = Hh;
+                p.tma_rows = Hh;
+                return launch_pair<8>(p, tmap, B, half_bytes + chunk * per_roi + scale_bytes, st);
+            }
+        }
         const int lanes_opts[4] = {8, 4, 2, 1};
         const int box_rows = (W <= 256 && encode_tiled_fn()) ? tma_box_rows(H) : 0;
         const int rows_pad = box_rows ? (H + box_rows - 1) / box_rows * box_rows : H;

@@ -332,6 +332,40 @@ def test_roi_pooling_conv_vs_oracle(pkg, H, W, Cn, pool):
     assert np.array_equal(got, ref), "expected bit-exact float32 (no FMA contraction)"
 
 
+@pytest.mark.parametrize("H,W,Cn,pool", [(38, 38, 1024, 14), (38, 50, 1024, 14), (38, 38, 512, 7), (37, 41, 64, 14),
+                                         (2, 3, 32, 2), (75, 75, 32, 7)])
+def test_roi_pooling_cluster_pair_form_matches(pkg, lib_option, H, W, Cn, pool):
+    """The pair form (a cluster of two CTAs holds half of the map rows each; taps on the other half go through
+    distributed shared memory) on even / odd row counts, and as the automatic choice for 38x50."""
+    lib_option("roipool_form", 2)
+    feat = S.feature_map(4, H, W, Cn)
+    rois = _all_size_rois(H, W)
+    got = pkg.RoiPoolingConv(pool, rois.shape[1])([feat, rois])
+    assert np.array_equal(got, O.roi_pooling_conv(feat, rois, pool))
+
+
+def test_roi_pooling_pair_form_batch_with_empty_slots(pkg, lib_option):
+    """Batched call through the detection records (slots beyond the kept count must be zero-filled)."""
+    from rock_art_radnet_b200.pipeline import ProposalPipeline
+    C = S.HotPathConfig()
+    B, H, W = 3, 38, 50
+    maps = [S.rpn_maps(60 + s, H, W, 9) for s in range(B)]
+    feat = torch.from_numpy(np.concatenate([S.feature_map(60 + s, H, W, 64) for s in range(B)])).cuda()
+    outs = []
+    for form in (1, 2):
+        lib_option("roipool_form", form)
+        pipe = ProposalPipeline(C, B, H, W, channels=64, pool_size=14, max_boxes=40, overlap_thresh=0.3)
+        pipe.decode(torch.from_numpy(np.concatenate([m[0] for m in maps])).cuda(),
+                    torch.from_numpy(np.concatenate([m[1] for m in maps])).cuda())
+        pipe.sort_nms()
+        pipe.pooled.fill_(7.0)
+        outs.append(pipe.pool(feat).clone())
+        counts = pipe.records.counts.cpu().numpy()
+    assert torch.equal(outs[0], outs[1])
+    for b in range(B):
+        assert bool((outs[1][b, int(counts[b]):] == 0).all())
+
+
 def test_roi_pooling_direct_kernel_matches(pkg, lib_option):
     lib_option("roipool_force_direct", 1)
     feat = S.feature_map(2, 38, 38, 256)

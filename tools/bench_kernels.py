@@ -263,10 +263,14 @@ def main():
         pipe.decode(cls, regr)
         pipe.sort_nms()
         kept = int(pipe.records.counts.sum().item())
-        t = time_ms(lambda: pipe.pool(feat), iters=10)
         nbytes = B * Hh * Ww * Cn * 4 + kept * 16 + kept * pool * pool * Cn * 4
-        res["roi_pool_%s_B%d" % (tag, B)] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
-                                                  frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk)
+        from rock_art_radnet_b200 import _lib
+        for form, ftag in ((0, ""), (1, "_whole_map_form"), (2, "_pair_form")):
+            _lib.set_option("roipool_form", form)
+            t = time_ms(lambda: pipe.pool(feat), iters=10)
+            res["roi_pool_%s_B%d%s" % (tag, B, ftag)] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
+                                                           frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk)
+        _lib.set_option("roipool_form", 0)
         del pipe, feat
         torch.cuda.empty_cache()
 

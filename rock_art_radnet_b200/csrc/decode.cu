@@ -23,8 +23,8 @@
 
 namespace radnet {
 
-constexpr int kDecodeCells = 64;      // cells per CTA
-static_assert(kDecodeCells == 64, "the write-out loop shifts by 6");
+constexpr int kDecodeCells = 128;     // cells per CTA (4.5 anchors per thread at A = 9: loads of several anchors in flight)
+static_assert(kDecodeCells == 128, "the write-out loop shifts by 7");
 constexpr int kDecodeThreads = 256;
 
 struct DecodedBox {
@@ -108,7 +108,7 @@ __device__ __forceinline__ bool decode_fast(int c, int r, float wf, float hf, fl
 }
 
 template <bool kF64>
-__global__ void __launch_bounds__(kDecodeThreads)
+__global__ void __launch_bounds__(kDecodeThreads, kF64 ? 2 : 5)
 decode_clip_kernel(const float *__restrict__ cls, const float *__restrict__ regr, int H, int W,
                    int A, unsigned magic_a, unsigned magic_w, AnchorTable anchors, float std_scaling, int use_regr,
                    int32_t *__restrict__ boxes_i32, uint32_t *__restrict__ keys,
@@ -196,7 +196,7 @@ decode_clip_kernel(const float *__restrict__ cls, const float *__restrict__ regr
 
     // transposed, coalesced write-out: anchor-major rows of ncell entries
     for (int p = threadIdx.x; p < ncell * A; p += kDecodeThreads) {
-        const int a = (ncell == kDecodeCells) ? (p >> 6) : p / ncell;
+        const int a = (ncell == kDecodeCells) ? (p >> 7) : p / ncell;
         const int cl = p - a * ncell;
         size_t o = (size_t)b * N + (size_t)a * HW + cell0 + cl;
         if (kF64) {

@@ -60,8 +60,8 @@ def keras_stubs(monkeypatch):
     tf.numpy_function = numpy_function
     for name, mod in (("keras", keras), ("keras.engine", engine), ("keras.engine.topology", topology), ("tensorflow", tf)):
         monkeypatch.setitem(sys.modules, name, mod)
-    import rock_art_radnet_b200.RoiPoolingConv as M
-    M = importlib.reload(M)
+    # the package re-exports the class under the submodule's name, so `import a.b as M` would bind the class
+    M = importlib.reload(importlib.import_module("rock_art_radnet_b200.RoiPoolingConv"))
     yield M, calls
     for name in ("keras", "keras.engine", "keras.engine.topology", "tensorflow"):
         monkeypatch.delitem(sys.modules, name, raising=False)
@@ -84,7 +84,7 @@ def test_roi_pooling_conv_is_a_keras_layer_when_keras_imports(keras_stubs):
 
 
 def test_roi_pooling_conv_without_keras_is_a_plain_callable():
-    import rock_art_radnet_b200.RoiPoolingConv as M
+    M = importlib.import_module("rock_art_radnet_b200.RoiPoolingConv")
     if M._LayerBase is not object:
         pytest.skip("a real Keras is installed")
     layer = M.RoiPoolingConv(7, 4)

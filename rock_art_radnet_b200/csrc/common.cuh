@@ -57,6 +57,12 @@ enum Option {
     kOptSamplerForceExact,   // sampler_force_exact: 0/1 (always the serial cumsum chain)
     kOptTargetsComputeCtas,  // targets_compute_ctas: 0 auto (43 % of the SMs)
     kOptTargetsTwoLaunches,  // targets_two_launches: 0/1 (fill and panels as two launches)
+    kOptRoipoolBands,        // roipool_bands: 0 auto, else the number of row bands of the band form
+    kOptRoipoolLanes,        // roipool_lanes: 0 auto (8), else 8 / 16 / 32 float4 lanes per pixel in the band form
+    kOptRoipoolPace,         // roipool_pace: ns slept per output column in the whole-map form (-1 auto, 0 none)
+    kOptRoipoolCluster,      // roipool_cluster: 0 none, 2 / 4 / 8 CTAs (neighbouring slices) per cluster in the whole-map form
+    kOptRoipoolSyncEvery,    // roipool_sync_every: cluster barrier every this many column rounds (0 = 2)
+    kOptRoipoolCtas,         // roipool_ctas: whole-map form with this many persistent CTAs (0 = one CTA per work item)
     kOptCount
 };
 long long get_option(int opt);
@@ -216,6 +222,10 @@ __device__ __forceinline__ void bulk_s2s_cluster(uint32_t remote_dst, const void
 // make generic-proxy shared-memory writes visible to the async proxy (bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// pacing barrier of a cluster (no data is exchanged): may be executed by partly diverged warps
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed;\nbarrier.cluster.wait;" ::: "memory");
 }
 // all threads of all CTAs of the cluster; release/acquire makes the DSMEM stores visible
 __device__ __forceinline__ void cluster_sync_all() {

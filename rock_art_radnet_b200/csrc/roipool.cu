@@ -25,11 +25,17 @@
 #include <cuda.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace radnet {
 
-constexpr int kPoolThreads = 512;
+#ifndef RADNET_POOL_THREADS
+#define RADNET_POOL_THREADS 512
+#endif
+constexpr int kSliceThreads = RADNET_POOL_THREADS;   // whole-map form (one CTA per SM)
+constexpr int kPoolThreads = 512;                    // band form (two CTAs per SM)
 constexpr int kMaxPool = 32;
 
 struct RoiPoolParams {
@@ -47,6 +53,12 @@ struct RoiPoolParams {
     int roi_chunk;           // RoIs whose y tables fit in shared memory at once
     int map_rows_pad;        // map rows held in shared memory (>= H: whole TMA boxes)
     int tma_rows;            // map rows per TMA box (0 = stage with cp.async)
+    int band_rows, n_bands;  // band form: source rows owned by a band, bands per map
+    int pace;                // whole-map form: nanoseconds a group sleeps after each output column (0 = none)
+    int grid;                // whole-map form: CTAs launched
+    int n_work;              // whole-map form: (panel, slice) work items; the grid may be smaller (persistent CTAs)
+    int cluster;             // whole-map form: CTAs per cluster (neighbouring slices of a panel), 1 = no cluster
+    int sync_every;          // whole-map form in clusters: cluster barrier every this many column rounds (0 = never)
 };
 
 // global -> shared TMA tile copy of a rank-4 tensor, completion (bytes) on an mbarrier
@@ -59,21 +71,30 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *t
 }
 
 // Per (RoI, output row) entry of the y table, 8 bytes = one LDS.64.
-//   bits  0..15  pixel index of the first cell of source row y+y0  ((y+y0)*W)
-//   bit   16     1 when y1 = y0+1 (else y1 = y0)
-//   bits 28..30  what the row cache has to do relative to the previous output row (kAct*)
+//   bits  0..23  byte offset, inside the staged slice, of the first cell of source row y+y0
+//   bits 27..31  what the two cached source rows have to do before this output row (kRow*)
+// A column keeps h0 = hrow(y0) and h1 = hrow(y1) in registers (hrow(r) = tl + (tr-tl)*xlerp of source row r).
 struct YEntry {
     unsigned code;
     float lerp;
 };
 enum : unsigned {
-    kActKeep = 0,      // same two source rows as the previous output row
-    kActShift = 1,     // y0 = previous y1, new y1: h0 <- h1, sample h1
-    kActShiftDup = 2,  // y0 = y1 = previous y1: h0 <- h1
-    kActBoth = 3,      // sample both rows
-    kActOneDup = 4,    // y0 = y1, new row: sample h0, h1 <- h0
-    kActExtend = 5     // y0 kept, previous rows were equal, new y1: sample h1
+    kRowAny = 1u << 31,      // something changes (sign bit: one compare)
+    kRowShift = 1u << 30,    // h0 <- h1           (y0 = previous y1)
+    kRowS0 = 1u << 29,       // h0 <- hrow(y0)     sampled
+    kRowDup = 1u << 28,      // h1 <- h0           (y1 = y0)
+    kRowS1 = 1u << 27,       // h1 <- hrow(y0 + 1) sampled
+    kRowOffMask = (1u << 24) - 1u
 };
+
+// the update the row cache needs going from source rows (plo, phi) to (lo, hi); first = no previous row
+__device__ __forceinline__ unsigned row_action(bool first, int lo, int hi, int plo, int phi) {
+    if (first) return kRowAny | kRowS0 | (hi == lo ? kRowDup : kRowS1);
+    if (lo == plo && hi == phi) return 0u;                                   // same two rows
+    if (lo == phi && phi != plo) return kRowAny | kRowShift | (hi != lo ? kRowS1 : 0u);
+    if (lo == plo && phi == plo && hi != lo) return kRowAny | kRowS1;        // rows were equal, new y1
+    return kRowAny | kRowS0 | (hi == lo ? kRowDup : kRowS1);
+}
 
 // RoI k of panel b as (x,y,w,h), already int32-truncated by the caller (RoiPoolingConv.py:69-72);
 // returns false for empty slots / RoIs that crop to nothing
@@ -110,30 +131,37 @@ __device__ __forceinline__ float lerp1(float a, float b, float t) {
     return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
 }
 
-// a + (b-a)*t on two lanes at once: packed subtract and multiply (FADD2/FMUL2), SCALAR final
-// adds.  ptxas 12.9 contracts a packed multiply feeding a packed add into FFMA2 even for
-// explicitly rounded PTX (and for the __fmul2_rn/__fadd2_rn intrinsics), which would break
-// bit-parity with TF's unfused arithmetic; a scalar add.rn.f32 is never contracted.
-// tests/test_build_sass.py checks the SASS of these kernels for FFMA.
+// a + (b-a)*t on two lanes at once with three packed instructions and NO contraction of the multiply into the
+// add.  ptxas 12.9 contracts a packed multiply feeding a packed add into FFMA2 even for explicitly rounded PTX,
+// which would break bit-parity with TF's unfused arithmetic.  So the product is itself issued as a packed FMA
+// with an addend of -0.0 (d*t + (-0.0) rounds exactly like d*t, signed zeros included; the -0.0 comes from a
+// kernel parameter so that ptxas cannot fold it away), and an FMA result feeding an add cannot be fused again:
+// FADD2 (b-a), FFMA2 (d*t - 0), FADD2 (a + m).  tests/test_build_sass.py checks that the kernels contain no
+// scalar FFMA and no FMUL2; the parity tests check the bits.
 __device__ __forceinline__ void lerp2(float a0, float a1, float b0, float b1, unsigned long long tt,
-                                      float &r0, float &r1) {
-    unsigned long long a, b, d, m;
+                                      unsigned long long nz, float &r0, float &r1) {
+    unsigned long long a, b, d, m, r;
     asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(a0), "f"(a1));
     asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(b0), "f"(b1));
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(b), "l"(a));
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(d), "l"(tt));
-    float m0, m1;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(m0), "=f"(m1) : "l"(m));
-    r0 = __fadd_rn(a0, m0);
-    r1 = __fadd_rn(a1, m1);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(m) : "l"(d), "l"(tt), "l"(nz));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(m));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
 }
-__device__ __forceinline__ float4 lerp4(const float4 &a, const float4 &b, float t) {
+__device__ __forceinline__ float4 lerp4(const float4 &a, const float4 &b, float t, unsigned long long nz) {
     unsigned long long tt;
     asm("mov.b64 %0, {%1,%1};" : "=l"(tt) : "f"(t));
     float4 r;
-    lerp2(a.x, a.y, b.x, b.y, tt, r.x, r.y);
-    lerp2(a.z, a.w, b.z, b.w, tt, r.z, r.w);
+    lerp2(a.x, a.y, b.x, b.y, tt, nz, r.x, r.y);
+    lerp2(a.z, a.w, b.z, b.w, tt, nz, r.z, r.w);
     return r;
+}
+// {-0.0f, -0.0f} that the compiler cannot constant-fold (pool is a kernel parameter, always >= 1)
+__device__ __forceinline__ unsigned long long opaque_neg_zero2(int pool) {
+    const unsigned w = 0x80000000u | ((unsigned)pool >> 31);
+    unsigned long long nz;
+    asm("mov.b64 %0, {%1,%1};" : "=l"(nz) : "r"(w));
+    return nz;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -143,65 +171,138 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// LANES = float4 lanes per pixel in the slice (8 -> 32 channels, 4 -> 16, 2 -> 8, 1 -> 4).
-//
-// Work decomposition: a group of LANES threads owns one output COLUMN (roi, px) and walks
-// py = 0..pool-1.  The horizontal interpolation of a source row, hrow(r) = tl + (tr-tl)*xlerp,
-// does not depend on py, so the two rows an output needs are cached in registers and reused
-// while y0/y1 repeat (always, when the RoI is upsampled: h < pool); only rows that change are
-// re-sampled (2 LDS.128 each).  top/bottom of TF's formula are exactly hrow(y0)/hrow(y1), so
-// the result is bit-identical to evaluating all four taps per output.
-template <int LANES>
-__global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPoolParams p,
+// One output column (roi, px), rows [py0, py1): a group of LANES threads (16 bytes each) walks py.  The
+// horizontal interpolation of a source row, hrow(r) = tl + (tr-tl)*xlerp, does not depend on py, so the two rows
+// an output needs are cached in registers and reused while y0/y1 repeat (always, when the RoI is upsampled:
+// h < pool); only rows that change are re-sampled (2 LDS.128 each).  top/bottom of TF's formula are exactly
+// hrow(y0)/hrow(y1), so the result is bit-identical to evaluating all four taps per output.
+// mapb = this lane's 16 bytes of pixel 0 of the staged slice; xo0/xo1 = byte offsets of the two x taps.
+#ifndef RADNET_POOL_STORE
+#define RADNET_POOL_STORE 0
+#endif
+__device__ __forceinline__ void st_pool_f4(float4 *p, const float4 &v) {
+#if RADNET_POOL_STORE == 0
+    st_stream_f4(p, v);
+#elif RADNET_POOL_STORE == 1
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#elif RADNET_POOL_STORE == 2
+    asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+    asm volatile("st.global.L1::no_allocate.L2::evict_last.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#endif
+}
+
+template <int POOL>
+__device__ __forceinline__ void pool_column(const unsigned char *mapb, const YEntry *yt, int py0, int py1,
+                                            unsigned xo0, unsigned xo1, float lx, unsigned row_step, float4 *dst,
+                                            size_t py_step, unsigned long long nz) {
+    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+    const unsigned char *t0 = mapb + xo0, *t1 = mapb + xo1;         // the two x taps in source row 0
+    auto body = [&](int py) {
+        const YEntry e = yt[py];
+        if ((int)e.code < 0) {
+            const unsigned off = e.code & kRowOffMask;
+            if (e.code & kRowS0)
+                h0 = lerp4(*reinterpret_cast<const float4 *>(t0 + off), *reinterpret_cast<const float4 *>(t1 + off),
+                           lx, nz);
+            else if (e.code & kRowShift)
+                h0 = h1;
+            if (e.code & kRowS1)
+                h1 = lerp4(*reinterpret_cast<const float4 *>(t0 + off + row_step),
+                           *reinterpret_cast<const float4 *>(t1 + off + row_step), lx, nz);
+            else if (e.code & kRowDup)
+                h1 = h0;
+        }
+        st_pool_f4(dst, lerp4(h0, h1, e.lerp, nz));
+        dst += py_step;
+    };
+    if (POOL > 0) {
+#pragma unroll
+        for (int py = 0; py < POOL; ++py) body(py);
+    } else {
+#pragma unroll 2
+        for (int py = py0; py < py1; ++py) body(py);
+    }
+}
+
+// x taps of output column px of a RoI that is cw cells wide and starts at cell x (TF-1 legacy weights with the
+// float32 scale cw/pool taken from a table); cw == 0 marks an empty slot: both taps on the zero pixel
+__device__ __forceinline__ void x_taps(int px, int x, int cw, const float *s_scale, unsigned pix_bytes,
+                                       unsigned zero_off, unsigned &xo0, unsigned &xo1, float &lx) {
+    if (cw > 0) {
+        const float src = __fmul_rn((float)px, s_scale[cw]);
+        const float fl = floorf(src);
+        const int lo = max((int)fl, 0), hi = min((int)ceilf(src), cw - 1);
+        lx = __fsub_rn(src, fl);
+        xo0 = (unsigned)(x + lo) * pix_bytes;
+        xo1 = (unsigned)(x + hi) * pix_bytes;
+    } else {
+        xo0 = xo1 = zero_off;
+        lx = 0.f;
+    }
+}
+
+// LANES = float4 lanes per pixel in the slice (8 -> 32 channels, 4 -> 16, 2 -> 8, 1 -> 4); POOL = compile-time
+// pool size (fully unrolled rows) or 0 for any pool size.
+template <int LANES, int POOL>
+__global__ void __launch_bounds__(kSliceThreads, 1) roi_pool_slice_kernel(RoiPoolParams p,
                                                                           const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;
     constexpr int kPixBytes = LANES * 16;
-    constexpr int G = kPoolThreads / LANES;          // columns in flight per CTA
+    constexpr int G = kSliceThreads / LANES;          // columns in flight per CTA
     const int HW = p.H * p.W;
     const int HWp = p.map_rows_pad * p.W;            // pixels held in shared memory (whole TMA boxes)
-    const int pool = p.pool, PP = pool * pool;
+    const int pool = POOL > 0 ? POOL : p.pool, PP = pool * pool;
     float4 *s_map = reinterpret_cast<float4 *>(smem);                                   // [HWp+1][LANES]
     YEntry *s_ytab = reinterpret_cast<YEntry *>(smem + (size_t)(HWp + 1) * kPixBytes);  // [chunk][pool]
     int2 *s_roi = reinterpret_cast<int2 *>(s_ytab + (size_t)p.roi_chunk * pool);        // [chunk] {x, cw}
     float *s_scale = reinterpret_cast<float *>(s_roi + p.roi_chunk);                    // [W+1] cw / pool (float32 divide)
 
-    const int b = blockIdx.x / p.n_slices;
-    const int s = blockIdx.x - b * p.n_slices;
     const int C4 = p.C >> 2;
     const int q = threadIdx.x % LANES;
     const int g = threadIdx.x / LANES;
+    const unsigned long long nz = opaque_neg_zero2(p.pool);
+    if (threadIdx.x == 0 && p.tma_rows > 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i <= p.W; i += kSliceThreads) s_scale[i] = __fdiv_rn((float)i, (float)p.pool);
+    if (g == 0) s_map[HWp * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);         // the "zero pixel"
+    const unsigned char *mapb = reinterpret_cast<const unsigned char *>(s_map) + q * 16;
+    const size_t py_step = (size_t)pool * C4;
+    const unsigned row_step = (unsigned)p.W * kPixBytes;
+
+    // a CTA takes (panel, slice) work items round robin: with as many CTAs as items this is one item each; with
+    // fewer (a multiple of the slices per panel) every CTA keeps its slice and the slices stay evenly loaded
+    uint32_t phase = 0;
+    for (int work = blockIdx.x; work < p.n_work; work += gridDim.x, phase ^= 1u) {
+    const int b = work / p.n_slices;
+    const int s = work - b * p.n_slices;
+    if (work != (int)blockIdx.x) __syncthreads();          // everybody is done with the previous map
 
     // ---- stage the channel slice of the whole map (read from HBM exactly once) --------
     if (p.tma_rows > 0) {
         // one elected thread: a TMA tile copy per box of `tma_rows` map rows (one box for maps up to 256 rows),
         // all completing on the same mbarrier; everybody else goes straight on to the first y tables
         if (threadIdx.x == 0) {
-            mbar_init(&s_bar, 1);
-            mbar_fence_init();
             const int n_box = p.map_rows_pad / p.tma_rows;
             mbar_expect_tx(&s_bar, (uint32_t)((size_t)HWp * kPixBytes));
             for (int k = 0; k < n_box; ++k)
                 tma_load_4d(reinterpret_cast<unsigned char *>(s_map) + (size_t)k * p.tma_rows * p.W * kPixBytes, &tmap,
                             s * LANES * 4, 0, k * p.tma_rows, b, &s_bar);
         }
-        if (g == 0) s_map[HWp * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);     // the "zero pixel"
-        for (int i = threadIdx.x; i <= p.W; i += kPoolThreads) s_scale[i] = __fdiv_rn((float)i, (float)p.pool);
     } else {
         const float4 *src = reinterpret_cast<const float4 *>(p.feat) + (size_t)b * HW * C4 + (size_t)s * LANES + q;
         for (int pix = g; pix < HW; pix += G) cp_async16(&s_map[pix * LANES + q], src + (size_t)pix * C4);
-        if (g == 0) s_map[HWp * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);     // the "zero pixel"
-        for (int i = threadIdx.x; i <= p.W; i += kPoolThreads) s_scale[i] = __fdiv_rn((float)i, (float)p.pool);
         cp_async_wait_all();
     }
     bool map_ready = p.tma_rows == 0;
-    const unsigned char *mapb = reinterpret_cast<const unsigned char *>(s_map) + q * 16;
-    const size_t py_step = (size_t)pool * C4;
 
     for (int r0 = 0; r0 < p.R; r0 += p.roi_chunk) {
         const int nr = min(p.roi_chunk, p.R - r0);
         __syncthreads();     // previous chunk done with the tables (and the map has landed)
-        for (int e = threadIdx.x; e < nr * pool; e += kPoolThreads) {
+        for (int e = threadIdx.x; e < nr * pool; e += kSliceThreads) {
             int rl = e / pool, i = e - rl * pool;
             int x, y, cw, ch;
             YEntry en;
@@ -210,18 +311,11 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
                 float pl;
                 legacy_axis(i, ch, pool, lo, hi, en.lerp);
                 if (i > 0) legacy_axis(i - 1, ch, pool, plo, phi, pl);
-                unsigned act;
-                if (i == 0) act = (hi == lo) ? kActOneDup : kActBoth;
-                else if (lo == plo && hi == phi) act = kActKeep;
-                else if (lo == phi && hi != lo && phi != plo) act = kActShift;
-                else if (lo == phi && hi == lo && phi != plo) act = kActShiftDup;
-                else if (lo == plo && phi == plo && hi != lo) act = kActExtend;
-                else act = (hi == lo) ? kActOneDup : kActBoth;
-                en.code = (unsigned)((y + lo) * p.W) | ((hi != lo) ? 0x10000u : 0u) | (act << 28);
+                en.code = (unsigned)((y + lo) * p.W) * kPixBytes | row_action(i == 0, lo, hi, plo, phi);
                 if (i == 0) s_roi[rl] = make_int2(x, cw);
             } else {
                 // rows add nothing and the column points at the zero pixel: output is exactly 0
-                en.code = (i == 0) ? (kActOneDup << 28) : (kActKeep << 28);
+                en.code = (i == 0) ? (kRowAny | kRowS0 | kRowDup) : 0u;
                 en.lerp = 0.f;
                 if (i == 0) s_roi[rl] = make_int2(0, 0);
             }
@@ -229,7 +323,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
         }
         __syncthreads();
         if (!map_ready) {            // the barrier above also ordered the mbarrier's initialisation before this wait
-            mbar_wait(&s_bar, 0);
+            mbar_wait(&s_bar, phase);
             map_ready = true;
         }
 
@@ -237,190 +331,146 @@ __global__ void __launch_bounds__(kPoolThreads, 1) roi_pool_slice_kernel(RoiPool
         // (rl, px) advance incrementally by G columns: no integer division in the column loop
         int rl = g / pool, px = g - rl * pool;
         const int d_rl = G / pool, d_px = G - d_rl * pool;
-        for (int col = g; col < ncol; col += G, rl += d_rl, px += d_px) {
+        int it = 0;
+        for (int base = 0; base < ncol; base += G, rl += d_rl, px += d_px, ++it) {
+            // the CTAs of a cluster own neighbouring channel slices of the same panel: keeping them within a few
+            // RoIs of each other makes their 128-byte pieces of an output pixel reach HBM together
+            if (p.sync_every > 0 && it % p.sync_every == 0) cluster_sync_relaxed();
             if (px >= pool) { px -= pool; ++rl; }
+            if (base + g >= ncol) continue;
             const int2 rx = s_roi[rl];
-            int xo0, xo1;
+            unsigned xo0, xo1;
             float lx;
-            if (rx.y > 0) {
-                // TF-1 legacy weights with the float32 scale cw/pool taken from a table
-                const float src = __fmul_rn((float)px, s_scale[rx.y]);
-                const float fl = floorf(src);
-                const int lo = max((int)fl, 0), hi = min((int)ceilf(src), rx.y - 1);
-                lx = __fsub_rn(src, fl);
-                xo0 = (rx.x + lo) * kPixBytes;
-                xo1 = (rx.x + hi) * kPixBytes;
-            } else {
-                xo0 = xo1 = HWp * kPixBytes;
-                lx = 0.f;
-            }
-            const YEntry *yt = s_ytab + rl * pool;
+            x_taps(px, rx.x, rx.y, s_scale, kPixBytes, (unsigned)HWp * kPixBytes, xo0, xo1, lx);
             float4 *dst = reinterpret_cast<float4 *>(p.out) +
                           (((size_t)b * p.R + r0 + rl) * PP + px) * C4 + (size_t)s * LANES + q;
-            const int row_step = p.W * kPixBytes;
-            float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
-#pragma unroll 2
-            for (int py = 0; py < pool; ++py) {
-                const YEntry e = yt[py];
-                const unsigned act = e.code >> 28;
-                if (act != kActKeep) {
-                    const unsigned char *row = mapb + (e.code & 0xFFFFu) * kPixBytes;
-                    if (act == kActShift || act == kActShiftDup) h0 = h1;
-                    if (act == kActBoth || act == kActOneDup)
-                        h0 = lerp4(*reinterpret_cast<const float4 *>(row + xo0),
-                                   *reinterpret_cast<const float4 *>(row + xo1), lx);
-                    if (act == kActOneDup) h1 = h0;
-                    if (act == kActShift || act == kActBoth || act == kActExtend)
-                        h1 = lerp4(*reinterpret_cast<const float4 *>(row + row_step + xo0),
-                                   *reinterpret_cast<const float4 *>(row + row_step + xo1), lx);
-                }
-                st_stream_f4(dst, lerp4(h0, h1, e.lerp));
-                dst += py_step;
-            }
+            pool_column<POOL>(mapb, s_ytab + rl * pool, 0, pool, xo0, xo1, lx, row_step, dst, py_step, nz);
+            // pacing (see the launcher): the HBM write stream loses ~10 % when every SM pushes stores as fast as it
+            // can issue them; a short sleep per column costs no issue slots
+            if (p.pace > 0) __nanosleep((unsigned)p.pace);
         }
     }
+    }   // work items
 }
 
-// ---- pair form: a cluster of two CTAs holds one channel slice, half of the map rows each --------------------
+// ---- band form: a CTA holds a band of map rows and emits the output rows that sample it -----------------------
 // For maps whose 32-channel slice does not fit one CTA's shared memory (600x800 px: 38*50*128 B = 243 KB) the
-// whole-map form had to fall back to 16-channel slices: 64-byte store segments, twice the CTAs (0.83 of the HBM
-// peak instead of 0.95).  Here CTA `rank` of a cluster of two stages rows [rank*Hh, rank*Hh + Hh) of the slice
-// (one TMA tile copy each) and the pair splits the output columns; a bilinear tap on a row of the other half is
-// a distributed-shared-memory load (ld.shared::cluster on the mapa-translated address).  Store lines stay 128
-// bytes, and when a half is small enough (38x38: 92 KB) two CTAs share an SM, so the staging of one cluster
-// overlaps the store stream of another.
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
+// whole-map form has to fall back to 16-channel slices: 64-byte store segments, twice the CTAs (0.84 of the HBM
+// peak instead of 0.96).  (A cluster of two CTAs holding half of the rows each, with the taps on the other half
+// going through distributed shared memory, was measured at 0.53-0.55: remote LDS.128 taps are too slow.)
+// Here the map rows are cut into `n_bands` bands of `band_rows` rows.  Output row py of a RoI samples source rows
+// ya = y + lo(py) and ya or ya + 1, so it belongs to exactly one band, ya / band_rows, and the CTA of that band
+// stages band_rows + 1 rows (one TMA tile copy; rows below the map are zero-filled by the TMA unit and never
+// sampled).  Every CTA of a (panel, slice) walks all RoIs but only the py range that falls into its band (ya is
+// non-decreasing in py, so the range is contiguous; RoIs without a row in the band are dropped from the column
+// list).  No data crosses CTAs, store lines stay 128 bytes, the map is read (band_rows+1)/band_rows times, and
+// two CTAs share an SM, so the staging of one overlaps the store stream of the other.
 template <int LANES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPoolThreads, 1)
-    roi_pool_pair_kernel(RoiPoolParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kPoolThreads, 2) roi_pool_band_kernel(RoiPoolParams p,
+                                                                         const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_nlive;
     constexpr int kPixBytes = LANES * 16;
     constexpr int G = kPoolThreads / LANES;          // columns in flight per CTA
-    const int Hh = p.tma_rows;                       // map rows per half
-    const int HWh = Hh * p.W;                        // pixels of a half (whole TMA box)
+    const int Hb = p.band_rows;
+    const int HWb = p.tma_rows * p.W;                // pixels staged (band_rows + 1 rows = one TMA box)
     const int pool = p.pool, PP = pool * pool;
-    float4 *s_map = reinterpret_cast<float4 *>(smem);                                   // [HWh+1][LANES]
-    YEntry *s_ytab = reinterpret_cast<YEntry *>(smem + (size_t)(HWh + 1) * kPixBytes);  // [chunk][pool]
-    int2 *s_roi = reinterpret_cast<int2 *>(s_ytab + (size_t)p.roi_chunk * pool);        // [chunk] {x, cw}
-    float *s_scale = reinterpret_cast<float *>(s_roi + p.roi_chunk);                    // [W+1] cw / pool (float32 divide)
+    float4 *s_map = reinterpret_cast<float4 *>(smem);                                   // [HWb+1][LANES]
+    int4 *s_roi = reinterpret_cast<int4 *>(smem + (size_t)(HWb + 1) * kPixBytes);       // [chunk] {x, cw, py_lo, py_hi}
+    YEntry *s_ytab = reinterpret_cast<YEntry *>(s_roi + p.roi_chunk);                   // [chunk][pool]
+    int *s_live = reinterpret_cast<int *>(s_ytab + (size_t)p.roi_chunk * pool);         // [chunk] RoIs with rows here
+    float *s_scale = reinterpret_cast<float *>(s_live + p.roi_chunk);                   // [W+1] cw / pool (float32 divide)
 
-    const int rank = (int)cluster_ctarank();
-    const int pairi = blockIdx.x >> 1;
-    const int b = pairi / p.n_slices;
-    const int s = pairi - b * p.n_slices;
+    const int band = blockIdx.x % p.n_bands;
+    const int bs = blockIdx.x / p.n_bands;
+    const int b = bs / p.n_slices;
+    const int s = bs - b * p.n_slices;
     const int C4 = p.C >> 2;
     const int q = threadIdx.x % LANES;
     const int g = threadIdx.x / LANES;
+    const int row_base = band * Hb;
+    const unsigned long long nz = opaque_neg_zero2(p.pool);
 
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         mbar_fence_init();
-        mbar_expect_tx(&s_bar, (uint32_t)((size_t)HWh * kPixBytes));
-        // rows beyond the map (second half of an odd H) are zero-filled by the TMA unit
-        tma_load_4d(s_map, &tmap, s * LANES * 4, 0, rank * Hh, b, &s_bar);
+        mbar_expect_tx(&s_bar, (uint32_t)((size_t)HWb * kPixBytes));
+        tma_load_4d(s_map, &tmap, s * LANES * 4, 0, row_base, b, &s_bar);
     }
-    if (g == 0) s_map[HWh * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);         // the "zero pixel"
+    if (g == 0) s_map[HWb * LANES + q] = make_float4(0.f, 0.f, 0.f, 0.f);         // the "zero pixel"
     for (int i = threadIdx.x; i <= p.W; i += kPoolThreads) s_scale[i] = __fdiv_rn((float)i, (float)p.pool);
     const unsigned char *mapb = reinterpret_cast<const unsigned char *>(s_map) + q * 16;
-    const uint32_t peer = cluster_map_shared(mapb, (uint32_t)(rank ^ 1));
     const size_t py_step = (size_t)pool * C4;
+    const unsigned row_step = (unsigned)p.W * kPixBytes;
     bool map_ready = false;
-
-    // a tap: 16 bytes at `off` inside the half `owner` of the slice
-    auto tap = [&](int owner, unsigned off) -> float4 {
-        return owner == rank ? *reinterpret_cast<const float4 *>(mapb + off) : ld_dsmem_f4(peer + off);
-    };
 
     for (int r0 = 0; r0 < p.R; r0 += p.roi_chunk) {
         const int nr = min(p.roi_chunk, p.R - r0);
         __syncthreads();     // previous chunk done with the tables
+        for (int rl = threadIdx.x; rl < nr; rl += kPoolThreads) s_roi[rl] = make_int4(0, 0, 0, 0);
+        __syncthreads();
         for (int e = threadIdx.x; e < nr * pool; e += kPoolThreads) {
             int rl = e / pool, i = e - rl * pool;
             int x, y, cw, ch;
             YEntry en;
+            en.code = 0u;
+            en.lerp = 0.f;
             if (fetch_roi(p, b, r0 + rl, x, y, cw, ch)) {
-                int lo, hi, plo = -1, phi = -1;
+                int lo, hi, plo = -1, phi = -1, nlo = -1, nhi;
                 float pl;
                 legacy_axis(i, ch, pool, lo, hi, en.lerp);
                 if (i > 0) legacy_axis(i - 1, ch, pool, plo, phi, pl);
-                unsigned act;
-                if (i == 0) act = (hi == lo) ? kActOneDup : kActBoth;
-                else if (lo == plo && hi == phi) act = kActKeep;
-                else if (lo == phi && hi != lo && phi != plo) act = kActShift;
-                else if (lo == phi && hi == lo && phi != plo) act = kActShiftDup;
-                else if (lo == plo && phi == plo && hi != lo) act = kActExtend;
-                else act = (hi == lo) ? kActOneDup : kActBoth;
-                // absolute source row y + lo; the kernel splits it into (half, row inside the half)
-                en.code = (unsigned)(y + lo) | ((hi != lo) ? 0x10000u : 0u) | (act << 28);
-                if (i == 0) s_roi[rl] = make_int2(x, cw);
-            } else {
-                en.code = (i == 0) ? (kActOneDup << 28) : (kActKeep << 28);
-                en.lerp = 0.f;
-                if (i == 0) s_roi[rl] = make_int2(0, 0);
+                if (i + 1 < pool) legacy_axis(i + 1, ch, pool, nlo, nhi, pl);
+                const int ya = y + lo;
+                if (ya / Hb == band) {
+                    const bool first = i == 0 || (y + plo) / Hb != band;
+                    const bool last = i + 1 == pool || (y + nlo) / Hb != band;
+                    en.code = (unsigned)((ya - row_base) * p.W) * kPixBytes | row_action(first, lo, hi, plo, phi);
+                    if (first) { s_roi[rl].x = x; s_roi[rl].y = cw; s_roi[rl].z = i; }
+                    if (last) s_roi[rl].w = i + 1;
+                }
+            } else if (band == 0) {
+                // empty slot: band 0 writes its zeros (rows add nothing and the column points at the zero pixel)
+                if (i == 0) { en.code = kRowAny | kRowS0 | kRowDup; s_roi[rl].z = 0; }
+                if (i + 1 == pool) s_roi[rl].w = pool;
             }
             s_ytab[e] = en;
         }
         __syncthreads();
+        if (threadIdx.x < 32) {          // ordered list of the RoIs of this chunk that have rows in this band
+            int n = 0;
+            for (int base = 0; base < nr; base += 32) {
+                const int rl = base + (int)threadIdx.x;
+                const bool live = rl < nr && s_roi[rl].w > s_roi[rl].z;
+                const unsigned m = __ballot_sync(0xffffffffu, live);
+                if (live) s_live[n + __popc(m & ((1u << threadIdx.x) - 1u))] = rl;
+                n += __popc(m);
+            }
+            if (threadIdx.x == 0) s_nlive = n;
+        }
+        __syncthreads();
         if (!map_ready) {
-            mbar_wait(&s_bar, 0);        // my half has landed ...
-            cluster_sync_all();          // ... and so has the partner's
+            mbar_wait(&s_bar, 0);
             map_ready = true;
         }
 
-        const int ncol = nr * pool;
-        // the pair walks the columns 2G at a time: CTA `rank` takes the rank-th group of G
-        const int g2 = g + rank * G;
-        int rl = g2 / pool, px = g2 - rl * pool;
-        const int d_rl = (2 * G) / pool, d_px = 2 * G - d_rl * pool;
-        for (int col = g2; col < ncol; col += 2 * G, rl += d_rl, px += d_px) {
-            while (px >= pool) { px -= pool; ++rl; }
-            const int2 rx = s_roi[rl];
-            const bool live = rx.y > 0;
-            unsigned xo0 = 0, xo1 = 0;
-            float lx = 0.f;
-            if (live) {
-                const float src = __fmul_rn((float)px, s_scale[rx.y]);
-                const float fl = floorf(src);
-                const int lo = max((int)fl, 0), hi = min((int)ceilf(src), rx.y - 1);
-                lx = __fsub_rn(src, fl);
-                xo0 = (unsigned)(rx.x + lo) * kPixBytes;
-                xo1 = (unsigned)(rx.x + hi) * kPixBytes;
-            }
-            const YEntry *yt = s_ytab + rl * pool;
+        const int ncol = s_nlive * pool;
+        int li = g / pool, px = g - li * pool;
+        const int d_li = G / pool, d_px = G - d_li * pool;
+        for (int col = g; col < ncol; col += G, li += d_li, px += d_px) {
+            if (px >= pool) { px -= pool; ++li; }
+            const int rl = s_live[li];
+            const int4 rx = s_roi[rl];
+            unsigned xo0, xo1;
+            float lx;
+            x_taps(px, rx.x, rx.y, s_scale, kPixBytes, (unsigned)HWb * kPixBytes, xo0, xo1, lx);
             float4 *dst = reinterpret_cast<float4 *>(p.out) +
-                          (((size_t)b * p.R + r0 + rl) * PP + px) * C4 + (size_t)s * LANES + q;
-            const unsigned row_bytes = (unsigned)p.W * kPixBytes;
-            float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
-#pragma unroll 2
-            for (int py = 0; py < pool; ++py) {
-                const YEntry e = yt[py];
-                const unsigned act = e.code >> 28;
-                if (act != kActKeep && live) {
-                    const int ya = (int)(e.code & 0xFFFFu), yb = ya + 1;           // absolute rows y0 and y0 + 1
-                    const int oa = ya >= Hh, ob = yb >= Hh;
-                    const unsigned ra = (unsigned)(ya - oa * Hh) * row_bytes, rb = (unsigned)(yb - ob * Hh) * row_bytes;
-                    if (act == kActShift || act == kActShiftDup) h0 = h1;
-                    if (act == kActBoth || act == kActOneDup) h0 = lerp4(tap(oa, ra + xo0), tap(oa, ra + xo1), lx);
-                    if (act == kActOneDup) h1 = h0;
-                    if (act == kActShift || act == kActBoth || act == kActExtend)
-                        h1 = lerp4(tap(ob, rb + xo0), tap(ob, rb + xo1), lx);
-                }
-                st_stream_f4(dst, lerp4(h0, h1, e.lerp));
-                dst += py_step;
-            }
+                          (((size_t)b * p.R + r0 + rl) * PP + (size_t)rx.z * pool + px) * C4 + (size_t)s * LANES + q;
+            pool_column<0>(mapb, s_ytab + rl * pool, rx.z, rx.w, xo0, xo1, lx, row_step, dst, py_step, nz);
         }
     }
-    if (!map_ready) {                    // no chunk at all (R == 0 cannot happen, but never leave the partner waiting)
-        mbar_wait(&s_bar, 0);
-        cluster_sync_all();
-    }
-    cluster_sync_all();                  // the partner may still be reading this half
+    if (!map_ready) mbar_wait(&s_bar, 0);      // never exit with the tile copy in flight
 }
 
 // Direct kernel: one CTA per (roi slot, output row); threads stride over px and channels.
@@ -434,6 +484,7 @@ __global__ void __launch_bounds__(256) roi_pool_direct_kernel(RoiPoolParams p) {
     int x, y, cw, ch;
     const bool ok = fetch_roi(p, b, k, x, y, cw, ch);
     const int CV = p.C / VEC;
+    const unsigned long long nz = opaque_neg_zero2(p.pool);
     float *orow = p.out + ((size_t)slot * pool + py) * pool * p.C;
     if (!ok) {
         for (int i = threadIdx.x; i < pool * p.C; i += blockDim.x) orow[i] = 0.f;
@@ -455,7 +506,7 @@ __global__ void __launch_bounds__(256) roi_pool_direct_kernel(RoiPoolParams p) {
             const float4 bl = __ldg(reinterpret_cast<const float4 *>(r1 + (size_t)x0 * p.C) + c);
             const float4 br = __ldg(reinterpret_cast<const float4 *>(r1 + (size_t)x1 * p.C) + c);
             st_stream_f4(reinterpret_cast<float4 *>(orow + (size_t)px * p.C) + c,
-                         lerp4(lerp4(tl, tr, lx), lerp4(bl, br, lx), ly));
+                         lerp4(lerp4(tl, tr, lx, nz), lerp4(bl, br, lx, nz), ly, nz));
         } else {
             float tl = __ldg(r0 + (size_t)x0 * p.C + c), tr = __ldg(r0 + (size_t)x1 * p.C + c);
             float bl = __ldg(r1 + (size_t)x0 * p.C + c), br = __ldg(r1 + (size_t)x1 * p.C + c);
@@ -465,21 +516,47 @@ __global__ void __launch_bounds__(256) roi_pool_direct_kernel(RoiPoolParams p) {
 }
 
 template <int LANES>
-static int launch_pair(const RoiPoolParams &p, const CUtensorMap &tmap, int B, size_t smem, cudaStream_t st) {
+static int launch_band(const RoiPoolParams &p, const CUtensorMap &tmap, int B, size_t smem, cudaStream_t st) {
     int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(roi_pool_pair_kernel<LANES>), dev, smem)) return rc;
-    roi_pool_pair_kernel<LANES><<<2 * B * p.n_slices, kPoolThreads, smem, st>>>(p, tmap);
-    return check_launch("roi_pool_pair_kernel");
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(roi_pool_band_kernel<LANES>), dev, smem)) return rc;
+    roi_pool_band_kernel<LANES><<<B * p.n_slices * p.n_bands, kPoolThreads, smem, st>>>(p, tmap);
+    return check_launch("roi_pool_band_kernel");
 }
 
-template <int LANES>
-static int launch_slice(const RoiPoolParams &p, const CUtensorMap &tmap, int B, size_t smem, cudaStream_t st) {
+template <int LANES, int POOL>
+static int launch_slice_pool(const RoiPoolParams &p, const CUtensorMap &tmap, int B, size_t smem, cudaStream_t st) {
     int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(roi_pool_slice_kernel<LANES>), dev, smem)) return rc;
-    roi_pool_slice_kernel<LANES><<<B * p.n_slices, kPoolThreads, smem, st>>>(p, tmap);
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(roi_pool_slice_kernel<LANES, POOL>), dev, smem))
+        return rc;
+    if (p.cluster > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)p.grid);
+        cfg.blockDim = dim3(kSliceThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        RADNET_CUDA(cudaLaunchKernelEx(&cfg, roi_pool_slice_kernel<LANES, POOL>, p, tmap));
+        return check_launch("roi_pool_slice_kernel (cluster)");
+    }
+    roi_pool_slice_kernel<LANES, POOL><<<p.grid, kSliceThreads, smem, st>>>(p, tmap);
     return check_launch("roi_pool_slice_kernel");
+}
+// the reference's two pool sizes (14: ResNet-50, 7: VGG-16) have their rows fully unrolled
+template <int LANES>
+static int launch_slice(const RoiPoolParams &p, const CUtensorMap &tmap, int B, size_t smem, cudaStream_t st) {
+#ifndef RADNET_POOL_NO_UNROLL
+    if (p.pool == 14) return launch_slice_pool<LANES, 14>(p, tmap, B, smem, st);
+    if (p.pool == 7) return launch_slice_pool<LANES, 7>(p, tmap, B, smem, st);
+#endif
+    return launch_slice_pool<LANES, 0>(p, tmap, B, smem, st);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -524,6 +601,64 @@ static int tma_box_rows(int H) {
     return best;
 }
 
+
+// ---- automatic pacing of the whole-map form ---------------------------------------------------------------------
+// The HBM write path of B200 delivers less when it is oversubscribed: a plain fill kernel writes 6.05 TB/s from 120
+// SMs and 5.78 TB/s from 148 (profiles/r02_fill_bw.log), cudaMemsetAsync 6.8-7.3 TB/s.  K4 needs all SMs (one SM
+// sustains ~46 GB/s of 16-byte stores), so instead of using fewer SMs every group sleeps a little after each
+// output column; the best sleep depends on the shape and on the clocks, so it is measured, not guessed.
+struct PaceKey {
+    int dev, B, H, W, C, pool, R, lanes;
+    bool operator==(const PaceKey &o) const {
+        return dev == o.dev && B == o.B && H == o.H && W == o.W && C == o.C && pool == o.pool && R == o.R && lanes == o.lanes;
+    }
+};
+struct PaceEntry {
+    PaceKey key;
+    int pace;
+};
+static std::mutex g_pace_mutex;
+static PaceEntry g_pace[128];
+static int g_pace_n = 0;
+
+static int cached_pace(const PaceKey &k) {
+    std::lock_guard<std::mutex> lock(g_pace_mutex);
+    for (int i = 0; i < g_pace_n; ++i)
+        if (g_pace[i].key == k) return g_pace[i].pace;
+    return -1;
+}
+static void store_pace(const PaceKey &k, int pace) {
+    std::lock_guard<std::mutex> lock(g_pace_mutex);
+    for (int i = 0; i < g_pace_n; ++i)
+        if (g_pace[i].key == k) { g_pace[i].pace = pace; return; }
+    if (g_pace_n < 128) g_pace[g_pace_n++] = PaceEntry{k, pace};
+}
+
+template <typename Launch>
+static int tune_pace(Launch &&go, cudaStream_t st, int *best_pace) {
+    static const int kCandidates[] = {0, 100, 200, 300, 450, 700};
+    cudaEvent_t e0, e1;
+    RADNET_CUDA(cudaEventCreate(&e0));
+    RADNET_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    int rc = RADNET_OK;
+    *best_pace = 0;
+    for (int c : kCandidates) {
+        if ((rc = go(c)) != RADNET_OK) break;                     // warm-up (also grants the shared memory size)
+        cudaEventRecord(e0, st);
+        for (int k = 0; k < 2 && rc == RADNET_OK; ++k) rc = go(c);
+        cudaEventRecord(e1, st);
+        if (rc != RADNET_OK) break;
+        if (cudaEventSynchronize(e1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "pace tuning"); break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best * 0.99f) { best = ms; *best_pace = c; }     // a later (slower-issuing) candidate must win clearly
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
 }  // namespace radnet
 
 using namespace radnet;
@@ -547,48 +682,72 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
     p.det_max_boxes = det_max_boxes;
     p.rois = rois; p.roi_count = roi_count; p.R = rois_per_panel; p.pool = pool; p.out = out;
     cudaStream_t st = (cudaStream_t)stream;
+    p.pace = (int)get_option(kOptRoipoolPace);
 
     int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
-    const int smem_limit = device_smem_optin(dev);
-    if (smem_limit < 0) return RADNET_E_CUDA;
+    const int smem_optin = device_smem_optin(dev);
+    if (smem_optin < 0) return RADNET_E_CUDA;
+    const int smem_limit = smem_optin - 256;        // dynamic bytes a CTA may ask for: the kernels' static variables come on top
     const size_t HW = (size_t)H * W;
     const size_t per_roi = (size_t)pool * sizeof(YEntry) + sizeof(int2);
-    const long long form = get_option(kOptRoipoolForm);          // 0 auto, 1 whole-map slices, 2 cluster pairs
+    const long long form = get_option(kOptRoipoolForm);          // 0 auto, 1 whole-map slices, 2 row bands
     if (C % 4 == 0 && !force_direct() && HW < 65536 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const int C4 = C / 4;
-        // pair form (32-channel slices, half the rows per CTA of a cluster of two): when the whole-map form cannot
-        // keep 32 channels in one CTA, or on request
-        const int Hh = (H + 1) / 2;
-        const size_t half_bytes = ((size_t)Hh * W + 1) * 8 * 16;
+        // band form (a band of map rows per CTA, 32 / 64 / 128-channel slices): when the whole-map form cannot keep
+        // 32 channels in one CTA, or on request (roipool_form = 2, roipool_bands = number of bands, roipool_lanes =
+        // float4 lanes per pixel)
         const size_t whole8 = (HW + 1) * 8 * 16 + ((size_t)W + 1) * sizeof(float) + 16 + 8 * per_roi;
-        const bool pair_fits = C4 % 8 == 0 && W <= 256 && Hh <= 256 && H >= 2 && encode_tiled_fn() &&
-                               half_bytes + ((size_t)W + 1) * sizeof(float) + 16 + 8 * per_roi <= (size_t)smem_limit &&
-                               2LL * B * (C4 / 8) < 0x7fffffffLL;
-        if (pair_fits && (form == 2 || (form == 0 && whole8 > (size_t)smem_limit))) {
+        const int bl_opt = (int)get_option(kOptRoipoolLanes);
+        int bl = bl_opt;
+        if (bl != 8 && bl != 16 && bl != 32) bl = 8;
+        if (C4 % bl == 0 && W <= 256 && H >= 2 && encode_tiled_fn() &&
+            (form == 2 || (form == 0 && whole8 > (size_t)smem_limit))) {
+            const size_t per_roi_b = (size_t)pool * sizeof(YEntry) + sizeof(int4) + sizeof(int);
             const size_t scale_bytes = ((size_t)W + 1) * sizeof(float) + 16;
-            // two CTAs per SM when a half is small enough: cap the shared memory at half an SM
-            size_t budget = (size_t)smem_limit;
-            if (2 * (half_bytes + scale_bytes + 32 * per_roi + 1024) <= (size_t)smem_limit + 1024)
-                budget = ((size_t)smem_limit + 1024) / 2 - 1024;
-            size_t chunk = (budget - half_bytes - scale_bytes) / per_roi;
-            if (chunk > (size_t)rois_per_panel) chunk = rois_per_panel;
-            alignas(64) CUtensorMap tmap;
-            memset(&tmap, 0, sizeof(tmap));
-            if (chunk >= 1 && make_map_tensor(&tmap, feat, B, H, W, C, 8, Hh)) {
-                p.n_slices = C4 / 8;
-                p.roi_chunk = (int)chunk;
-                p.map_rows_pad = Hh;
-                p.tma_rows = Hh;
-                return launch_pair<8>(p, tmap, B, half_bytes + chunk * per_roi + scale_bytes, st);
+            const size_t budget2 = ((size_t)smem_optin + 1024) / 2 - 1024 - 256; // two CTAs per SM (1 KB reserved + static, each)
+            auto band_bytes = [&](int nb) { return ((size_t)((H + nb - 1) / nb + 1) * W + 1) * bl * 16; };
+            int nb = (int)get_option(kOptRoipoolBands);
+            if (nb < 2 || nb > H) {
+                // fewest bands that let two CTAs share an SM; else the fewest that fit at all
+                nb = 0;
+                for (int k = 2; k <= H && k <= 16 && !nb; ++k)
+                    if (band_bytes(k) + scale_bytes + 64 * per_roi_b <= budget2) nb = k;
+                for (int k = 2; k <= H && !nb; ++k)
+                    if (band_bytes(k) + scale_bytes + 8 * per_roi_b <= (size_t)smem_limit) nb = k;
+            }
+            const int Hb = nb ? (H + nb - 1) / nb : 0;
+            nb = nb ? (H + Hb - 1) / Hb : 0;                                   // bands that own at least one row
+            if (nb >= 1 && Hb + 1 <= 256 && band_bytes(nb) + scale_bytes + 8 * per_roi_b <= (size_t)smem_limit &&
+                (long long)B * (C4 / bl) * nb < 0x7fffffffLL) {
+                const size_t map_bytes = ((size_t)(Hb + 1) * W + 1) * bl * 16;
+                size_t budget = map_bytes + scale_bytes + 8 * per_roi_b <= budget2 ? budget2 : (size_t)smem_limit;
+                size_t chunk = (budget - map_bytes - scale_bytes) / per_roi_b;
+                if (chunk > (size_t)rois_per_panel) chunk = rois_per_panel;
+                alignas(64) CUtensorMap tmap;
+                memset(&tmap, 0, sizeof(tmap));
+                if (make_map_tensor(&tmap, feat, B, H, W, C, bl, Hb + 1)) {
+                    p.n_slices = C4 / bl;
+                    p.roi_chunk = (int)chunk;
+                    p.map_rows_pad = Hb + 1;
+                    p.tma_rows = Hb + 1;
+                    p.band_rows = Hb;
+                    p.n_bands = nb;
+                    const size_t smem = map_bytes + chunk * per_roi_b + scale_bytes;
+                    if (bl == 8) return launch_band<8>(p, tmap, B, smem, st);
+                    if (bl == 16) return launch_band<16>(p, tmap, B, smem, st);
+                    return launch_band<32>(p, tmap, B, smem, st);
+                }
             }
         }
         const int lanes_opts[4] = {8, 4, 2, 1};
         const int box_rows = (W <= 256 && encode_tiled_fn()) ? tma_box_rows(H) : 0;
         const int rows_pad = box_rows ? (H + box_rows - 1) / box_rows * box_rows : H;
+        const int max_lanes = (bl_opt == 4 || bl_opt == 2 || bl_opt == 1) ? bl_opt : 8;   // roipool_lanes caps the slice width
         for (int li = 0; li < 4; ++li) {
             int L = lanes_opts[li];
+            if (L > max_lanes) continue;
             size_t map_bytes = ((size_t)rows_pad * W + 1) * L * 16;
             const size_t scale_bytes = ((size_t)W + 1) * sizeof(float) + 16;
             if (C4 % L != 0 || map_bytes + scale_bytes + 8 * per_roi > (size_t)smem_limit) continue;
@@ -598,17 +757,46 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
             p.n_slices = C4 / L;
             p.roi_chunk = (int)chunk;
             if ((long long)B * p.n_slices >= 0x7fffffffLL) continue;
+            {
+                const int cs = (int)get_option(kOptRoipoolCluster), every = (int)get_option(kOptRoipoolSyncEvery);
+                p.cluster = (cs == 2 || cs == 4 || cs == 8) && p.n_slices % cs == 0 ? cs : 1;
+                p.sync_every = p.cluster > 1 ? (every > 0 ? every : 2) : 0;
+                p.n_work = B * p.n_slices;
+                const long long ctas = get_option(kOptRoipoolCtas);
+                p.grid = (ctas > 0 && ctas < p.n_work && p.cluster == 1) ? (int)ctas : p.n_work;
+            }
             alignas(64) CUtensorMap tmap;
             memset(&tmap, 0, sizeof(tmap));
             p.map_rows_pad = rows_pad;
             p.tma_rows = (box_rows && make_map_tensor(&tmap, feat, B, H, W, C, L, box_rows)) ? box_rows : 0;
             if (!p.tma_rows && rows_pad != H) continue;            // sized for TMA boxes but no descriptor: next option
-            switch (L) {
-                case 8: return launch_slice<8>(p, tmap, B, smem, st);
-                case 4: return launch_slice<4>(p, tmap, B, smem, st);
-                case 2: return launch_slice<2>(p, tmap, B, smem, st);
-                default: return launch_slice<1>(p, tmap, B, smem, st);
+            auto go = [&](int pace) {
+                p.pace = pace;
+                switch (L) {
+                    case 8: return launch_slice<8>(p, tmap, B, smem, st);
+                    case 4: return launch_slice<4>(p, tmap, B, smem, st);
+                    case 2: return launch_slice<2>(p, tmap, B, smem, st);
+                    default: return launch_slice<1>(p, tmap, B, smem, st);
+                }
+            };
+            if (p.pace >= 0) return go(p.pace);
+            // automatic pacing: measured once per (device, shape) on the caller's own buffers (the launches are
+            // idempotent), never while the stream is being captured into a graph
+            const PaceKey key{dev, B, H, W, C, pool, rois_per_panel, L};
+            int pace = cached_pace(key);
+            if (pace < 0) {
+                const int sms = device_sm_count(dev);
+                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+                if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusActive;
+                if (p.n_work < 4 * sms)
+                    pace = 0;                                   // too small to load HBM: nothing to pace
+                else if (cap != cudaStreamCaptureStatusNone)
+                    return go(0);                               // not cached: tuned on the first eager call
+                else if (int rc = tune_pace(go, st, &pace))
+                    return rc;
+                store_pace(key, pace);
             }
+            return go(pace);
         }
     }
     unsigned grid = (unsigned)((long long)B * rois_per_panel * pool);

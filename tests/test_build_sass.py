@@ -23,21 +23,28 @@ def _sass():
     return funcs
 
 
-def test_sm100a_and_no_packed_fma_in_roi_pool():
+def test_sm100a_and_no_contracted_multiply_add_in_roi_pool():
     funcs = _sass()
     pool = {k: v for k, v in funcs.items() if "roi_pool" in k}
     assert len(pool) >= 5
     for name, lines in pool.items():
-        text = "\n".join(lines)
-        # TF computes a + (b-a)*t with separate multiply and add; ptxas 12.9 contracts packed
-        # mul+add into FFMA2, so the kernels keep the final add scalar (see roipool.cu)
-        assert "FFMA2" not in text, name
-    slice8 = "\n".join(next(v for k, v in pool.items() if "slice_kernelILi8" in k))
-    assert "FMUL2" in slice8 and "FADD2" in slice8          # packed f32x2 math is in use
+        # TF computes a + (b-a)*t with separate multiply and add.  ptxas 12.9 contracts a packed multiply feeding a
+        # packed add into FFMA2, so the kernels issue the PRODUCT as a packed FMA whose addend is -0.0 held in a
+        # uniform register (d*t + (-0.0) == d*t exactly) and add with a separate FADD2 (see roipool.cu): there must
+        # be no packed multiply left that could be contracted, and every FFMA2 must be of that form
+        for ln in lines:
+            assert "FMUL2" not in ln, (name, ln)
+            if "FFMA2" in ln:
+                ops = ln.split("FFMA2")[1].split(";")[0].split(",")
+                assert ops[-1].strip().startswith("UR"), (name, ln)
+    slice8 = "\n".join(next(v for k, v in pool.items() if "slice_kernelILi8ELi14" in k))
+    assert "FFMA2" in slice8 and "FADD2" in slice8          # packed f32x2 math is in use
     assert "UTMALDG.4D" in slice8                           # TMA tensor copy of the map slice (cp.async.bulk.tensor.4d)
     assert "SYNCS" in slice8                                # ... completing on an mbarrier
     assert "LDGSTS" in slice8                               # cp.async staging kept for maps wider than a TMA box
     assert "STG.E.EF.128" in slice8                         # streaming 16-byte stores
+    band = "\n".join(next(v for k, v in pool.items() if "band_kernel" in k))
+    assert "UTMALDG.4D" in band and "STG.E.EF.128" in band
 
 
 def test_nms_uses_tma_bulk_copy_mbarrier_and_simd_minmax():

@@ -334,17 +334,19 @@ def test_roi_pooling_conv_vs_oracle(pkg, H, W, Cn, pool):
 
 @pytest.mark.parametrize("H,W,Cn,pool", [(38, 38, 1024, 14), (38, 50, 1024, 14), (38, 38, 512, 7), (37, 41, 64, 14),
                                          (2, 3, 32, 2), (75, 75, 32, 7)])
-def test_roi_pooling_cluster_pair_form_matches(pkg, lib_option, H, W, Cn, pool):
-    """The pair form (a cluster of two CTAs holds half of the map rows each; taps on the other half go through
-    distributed shared memory) on even / odd row counts, and as the automatic choice for 38x50."""
+@pytest.mark.parametrize("bands", [0, 2, 3, 5])
+def test_roi_pooling_band_form_matches(pkg, lib_option, H, W, Cn, pool, bands):
+    """The band form (a CTA holds a band of map rows and emits the output rows that sample it) on even / odd row
+    counts and band counts that do not divide H; it is the automatic choice for 38x50."""
     lib_option("roipool_form", 2)
+    lib_option("roipool_bands", bands)
     feat = S.feature_map(4, H, W, Cn)
     rois = _all_size_rois(H, W)
     got = pkg.RoiPoolingConv(pool, rois.shape[1])([feat, rois])
     assert np.array_equal(got, O.roi_pooling_conv(feat, rois, pool))
 
 
-def test_roi_pooling_pair_form_batch_with_empty_slots(pkg, lib_option):
+def test_roi_pooling_band_form_batch_with_empty_slots(pkg, lib_option):
     """Batched call through the detection records (slots beyond the kept count must be zero-filled)."""
     from rock_art_radnet_b200.pipeline import ProposalPipeline
     C = S.HotPathConfig()

@@ -2,7 +2,7 @@
 # profiling build of the library (phase timestamps in the NMS and target kernels); not used by tests or bench
 set -e
 cd "$(dirname "$0")/../rock_art_radnet_b200"
-SRC=$(python - <<'PY'
+SRC=$(PYTHONPATH=.. python - <<'PY'
 from rock_art_radnet_b200.build import SOURCES
 print(" ".join("csrc/" + s for s in SOURCES))
 PY

@@ -59,9 +59,8 @@ enum Option {
     kOptTargetsTwoLaunches,  // targets_two_launches: 0/1 (fill and panels as two launches)
     kOptRoipoolBands,        // roipool_bands: 0 auto, else the number of row bands of the band form
     kOptRoipoolLanes,        // roipool_lanes: 0 auto (8), else 8 / 16 / 32 float4 lanes per pixel in the band form
-    kOptRoipoolPace,         // roipool_pace: ns slept per output column in the whole-map form (-1 auto, 0 none)
-    kOptRoipoolCluster,      // roipool_cluster: 0 none, 2 / 4 / 8 CTAs (neighbouring slices) per cluster in the whole-map form
-    kOptRoipoolSyncEvery,    // roipool_sync_every: cluster barrier every this many column rounds (0 = 2)
+    kOptRoipoolCluster,      // roipool_cluster: -1 tuned at the first call, 0/1 none, 2 / 4 / 8 CTAs (neighbouring slices) per cluster
+    kOptRoipoolSyncEvery,    // roipool_sync_every: with roipool_cluster >= 0, CTA / cluster barrier every this many column rounds
     kOptRoipoolCtas,         // roipool_ctas: whole-map form with this many persistent CTAs (0 = one CTA per work item)
     kOptCount
 };

@@ -18,7 +18,12 @@
 //   * 8 lanes x float4 cover the 32 channels of one output pixel; a warp writes 4 full
 //     128-byte lines per store instruction with a streaming (evict-first) hint.
 //   * value = top + (bottom-top)*ylerp, top = tl + (tr-tl)*xlerp, separate IEEE float32
-//     multiply and add (never fused) - bit-identical to the CPU kernel of TF-1.
+//     multiply and add (never fused) - bit-identical to the CPU kernel of TF-1.  The multiply is
+//     issued as a packed FMA with a -0.0 addend so that ptxas cannot contract it (see lerp2).
+//   * the kernel is co-limited by instruction issue (one SM sustains ~46 GB/s of 16-byte stores)
+//     and by how HBM takes the write stream; the inner loop costs ~30 instructions per 16-byte
+//     store (flag-coded y table, cached rows), and the launcher tunes how tightly the warps of a
+//     CTA / the CTAs of neighbouring slices are kept in lockstep (see "automatic lockstep").
 //
 // A direct (global-load) kernel covers maps whose slice does not fit in shared memory
 // and channel counts that are not a multiple of 4.
@@ -54,11 +59,10 @@ struct RoiPoolParams {
     int map_rows_pad;        // map rows held in shared memory (>= H: whole TMA boxes)
     int tma_rows;            // map rows per TMA box (0 = stage with cp.async)
     int band_rows, n_bands;  // band form: source rows owned by a band, bands per map
-    int pace;                // whole-map form: nanoseconds a group sleeps after each output column (0 = none)
     int grid;                // whole-map form: CTAs launched
     int n_work;              // whole-map form: (panel, slice) work items; the grid may be smaller (persistent CTAs)
     int cluster;             // whole-map form: CTAs per cluster (neighbouring slices of a panel), 1 = no cluster
-    int sync_every;          // whole-map form in clusters: cluster barrier every this many column rounds (0 = never)
+    int sync_every;          // whole-map form: CTA (or cluster) barrier every this many column rounds (0 = never)
 };
 
 // global -> shared TMA tile copy of a rank-4 tensor, completion (bytes) on an mbarrier
@@ -333,9 +337,13 @@ __global__ void __launch_bounds__(kSliceThreads, 1) roi_pool_slice_kernel(RoiPoo
         const int d_rl = G / pool, d_px = G - d_rl * pool;
         int it = 0;
         for (int base = 0; base < ncol; base += G, rl += d_rl, px += d_px, ++it) {
-            // the CTAs of a cluster own neighbouring channel slices of the same panel: keeping them within a few
-            // RoIs of each other makes their 128-byte pieces of an output pixel reach HBM together
-            if (p.sync_every > 0 && it % p.sync_every == 0) cluster_sync_relaxed();
+            // lockstep: the warps of the CTA (and, in a cluster, the CTAs of neighbouring channel slices of the same
+            // panel) are kept within `sync_every` column rounds of each other, so that what the SM writes at any
+            // moment stays within a few RoIs - see the launcher for the measured effect
+            if (p.sync_every > 0 && it % p.sync_every == 0) {
+                if (p.cluster > 1) cluster_sync_relaxed();
+                else __syncthreads();
+            }
             if (px >= pool) { px -= pool; ++rl; }
             if (base + g >= ncol) continue;
             const int2 rx = s_roi[rl];
@@ -345,9 +353,6 @@ __global__ void __launch_bounds__(kSliceThreads, 1) roi_pool_slice_kernel(RoiPoo
             float4 *dst = reinterpret_cast<float4 *>(p.out) +
                           (((size_t)b * p.R + r0 + rl) * PP + px) * C4 + (size_t)s * LANES + q;
             pool_column<POOL>(mapb, s_ytab + rl * pool, 0, pool, xo0, xo1, lx, row_step, dst, py_step, nz);
-            // pacing (see the launcher): the HBM write stream loses ~10 % when every SM pushes stores as fast as it
-            // can issue them; a short sleep per column costs no issue slots
-            if (p.pace > 0) __nanosleep((unsigned)p.pace);
         }
     }
     }   // work items
@@ -602,57 +607,63 @@ static int tma_box_rows(int H) {
 }
 
 
-// ---- automatic pacing of the whole-map form ---------------------------------------------------------------------
-// The HBM write path of B200 delivers less when it is oversubscribed: a plain fill kernel writes 6.05 TB/s from 120
-// SMs and 5.78 TB/s from 148 (profiles/r02_fill_bw.log), cudaMemsetAsync 6.8-7.3 TB/s.  K4 needs all SMs (one SM
-// sustains ~46 GB/s of 16-byte stores), so instead of using fewer SMs every group sleeps a little after each
-// output column; the best sleep depends on the shape and on the clocks, so it is measured, not guessed.
-struct PaceKey {
+// ---- automatic lockstep of the whole-map form -------------------------------------------------------------------
+// K4 is a pure HBM write stream of 128-byte (or 64-byte) pieces, and how well HBM takes it depends on WHAT the SMs
+// write at the same time, not only on how much.  Measured on B200 (64 panels, 38x38x1024, pool 14; fraction of the
+// 6.56 TB/s copy peak): warps free-running 0.86-0.90; a CTA barrier after every round of 64 output columns 0.97; two
+// neighbouring slices in a cluster with a cluster barrier every second round 1.01.  The same barriers COST 10-20 %
+// on 7x7x512 (VGG-16) and on 16-channel slices (38x50 maps), where the free-running form reaches 0.87 / 0.96.
+// (Related: a plain fill kernel writes 6.05 TB/s from 120 SMs but 5.78 TB/s from 148, cudaMemsetAsync 6.8-7.3 TB/s -
+// profiles/r02_fill_bw.log, r02_tma_store_bw.log.)  So the choice is measured, not guessed: the first eager call for
+// a (device, shape) times the candidates below on the caller's own buffers and the result is cached.
+static const int kLockstep[][2] = {{1, 0}, {1, 1}, {1, 2}, {2, 1}, {2, 2}, {2, 4}};     // {CTAs per cluster, sync_every}
+constexpr int kLockstepN = sizeof(kLockstep) / sizeof(kLockstep[0]);
+
+struct TuneKey {
     int dev, B, H, W, C, pool, R, lanes;
-    bool operator==(const PaceKey &o) const {
+    bool operator==(const TuneKey &o) const {
         return dev == o.dev && B == o.B && H == o.H && W == o.W && C == o.C && pool == o.pool && R == o.R && lanes == o.lanes;
     }
 };
-struct PaceEntry {
-    PaceKey key;
-    int pace;
+struct TuneEntry {
+    TuneKey key;
+    int choice;
 };
-static std::mutex g_pace_mutex;
-static PaceEntry g_pace[128];
-static int g_pace_n = 0;
+static std::mutex g_tune_mutex;
+static TuneEntry g_tune[128];
+static int g_tune_n = 0;
 
-static int cached_pace(const PaceKey &k) {
-    std::lock_guard<std::mutex> lock(g_pace_mutex);
-    for (int i = 0; i < g_pace_n; ++i)
-        if (g_pace[i].key == k) return g_pace[i].pace;
+static int cached_choice(const TuneKey &k) {
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    for (int i = 0; i < g_tune_n; ++i)
+        if (g_tune[i].key == k) return g_tune[i].choice;
     return -1;
 }
-static void store_pace(const PaceKey &k, int pace) {
-    std::lock_guard<std::mutex> lock(g_pace_mutex);
-    for (int i = 0; i < g_pace_n; ++i)
-        if (g_pace[i].key == k) { g_pace[i].pace = pace; return; }
-    if (g_pace_n < 128) g_pace[g_pace_n++] = PaceEntry{k, pace};
+static void store_choice(const TuneKey &k, int choice) {
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    for (int i = 0; i < g_tune_n; ++i)
+        if (g_tune[i].key == k) { g_tune[i].choice = choice; return; }
+    if (g_tune_n < 128) g_tune[g_tune_n++] = TuneEntry{k, choice};
 }
 
 template <typename Launch>
-static int tune_pace(Launch &&go, cudaStream_t st, int *best_pace) {
-    static const int kCandidates[] = {0, 100, 200, 300, 450, 700};
+static int tune_lockstep(Launch &&go, cudaStream_t st, int *best_choice) {
     cudaEvent_t e0, e1;
     RADNET_CUDA(cudaEventCreate(&e0));
     RADNET_CUDA(cudaEventCreate(&e1));
     float best = 1e30f;
     int rc = RADNET_OK;
-    *best_pace = 0;
-    for (int c : kCandidates) {
-        if ((rc = go(c)) != RADNET_OK) break;                     // warm-up (also grants the shared memory size)
+    *best_choice = 0;
+    for (int c = 0; c < kLockstepN; ++c) {
+        if ((rc = go(kLockstep[c][0], kLockstep[c][1])) != RADNET_OK) break;     // warm-up
         cudaEventRecord(e0, st);
-        for (int k = 0; k < 2 && rc == RADNET_OK; ++k) rc = go(c);
+        for (int k = 0; k < 2 && rc == RADNET_OK; ++k) rc = go(kLockstep[c][0], kLockstep[c][1]);
         cudaEventRecord(e1, st);
         if (rc != RADNET_OK) break;
-        if (cudaEventSynchronize(e1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "pace tuning"); break; }
+        if (cudaEventSynchronize(e1) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "lockstep tuning"); break; }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        if (ms < best * 0.99f) { best = ms; *best_pace = c; }     // a later (slower-issuing) candidate must win clearly
+        if (ms < best * 0.985f) { best = ms; *best_choice = c; }       // a later candidate has to win clearly
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -682,7 +693,6 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
     p.det_max_boxes = det_max_boxes;
     p.rois = rois; p.roi_count = roi_count; p.R = rois_per_panel; p.pool = pool; p.out = out;
     cudaStream_t st = (cudaStream_t)stream;
-    p.pace = (int)get_option(kOptRoipoolPace);
 
     int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
@@ -757,21 +767,18 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
             p.n_slices = C4 / L;
             p.roi_chunk = (int)chunk;
             if ((long long)B * p.n_slices >= 0x7fffffffLL) continue;
-            {
-                const int cs = (int)get_option(kOptRoipoolCluster), every = (int)get_option(kOptRoipoolSyncEvery);
-                p.cluster = (cs == 2 || cs == 4 || cs == 8) && p.n_slices % cs == 0 ? cs : 1;
-                p.sync_every = p.cluster > 1 ? (every > 0 ? every : 2) : 0;
-                p.n_work = B * p.n_slices;
-                const long long ctas = get_option(kOptRoipoolCtas);
-                p.grid = (ctas > 0 && ctas < p.n_work && p.cluster == 1) ? (int)ctas : p.n_work;
-            }
+            p.n_work = B * p.n_slices;
+            const long long ctas = get_option(kOptRoipoolCtas);
+            p.grid = (ctas > 0 && ctas < p.n_work) ? (int)ctas : p.n_work;
             alignas(64) CUtensorMap tmap;
             memset(&tmap, 0, sizeof(tmap));
             p.map_rows_pad = rows_pad;
             p.tma_rows = (box_rows && make_map_tensor(&tmap, feat, B, H, W, C, L, box_rows)) ? box_rows : 0;
             if (!p.tma_rows && rows_pad != H) continue;            // sized for TMA boxes but no descriptor: next option
-            auto go = [&](int pace) {
-                p.pace = pace;
+            auto go = [&](int cluster, int sync_every) {
+                p.cluster = (cluster == 2 || cluster == 4 || cluster == 8) && p.n_slices % cluster == 0 &&
+                                    p.grid == p.n_work ? cluster : 1;
+                p.sync_every = sync_every;
                 switch (L) {
                     case 8: return launch_slice<8>(p, tmap, B, smem, st);
                     case 4: return launch_slice<4>(p, tmap, B, smem, st);
@@ -779,24 +786,25 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
                     default: return launch_slice<1>(p, tmap, B, smem, st);
                 }
             };
-            if (p.pace >= 0) return go(p.pace);
-            // automatic pacing: measured once per (device, shape) on the caller's own buffers (the launches are
+            const int cs_opt = (int)get_option(kOptRoipoolCluster), every_opt = (int)get_option(kOptRoipoolSyncEvery);
+            if (cs_opt >= 0) return go(cs_opt, every_opt > 0 ? every_opt : (cs_opt > 1 ? 2 : 0));
+            // automatic lockstep: measured once per (device, shape) on the caller's own buffers (the launches are
             // idempotent), never while the stream is being captured into a graph
-            const PaceKey key{dev, B, H, W, C, pool, rois_per_panel, L};
-            int pace = cached_pace(key);
-            if (pace < 0) {
+            const TuneKey key{dev, B, H, W, C, pool, rois_per_panel, L};
+            int choice = cached_choice(key);
+            if (choice < 0) {
                 const int sms = device_sm_count(dev);
                 cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
                 if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusActive;
                 if (p.n_work < 4 * sms)
-                    pace = 0;                                   // too small to load HBM: nothing to pace
+                    choice = 0;                                 // too small to load HBM: nothing to tune
                 else if (cap != cudaStreamCaptureStatusNone)
-                    return go(0);                               // not cached: tuned on the first eager call
-                else if (int rc = tune_pace(go, st, &pace))
+                    return go(1, 0);                            // not cached: tuned on the first eager call
+                else if (int rc = tune_lockstep(go, st, &choice))
                     return rc;
-                store_pace(key, pace);
+                store_choice(key, choice);
             }
-            return go(pace);
+            return go(kLockstep[choice][0], kLockstep[choice][1]);
         }
     }
     unsigned grid = (unsigned)((long long)B * rois_per_panel * pool);

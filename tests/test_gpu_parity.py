@@ -368,6 +368,38 @@ def test_roi_pooling_band_form_batch_with_empty_slots(pkg, lib_option):
         assert bool((outs[1][b, int(counts[b]):] == 0).all())
 
 
+@pytest.mark.parametrize("cluster,every,ctas", [(0, 0, 0), (0, 1, 0), (0, 3, 0), (2, 1, 0), (2, 2, 0), (4, 2, 0), (8, 1, 0),
+                                                (0, 0, 3), (0, 2, 5), (-1, 0, 0)])
+def test_roi_pooling_lockstep_and_persistent_variants_match(pkg, lib_option, cluster, every, ctas):
+    """Whole-map form: CTA / cluster barriers every few column rounds (the lockstep the launcher tunes per shape) and a
+    grid smaller than the number of (panel, slice) work items never change a bit of the result."""
+    from rock_art_radnet_b200.pipeline import ProposalPipeline
+    lib_option("roipool_form", 1)
+    lib_option("roipool_cluster", cluster)
+    lib_option("roipool_sync_every", every)
+    lib_option("roipool_ctas", ctas)
+    C = S.HotPathConfig()
+    B, H, W, Cn = 3, 38, 38, 256
+    maps = [S.rpn_maps(40 + s, H, W, 9) for s in range(B)]
+    feat_np = np.concatenate([S.feature_map(40 + s, H, W, Cn) for s in range(B)])
+    pipe = ProposalPipeline(C, B, H, W, channels=Cn, pool_size=14, max_boxes=60, overlap_thresh=0.5)
+    pipe.decode(torch.from_numpy(np.concatenate([m[0] for m in maps])).cuda(),
+                torch.from_numpy(np.concatenate([m[1] for m in maps])).cuda())
+    pipe.sort_nms()
+    pipe.pooled.fill_(3.0)
+    got = pipe.pool(torch.from_numpy(feat_np).cuda()).cpu().numpy()
+    counts = pipe.records.counts.cpu().numpy()
+    boxes = pipe.records.boxes.cpu().numpy()
+    for b in range(B):
+        n = int(counts[b])
+        rois = np.zeros((1, 60, 4), np.float64)
+        rois[0, :n, 0], rois[0, :n, 1] = boxes[b, :n, 0], boxes[b, :n, 1]
+        rois[0, :n, 2], rois[0, :n, 3] = boxes[b, :n, 2] - boxes[b, :n, 0], boxes[b, :n, 3] - boxes[b, :n, 1]
+        want = O.roi_pooling_conv(feat_np[b:b + 1], rois[:, :n], 14)
+        assert np.array_equal(got[b, :n], want[0]), (b, cluster, every, ctas)
+        assert (got[b, n:] == 0).all()
+
+
 def test_roi_pooling_direct_kernel_matches(pkg, lib_option):
     lib_option("roipool_force_direct", 1)
     feat = S.feature_map(2, 38, 38, 256)

@@ -265,13 +265,18 @@ def main():
         kept = int(pipe.records.counts.sum().item())
         nbytes = B * Hh * Ww * Cn * 4 + kept * 16 + kept * pool * pool * Cn * 4
         from rock_art_radnet_b200 import _lib
-        for form, bands, ftag in ((0, 0, ""), (1, 0, "_whole_map_form"), (2, 2, "_2_bands"), (2, 3, "_3_bands"),
-                                  (2, 4, "_4_bands")):
+        # automatic choice first (form 0, lockstep tuned at the first call), then the fixed variants it chooses between
+        for form, bands, cluster, every, ftag in ((0, 0, -1, 0, ""), (1, 0, 0, 0, "_free_running"), (1, 0, 0, 1, "_cta_lockstep"),
+                                                  (1, 0, 2, 2, "_pair_lockstep"), (2, 2, -1, 0, "_2_bands"), (2, 3, -1, 0, "_3_bands")):
             _lib.set_option("roipool_form", form)
             _lib.set_option("roipool_bands", bands)
+            _lib.set_option("roipool_cluster", cluster)
+            _lib.set_option("roipool_sync_every", every)
             t = time_ms(lambda: pipe.pool(feat), iters=10)
             res["roi_pool_%s_B%d%s" % (tag, B, ftag)] = dict(t, algorithmic_bytes=nbytes, gbs=nbytes / t["p50_ms"] / 1e6,
                                                            frac_of_measured_peak=nbytes / t["p50_ms"] / 1e6 / pk)
+        _lib.set_option("roipool_cluster", -1)
+        _lib.set_option("roipool_sync_every", 0)
         _lib.set_option("roipool_form", 0)
         _lib.set_option("roipool_bands", 0)
         del pipe, feat

@@ -36,10 +36,9 @@ for (B, Cn, pool, name, H, W) in ([(b, c, pl, "%dx%dx%d_p%d_B%d" % (h, w, c, pl,
     for fm in forms:
         form, bands, lanes = fm[:3]
         pace = fm[3] if len(fm) > 3 else 0
-        _lib.set_option("roipool_cluster", fm[4] if len(fm) > 4 else 0)
+        _lib.set_option("roipool_cluster", fm[4] if len(fm) > 4 else -1)
         _lib.set_option("roipool_sync_every", fm[5] if len(fm) > 5 else 0)
         _lib.set_option("roipool_ctas", fm[6] if len(fm) > 6 else 0)
-        _lib.set_option("roipool_pace", pace)
         _lib.set_option("roipool_form", form)
         _lib.set_option("roipool_bands", bands)
         _lib.set_option("roipool_lanes", lanes)

@@ -28,8 +28,8 @@ int cuda_fail(cudaError_t e, const char *what) {
 static const char *const kOptionNames[kOptCount] = {
     "nms_cluster", "nms_cluster_size", "nms_cluster_ranks", "nms_sel_target",
     "nms_lookahead", "roipool_force_direct", "targets_hit_cap", "roipool_form", "sampler_force_exact",
-    "targets_compute_ctas", "targets_two_launches", "roipool_bands", "roipool_lanes", "roipool_cluster", "roipool_sync_every", "roipool_ctas"};
-static const long long kOptionDefaults[kOptCount] = {-1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0, 0};
+    "targets_compute_ctas", "targets_two_launches", "roipool_bands", "roipool_lanes", "roipool_cluster", "roipool_sync_every", "roipool_ctas", "targets_fill_bulk"};
+static const long long kOptionDefaults[kOptCount] = {-1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0};
 
 struct OptionTable {
     std::atomic<long long> v[kOptCount];

@@ -62,6 +62,7 @@ enum Option {
     kOptRoipoolCluster,      // roipool_cluster: -1 tuned at the first call, 0/1 none, 2 / 4 / 8 CTAs (neighbouring slices) per cluster
     kOptRoipoolSyncEvery,    // roipool_sync_every: with roipool_cluster >= 0, CTA / cluster barrier every this many column rounds
     kOptRoipoolCtas,         // roipool_ctas: whole-map form with this many persistent CTAs (0 = one CTA per work item)
+    kOptTargetsFillBulk,     // targets_fill_bulk: 0 plain stores, 1 regression zeros by TMA bulk copies from a zeroed buffer, else buffer bytes
     kOptCount
 };
 long long get_option(int opt);

@@ -197,8 +197,11 @@ def test_calc_region_props_matches_reference_golden(pkg, manifest, golden_a3):
     assert pkg.calc_rpn is pkg.calc_region_props
 
 
-def test_rpn_targets_batched_presample_vs_oracle(pkg):
+@pytest.mark.parametrize("fill_bulk", [0, 1, 4096])
+def test_rpn_targets_batched_presample_vs_oracle(pkg, lib_option, fill_bulk):
+    """fill_bulk > 0: the regression zeros are streamed by TMA bulk copies that every CTA of the launch shares out."""
     from rock_art_radnet_b200.utils import rpn_targets_device
+    lib_option("targets_fill_bulk", fill_bulk)
     C = S.HotPathConfig((64, 128, 256, 512))          # 12 anchors
     sizes = [(600, 600, 20), (800, 600, 9), (600, 750, 33), (600, 600, 0)]
     B, Gmax = len(sizes), 33

@@ -296,6 +296,12 @@ def bench_targets(dev, C, pipe, peak):
                     "gbs_stream": nbytes / ms_s / 1e6, "frac_stream": nbytes / ms_s / 1e6 / peak,
                     "l2": "ms: L2 flushed before every launch; ms_stream: 40 launches over 4 output sets (266 MB > L2)"}
         if tag == "rpn":
+            # context for a 66.6 MB burst: the driver's own memset of the same two tensors, timed the same two ways
+            # (a burst this short never sees the steady-state HBM rate the roofline peak is quoted at)
+            ms_m = event_ms(lambda: (sets[0].y_cls.zero_(), sets[0].y_regr.zero_()), dev, before=upload)
+            ms_ms = stream_ms([(lambda t=t: (t.y_cls.zero_(), t.y_regr.zero_())) for t in sets], 40)
+            out[tag].update(memset_same_tensors_ms=ms_m, memset_same_tensors_ms_stream=ms_ms,
+                            frac_of_memset=ms_m / ms, frac_of_memset_stream=ms_ms / ms_s)
             y_cls = sets[0].y_cls
             sub = RpnSubsampler(B, H, W, A, device=dev)
             states = seed_states(np.arange(B), device=dev)

@@ -19,6 +19,8 @@
 // it lies more than 2e-4 away from a half-integer, rintf() of it IS np.round() of the reference value;
 // the float64 path (two exp() in double) then runs only for the ~0.2 % of anchors near a rounding
 // boundary, for large maps / sizes, and for non-finite inputs.  Outputs stay bit-exact.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace radnet {
@@ -110,7 +112,7 @@ __device__ __forceinline__ bool decode_fast(int c, int r, float wf, float hf, fl
 template <bool kF64>
 __global__ void __launch_bounds__(kDecodeThreads, kF64 ? 2 : 5)
 decode_clip_kernel(const float *__restrict__ cls, const float *__restrict__ regr, int H, int W,
-                   int A, unsigned magic_a, unsigned magic_w, AnchorTable anchors, float std_scaling, int use_regr,
+                   int A, unsigned magic_a, unsigned magic_w, AnchorTable anchors, float std_scaling, float inv_scale, int use_regr,
                    int32_t *__restrict__ boxes_i32, uint32_t *__restrict__ keys,
                    double *__restrict__ boxes_f64, float *__restrict__ scores,
                    uint8_t *__restrict__ valid, int32_t *__restrict__ stats) {
@@ -143,10 +145,17 @@ decode_clip_kernel(const float *__restrict__ cls, const float *__restrict__ regr
         const int c = cell - r * W;
         float4 t = __ldg(regr_b + p);
         float s = __ldg(cls_b + p);
-        t.x = __fdiv_rn(t.x, std_scaling);
-        t.y = __fdiv_rn(t.y, std_scaling);
-        t.z = __fdiv_rn(t.z, std_scaling);
-        t.w = __fdiv_rn(t.w, std_scaling);
+        if (inv_scale != 0.f) {          // std_scaling is a power of two: the float32 quotient is the exact product
+            t.x = __fmul_rn(t.x, inv_scale);
+            t.y = __fmul_rn(t.y, inv_scale);
+            t.z = __fmul_rn(t.z, inv_scale);
+            t.w = __fmul_rn(t.w, inv_scale);
+        } else {
+            t.x = __fdiv_rn(t.x, std_scaling);
+            t.y = __fdiv_rn(t.y, std_scaling);
+            t.z = __fdiv_rn(t.z, std_scaling);
+            t.w = __fdiv_rn(t.w, std_scaling);
+        }
         int4 fbox;
         int fvalid = 0;
         const double aw = anchors.wh[a][0], ah = anchors.wh[a][1];
@@ -253,6 +262,14 @@ static int decode_common(bool f64, const float *cls, const float *regr, int B, i
     const unsigned magic_a = A > 1 ? (unsigned)((0x100000000ULL + (unsigned)A - 1) / (unsigned)A) : 0u;   // n < 64 * 64
     const unsigned magic_w = ((unsigned long long)HW * (unsigned)W < 0x100000000ULL && W > 1)
                                  ? (unsigned)((0x100000000ULL + (unsigned)W - 1) / (unsigned)W) : 0u;
+    // x / s == x * (1 / s) bit for bit when s is a power of two whose reciprocal is a normal float32 (the reference's
+    // std_scaling is 4.0); denormal quotients round identically because the product is exact before rounding
+    float inv_scale = 0.f;
+    {
+        int e = 0;
+        const float m = frexpf(fabsf(std_scaling), &e);
+        if (m == 0.5f && e > -100 && e < 100) inv_scale = 1.0f / std_scaling;
+    }
     dim3 grid((HW + kDecodeCells - 1) / kDecodeCells, B);
     size_t per = f64 ? (sizeof(double4) + sizeof(uint32_t) + 1) : (sizeof(int4) + sizeof(uint32_t));
     size_t smem = (size_t)A * (kDecodeCells + 1) * per + 16;
@@ -261,11 +278,11 @@ static int decode_common(bool f64, const float *cls, const float *regr, int B, i
     if (f64) {
         if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(decode_clip_kernel<true>), dev, smem)) return rc;
         decode_clip_kernel<true><<<grid, kDecodeThreads, smem, st>>>(
-            cls, regr, H, W, A, magic_a, magic_w, tab, std_scaling, use_regr, nullptr, nullptr, boxes_f64, scores, valid, stats);
+            cls, regr, H, W, A, magic_a, magic_w, tab, std_scaling, inv_scale, use_regr, nullptr, nullptr, boxes_f64, scores, valid, stats);
     } else {
         if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(decode_clip_kernel<false>), dev, smem)) return rc;
         decode_clip_kernel<false><<<grid, kDecodeThreads, smem, st>>>(
-            cls, regr, H, W, A, magic_a, magic_w, tab, std_scaling, use_regr, boxes_i32, keys, nullptr, nullptr, nullptr, stats);
+            cls, regr, H, W, A, magic_a, magic_w, tab, std_scaling, inv_scale, use_regr, boxes_i32, keys, nullptr, nullptr, nullptr, stats);
     }
     return check_launch("decode_clip_kernel");
 }

@@ -548,10 +548,13 @@ static int launch_slice_pool(const RoiPoolParams &p, const CUtensorMap &tmap, in
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        RADNET_CUDA(cudaLaunchKernelEx(&cfg, roi_pool_slice_kernel<LANES, POOL>, p, tmap));
-        return check_launch("roi_pool_slice_kernel (cluster)");
+        if (cudaLaunchKernelEx(&cfg, roi_pool_slice_kernel<LANES, POOL>, p, tmap) == cudaSuccess)
+            return check_launch("roi_pool_slice_kernel (cluster)");
+        cudaGetLastError();            // a refused cluster launch (MPS, partitioned GPU): same barriers inside each CTA only
     }
-    roi_pool_slice_kernel<LANES, POOL><<<p.grid, kSliceThreads, smem, st>>>(p, tmap);
+    RoiPoolParams q = p;
+    q.cluster = 1;
+    roi_pool_slice_kernel<LANES, POOL><<<q.grid, kSliceThreads, smem, st>>>(q, tmap);
     return check_launch("roi_pool_slice_kernel");
 }
 // the reference's two pool sizes (14: ResNet-50, 7: VGG-16) have their rows fully unrolled
@@ -705,15 +708,16 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
     if (C % 4 == 0 && !force_direct() && HW < 65536 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const int C4 = C / 4;
-        // band form (a band of map rows per CTA, 32 / 64 / 128-channel slices): when the whole-map form cannot keep
-        // 32 channels in one CTA, or on request (roipool_form = 2, roipool_bands = number of bands, roipool_lanes =
-        // float4 lanes per pixel)
-        const size_t whole8 = (HW + 1) * 8 * 16 + ((size_t)W + 1) * sizeof(float) + 16 + 8 * per_roi;
+        // band form (a band of map rows per CTA, 32 / 64 / 128-channel slices): only on request (roipool_form = 2,
+        // roipool_bands = number of bands, roipool_lanes = float4 lanes per pixel).  It keeps 128-byte store lines for
+        // maps whose 32-channel slice does not fit one CTA (38x50), but once the inner loop was no longer
+        // issue-bound the whole-map form with 16-channel slices measured 0.95-0.96 of the HBM peak there against
+        // 0.73-0.80 for two or three bands (every band CTA rebuilds the y tables and has a different amount of work)
         const int bl_opt = (int)get_option(kOptRoipoolLanes);
         int bl = bl_opt;
         if (bl != 8 && bl != 16 && bl != 32) bl = 8;
         if (C4 % bl == 0 && W <= 256 && H >= 2 && encode_tiled_fn() &&
-            (form == 2 || (form == 0 && whole8 > (size_t)smem_limit))) {
+            form == 2) {
             const size_t per_roi_b = (size_t)pool * sizeof(YEntry) + sizeof(int4) + sizeof(int);
             const size_t scale_bytes = ((size_t)W + 1) * sizeof(float) + 16;
             const size_t budget2 = ((size_t)smem_optin + 1024) / 2 - 1024 - 256; // two CTAs per SM (1 KB reserved + static, each)

@@ -340,7 +340,7 @@ def test_roi_pooling_conv_vs_oracle(pkg, H, W, Cn, pool):
 @pytest.mark.parametrize("bands", [0, 2, 3, 5])
 def test_roi_pooling_band_form_matches(pkg, lib_option, H, W, Cn, pool, bands):
     """The band form (a CTA holds a band of map rows and emits the output rows that sample it) on even / odd row
-    counts and band counts that do not divide H; it is the automatic choice for 38x50."""
+    counts and band counts that do not divide H (kept as a selectable form; the whole-map form measured faster on every shape)."""
     lib_option("roipool_form", 2)
     lib_option("roipool_bands", bands)
     feat = S.feature_map(4, H, W, Cn)

@@ -434,6 +434,11 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.k4_lockstep:
+        from rock_art_radnet_b200 import _lib
+        c, e = (int(v) for v in args.k4_lockstep.split(","))
+        _lib.set_option("roipool_cluster", c)
+        _lib.set_option("roipool_sync_every", e)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -636,7 +641,8 @@ def run_b200_arm(args):
                                "what": "radnet_sort_nms_i32, one 600-px panel (12,996 candidates) per launch; p50/p95 = "
                                        "CUDA-graph replay between two events (device latency), p50_python_call = the "
                                        "same launch issued through the ctypes binding"},
-            "roofline": {"kernel": "roi_pool_slice_kernel<8>", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "roi_pool_slice_kernel<8, 14>", "launch_form": pipe.pool_form(),
+                         "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pool_bytes, "avg_launch_ms": pool_ms},
@@ -670,6 +676,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-extra", action="store_true", help="headline only (profiling runs)")
+    ap.add_argument("--k4-lockstep", default=None, metavar="CLUSTER,EVERY",
+                    help="fix K4's launch form instead of letting the first call time the candidates (profiling runs: "
+                         "under ncu the timing of the candidates means nothing)")
     ap.add_argument("--sweep-panels", type=int, default=10000)
     ap.add_argument("--tiled-panels", type=int, default=4, help="1600-px panels per GPU in the tiled section")
     ap.add_argument("--tiled-steps", type=int, default=5)

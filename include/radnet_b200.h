@@ -156,6 +156,10 @@ int radnet_nms_f64(const double *boxes, const double *probs, const uint8_t *vali
 int radnet_roi_pool(const float *feat, int B, int H, int W, int C, const void *det,
                     int det_max_boxes, const int32_t *rois, const int32_t *roi_count,
                     int rois_per_panel, int pool, float *out, void *stream);
+/* The launch form radnet_roi_pool settled on for this shape on the current device (a large call times a few
+ * equivalent forms once - see option roipool_cluster): h_out3 = {float4 lanes per pixel of a slice, CTAs per
+ * cluster, barrier every n column rounds}, or {-1, -1, -1} when no call of this shape has been tuned yet. */
+int radnet_roi_pool_form(int B, int H, int W, int C, int pool, int rois_per_panel, int *h_out3);
 
 /* --------------------------------------------------- K3: RPN anchor target assignment
  * Replaces the deterministic part of calc_region_props (reference faster_rcnn/utils.py:

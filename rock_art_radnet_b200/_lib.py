@@ -39,6 +39,7 @@ SIGNATURES = {
                                c_void_p, c_size_t, c_void_p]),
     "radnet_roi_pool": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                 c_int, c_int, c_void_p, c_void_p]),
+    "radnet_roi_pool_form": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "radnet_set_option": (c_int, [ctypes.c_char_p, c_longlong]),
     "radnet_get_option": (c_int, [ctypes.c_char_p, c_void_p]),
     "radnet_rpn_targets_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

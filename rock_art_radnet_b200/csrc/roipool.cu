@@ -642,6 +642,18 @@ static int cached_choice(const TuneKey &k) {
         if (g_tune[i].key == k) return g_tune[i].choice;
     return -1;
 }
+// first tuned entry of this shape, whatever its slice width
+static bool find_shape(int dev, int B, int H, int W, int C, int pool, int R, TuneEntry *out) {
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    for (int i = 0; i < g_tune_n; ++i) {
+        const TuneKey &k = g_tune[i].key;
+        if (k.dev == dev && k.B == B && k.H == H && k.W == W && k.C == C && k.pool == pool && k.R == R) {
+            *out = g_tune[i];
+            return true;
+        }
+    }
+    return false;
+}
 static void store_choice(const TuneKey &k, int choice) {
     std::lock_guard<std::mutex> lock(g_tune_mutex);
     for (int i = 0; i < g_tune_n; ++i)
@@ -676,6 +688,21 @@ static int tune_lockstep(Launch &&go, cudaStream_t st, int *best_choice) {
 }  // namespace radnet
 
 using namespace radnet;
+
+extern "C" int radnet_roi_pool_form(int B, int H, int W, int C, int pool, int rois_per_panel, int *h_out3) {
+    RADNET_CHECK_ARG(h_out3, "roi_pool_form: null pointer");
+    int dev = 0;
+    RADNET_CUDA(cudaGetDevice(&dev));
+    TuneEntry e;
+    if (find_shape(dev, B, H, W, C, pool, rois_per_panel, &e)) {
+        h_out3[0] = e.key.lanes;
+        h_out3[1] = kLockstep[e.choice][0];
+        h_out3[2] = kLockstep[e.choice][1];
+    } else {
+        h_out3[0] = h_out3[1] = h_out3[2] = -1;
+    }
+    return RADNET_OK;
+}
 
 // option roipool_force_direct = 1 forces the direct kernel (parity tests exercise both)
 static bool force_direct() { return get_option(kOptRoipoolForceDirect) == 1; }

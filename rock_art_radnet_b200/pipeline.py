@@ -125,6 +125,13 @@ class ProposalPipeline:
                   D.ptr(out), D.stream_ptr(self.device))
         return out
 
+    def pool_form(self):
+        """The launch form K4 settled on for this shape (include/radnet_b200.h, radnet_roi_pool_form):
+        {"lanes", "cluster", "sync_every"}, or None before the first large call."""
+        out = (ctypes.c_int * 3)()
+        _lib.call("radnet_roi_pool_form", self.batch, self.H, self.W, self.channels, self.pool_size, self.max_boxes, out)
+        return None if out[0] < 0 else {"lanes": int(out[0]), "cluster": int(out[1]), "sync_every": int(out[2])}
+
     def __call__(self, cls, regr, feat):
         """cls (B,H,W,A), regr (B,H,W,4A), feat (B,H,W,C): float32 CUDA tensors.
         Returns (DetectionRecords, pooled (B,max_boxes,pool,pool,C)); nothing is synchronised."""

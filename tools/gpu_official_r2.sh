@@ -11,7 +11,13 @@ timeout 900 python tools/bench_kernels.py --out gpurun_out/kernels.json > gpurun
 RADNET_B200_LIB=rock_art_radnet_b200/_C/libradnet_b200_prof.so timeout 300 python tools/tgt_phase_profile.py 64 > gpurun_out/tgt_phase_64.log 2>&1
 RADNET_B200_LIB=rock_art_radnet_b200/_C/libradnet_b200_prof.so timeout 300 python tools/tgt_phase_profile.py 512 > gpurun_out/tgt_phase_512.log 2>&1
 # launch list + full capture of the dominant kernel on the bench command itself (64 panels, headline only)
-PROF="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-extra"
+# the launch form K4 tuned itself to in the plain run is fixed for the runs under ncu (timing candidates under a profiler means nothing)
+FORM=$(python -c "
+import json
+f=json.loads([l for l in open('gpurun_out/bench.log') if l.startswith('{')][-1])['roofline'].get('launch_form') or {}
+print('%d,%d' % (f.get('cluster', 0), f.get('sync_every', 0)))")
+echo "K4 launch form (cluster,sync_every): $FORM"
+PROF="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-extra --k4-lockstep $FORM"
 timeout 300 $PROF > gpurun_out/prof_plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_launches.log 2>&1
 timeout 300 $PROF > gpurun_out/prof_plain2.log 2>&1 && \

@@ -72,6 +72,20 @@ def main():
         elif fn.startswith("launches") and fn.endswith(".csv"):
             json.dump(launch_summary(p), open(os.path.join(OUT, "%s_%s.json" % (prefix, fn[:-4])), "w"), indent=1)
             print("wrote", fn)
+    # DRAM traffic of one full-size K4 launch for bench.py's roofline.traffic
+    pool = os.path.join(OUT, "%s_prof_pool.json" % prefix)
+    if os.path.exists(pool):
+        k = json.load(open(pool))[0]
+
+        def num(key):
+            val, unit = k[key].rsplit(" ", 1)
+            return float(val.replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
+        json.dump({"kernel": k["kernel"], "panels_per_launch": 64, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                   "source": "profiles/%s_prof_pool.json: ncu --set full --clock-control none on `bench.py --steps 2 --warmup 3 "
+                             "--no-cpu-baseline --skip-extra` with K4's tuned launch form fixed" % prefix,
+                   "traffic_bytes_per_launch": rd + wr}, open(os.path.join(OUT, "roofline_traffic.json"), "w"), indent=1)
+        print("wrote roofline_traffic.json", rd + wr)
     for fn in ("kernels.json", "bench.log", "bench_quick.log"):
         p = os.path.join(SRC, fn)
         if os.path.exists(p):

@@ -158,7 +158,8 @@ int radnet_roi_pool(const float *feat, int B, int H, int W, int C, const void *d
                     int rois_per_panel, int pool, float *out, void *stream);
 /* The launch form radnet_roi_pool settled on for this shape on the current device (a large call times a few
  * equivalent forms once - see option roipool_cluster): h_out3 = {float4 lanes per pixel of a slice, CTAs per
- * cluster, barrier every n column rounds}, or {-1, -1, -1} when no call of this shape has been tuned yet. */
+ * cluster, barrier every n column rounds}, or {-1, -1, -1} when no call of this shape has been tuned yet.  The form
+ * is per (device, H, W, C, pool, rois_per_panel); B is accepted for symmetry with radnet_roi_pool and ignored. */
 int radnet_roi_pool_form(int B, int H, int W, int C, int pool, int rois_per_panel, int *h_out3);
 
 /* --------------------------------------------------- K3: RPN anchor target assignment

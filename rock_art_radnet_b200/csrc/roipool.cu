@@ -622,10 +622,12 @@ static int tma_box_rows(int H) {
 static const int kLockstep[][2] = {{1, 0}, {1, 1}, {1, 2}, {2, 1}, {2, 2}, {2, 4}};     // {CTAs per cluster, sync_every}
 constexpr int kLockstepN = sizeof(kLockstep) / sizeof(kLockstep[0]);
 
+// the batch size is not part of the key: the form is a property of what one CTA writes (map shape, channels, pool,
+// RoIs per panel, slice width), and a ragged last batch must not be tuned afresh in the middle of a sweep
 struct TuneKey {
-    int dev, B, H, W, C, pool, R, lanes;
+    int dev, H, W, C, pool, R, lanes;
     bool operator==(const TuneKey &o) const {
-        return dev == o.dev && B == o.B && H == o.H && W == o.W && C == o.C && pool == o.pool && R == o.R && lanes == o.lanes;
+        return dev == o.dev && H == o.H && W == o.W && C == o.C && pool == o.pool && R == o.R && lanes == o.lanes;
     }
 };
 struct TuneEntry {
@@ -643,11 +645,11 @@ static int cached_choice(const TuneKey &k) {
     return -1;
 }
 // first tuned entry of this shape, whatever its slice width
-static bool find_shape(int dev, int B, int H, int W, int C, int pool, int R, TuneEntry *out) {
+static bool find_shape(int dev, int H, int W, int C, int pool, int R, TuneEntry *out) {
     std::lock_guard<std::mutex> lock(g_tune_mutex);
     for (int i = 0; i < g_tune_n; ++i) {
         const TuneKey &k = g_tune[i].key;
-        if (k.dev == dev && k.B == B && k.H == H && k.W == W && k.C == C && k.pool == pool && k.R == R) {
+        if (k.dev == dev && k.H == H && k.W == W && k.C == C && k.pool == pool && k.R == R) {
             *out = g_tune[i];
             return true;
         }
@@ -694,7 +696,8 @@ extern "C" int radnet_roi_pool_form(int B, int H, int W, int C, int pool, int ro
     int dev = 0;
     RADNET_CUDA(cudaGetDevice(&dev));
     TuneEntry e;
-    if (find_shape(dev, B, H, W, C, pool, rois_per_panel, &e)) {
+    (void)B;                        // the form does not depend on the batch size (see TuneKey)
+    if (find_shape(dev, H, W, C, pool, rois_per_panel, &e)) {
         h_out3[0] = e.key.lanes;
         h_out3[1] = kLockstep[e.choice][0];
         h_out3[2] = kLockstep[e.choice][1];
@@ -821,18 +824,14 @@ extern "C" int radnet_roi_pool(const float *feat, int B, int H, int W, int C, co
             if (cs_opt >= 0) return go(cs_opt, every_opt > 0 ? every_opt : (cs_opt > 1 ? 2 : 0));
             // automatic lockstep: measured once per (device, shape) on the caller's own buffers (the launches are
             // idempotent), never while the stream is being captured into a graph
-            const TuneKey key{dev, B, H, W, C, pool, rois_per_panel, L};
+            if (p.n_work < 4 * device_sm_count(dev)) return go(1, 0);     // too small to load HBM: free-running
+            const TuneKey key{dev, H, W, C, pool, rois_per_panel, L};
             int choice = cached_choice(key);
             if (choice < 0) {
-                const int sms = device_sm_count(dev);
                 cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
                 if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusActive;
-                if (p.n_work < 4 * sms)
-                    choice = 0;                                 // too small to load HBM: nothing to tune
-                else if (cap != cudaStreamCaptureStatusNone)
-                    return go(1, 0);                            // not cached: tuned on the first eager call
-                else if (int rc = tune_lockstep(go, st, &choice))
-                    return rc;
+                if (cap != cudaStreamCaptureStatusNone) return go(1, 0);       // not cached: tuned on the first eager call
+                if (int rc = tune_lockstep(go, st, &choice)) return rc;
                 store_choice(key, choice);
             }
             return go(kLockstep[choice][0], kLockstep[choice][1]);

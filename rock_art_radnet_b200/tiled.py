@@ -47,6 +47,8 @@ class TiledPanelRunner:
         self.ratio = torch.ones((max(self.n_local, 1),), dtype=torch.float64, device=dev)
         self.launches = 0
         self.has_pooled = alloc_pooled
+        # width of a merged panel record: final_nms / class_nms keep room for every box of the panel's T tiles
+        self.final_stride = DT.record_bytes(self.T * self.max_boxes)
 
     def chunks(self):
         """(first local slot, size, pipeline) of every chunk."""
@@ -84,9 +86,11 @@ class TiledPanelRunner:
             final = DT.class_nms(merged, n_owned, 1, self.n_cls, 0.4, max_boxes=300)
             self.launches += 2
             final_raw = final.raw
+            assert int(final_raw.shape[1]) == self.final_stride
         else:
-            final_raw = torch.zeros((0, self.tile_records.stride), dtype=torch.uint8, device=self.device)
-        self.final_stride = int(final_raw.shape[1]) if n_owned else None
+            # a rank that owns no panel (fewer panels than ranks) still takes part in the gather, with rows of the
+            # SAME width as everybody else's final records - not the (narrower) tile records
+            final_raw = torch.zeros((0, self.final_stride), dtype=torch.uint8, device=self.device)
         return self.router.gather_final(final_raw)
 
 

@@ -22,5 +22,5 @@ for ln in open('gpurun_out/scale.log'):
         print(d['n_gpus'], round(d['value']), 'panels/s  e2e', round(d['e2e']['value']), ' ms/step', round(d['ms_per_step'], 3), d['clocks'])
 PY
 if [ $NG -ge 2 ]; then
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29531 tools/check_sharded_detect.py --panels 4 2>&1 | tail -2
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29531 tools/check_sharded_detect.py --panels 4 2>&1 | tail -2
 fi

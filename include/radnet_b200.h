@@ -67,7 +67,7 @@ int radnet_device_info(int *h_out3);
  * them):  nms_cluster (-1 auto, 0 one CTA per panel), nms_cluster_size (0 auto | 2 | 4 | 8 | 16),
  * nms_cluster_ranks, nms_sel_target, nms_lookahead (0 = default), roipool_force_direct (0 | 1),
  * roipool_form (0 auto | 1 whole-map slices | 2 row bands), roipool_bands / roipool_lanes (band form: bands per map,
- * float4 lanes per pixel; 0 = auto), roipool_cluster (-1 = lockstep tuned by timing at the first large call per shape |
+ * float4 lanes per pixel, 8 | 16 | 32; whole-map form: 4 | 2 | 1 caps the slice width; 0 = auto), roipool_cluster (-1 = lockstep tuned by timing at the first large call per shape |
  * 0 none | 2 | 4 | 8 CTAs per cluster) with roipool_sync_every (barrier every n column rounds), roipool_ctas (0 = one
  * CTA per work item, else that many persistent CTAs), targets_hit_cap (0 = default),
  * targets_compute_ctas (0 = 43 % of the SMs), targets_two_launches (0 | 1: fill and panels as two

@@ -660,7 +660,13 @@ static void store_choice(const TuneKey &k, int choice) {
     std::lock_guard<std::mutex> lock(g_tune_mutex);
     for (int i = 0; i < g_tune_n; ++i)
         if (g_tune[i].key == k) { g_tune[i].choice = choice; return; }
-    if (g_tune_n < 128) g_tune[g_tune_n++] = TuneEntry{k, choice};
+    if (g_tune_n < 128) {
+        g_tune[g_tune_n++] = TuneEntry{k, choice};
+    } else {                                        // table full: recycle the slots round robin rather than re-tune forever
+        static int next = 0;
+        g_tune[next] = TuneEntry{k, choice};
+        next = (next + 1) % 128;
+    }
 }
 
 template <typename Launch>

@@ -229,6 +229,50 @@ __device__ __forceinline__ void pool_column(const unsigned char *mapb, const YEn
     }
 }
 
+// Two neighbouring output columns (roi, px) and (roi, px + 1) at once: they share the RoI's y table, so the table
+// entry, its decoding and the branches on it are paid once per pair of 16-byte stores, and the two columns' taps
+// and lerps are independent work the scheduler can overlap.  has_b = false: the pair has only its first column
+// (odd pool sizes); the caller makes column B shadow column A and its stores are skipped.
+template <int POOL>
+__device__ __forceinline__ void pool_column_pair(const unsigned char *mapb, const YEntry *yt, int npy, unsigned xa0,
+                                                 unsigned xa1, float lxa, unsigned xb0, unsigned xb1, float lxb,
+                                                 bool has_b, unsigned row_step, float4 *dst, size_t px_step,
+                                                 size_t py_step, unsigned long long nz) {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+    const unsigned char *ta0 = mapb + xa0, *ta1 = mapb + xa1, *tb0 = mapb + xb0, *tb1 = mapb + xb1;
+    auto ld = [](const unsigned char *p) { return *reinterpret_cast<const float4 *>(p); };
+    auto body = [&](int py) {
+        const YEntry e = yt[py];
+        if ((int)e.code < 0) {
+            const unsigned off = e.code & kRowOffMask;
+            if (e.code & kRowS0) {
+                a0 = lerp4(ld(ta0 + off), ld(ta1 + off), lxa, nz);
+                b0 = lerp4(ld(tb0 + off), ld(tb1 + off), lxb, nz);
+            } else if (e.code & kRowShift) {
+                a0 = a1;
+                b0 = b1;
+            }
+            if (e.code & kRowS1) {
+                a1 = lerp4(ld(ta0 + off + row_step), ld(ta1 + off + row_step), lxa, nz);
+                b1 = lerp4(ld(tb0 + off + row_step), ld(tb1 + off + row_step), lxb, nz);
+            } else if (e.code & kRowDup) {
+                a1 = a0;
+                b1 = b0;
+            }
+        }
+        st_pool_f4(dst, lerp4(a0, a1, e.lerp, nz));
+        if (has_b) st_pool_f4(dst + px_step, lerp4(b0, b1, e.lerp, nz));
+        dst += py_step;
+    };
+    if (POOL > 0) {
+#pragma unroll
+        for (int py = 0; py < POOL; ++py) body(py);
+    } else {
+#pragma unroll 2
+        for (int py = 0; py < npy; ++py) body(py);
+    }
+}
+
 // x taps of output column px of a RoI that is cw cells wide and starts at cell x (TF-1 legacy weights with the
 // float32 scale cw/pool taken from a table); cw == 0 marks an empty slot: both taps on the zero pixel
 __device__ __forceinline__ void x_taps(int px, int x, int cw, const float *s_scale, unsigned pix_bytes,
@@ -331,15 +375,49 @@ __global__ void __launch_bounds__(kSliceThreads, 1) roi_pool_slice_kernel(RoiPoo
             map_ready = true;
         }
 
+        if (LANES == 8) {
+        // 32-channel slices: a group takes PAIRS of neighbouring columns (px, px + 1) - measured 0.87 -> 0.92 of the HBM
+        // peak on 7x7x512, 0.956 -> 0.963 sustained on 14x14x1024; on 16-channel slices (38x50 maps) pairs measured
+        // 0.89 against 0.95 for single columns, so narrower slices keep one column per group
+        // ppair pairs per RoI, the last one single when pool is odd; (rl, k) advance incrementally by G pairs: no
+        // integer division in the loop
+        const int ppair = (pool + 1) >> 1;
+        const int npair = nr * ppair;
+        int rl = g / ppair, k = g - rl * ppair;
+        const int d_rl = G / ppair, d_k = G - d_rl * ppair;
+        int it = 0;
+        for (int base = 0; base < npair; base += G, rl += d_rl, k += d_k, ++it) {
+            // lockstep: the warps of the CTA (and, in a cluster, the CTAs of neighbouring channel slices of the same
+            // panel) are kept within `sync_every` rounds of each other, so that what the SM writes at any moment stays
+            // within a few RoIs - see the launcher for the measured effect
+            if (p.sync_every > 0 && it % p.sync_every == 0) {
+                if (p.cluster > 1) cluster_sync_relaxed();
+                else __syncthreads();
+            }
+            if (k >= ppair) { k -= ppair; ++rl; }
+            if (base + g >= npair) continue;
+            const int2 rx = s_roi[rl];
+            const int px = 2 * k;
+            const bool has_b = px + 1 < pool;
+            unsigned xa0, xa1, xb0, xb1;
+            float lxa, lxb;
+            x_taps(px, rx.x, rx.y, s_scale, kPixBytes, (unsigned)HWp * kPixBytes, xa0, xa1, lxa);
+            if (has_b) {
+                x_taps(px + 1, rx.x, rx.y, s_scale, kPixBytes, (unsigned)HWp * kPixBytes, xb0, xb1, lxb);
+            } else {               // single column: B shadows A (valid addresses for every row offset, nothing stored)
+                xb0 = xa0; xb1 = xa1; lxb = lxa;
+            }
+            float4 *dst = reinterpret_cast<float4 *>(p.out) +
+                          (((size_t)b * p.R + r0 + rl) * PP + px) * C4 + (size_t)s * LANES + q;
+            pool_column_pair<POOL>(mapb, s_ytab + rl * pool, pool, xa0, xa1, lxa, xb0, xb1, lxb, has_b, row_step, dst,
+                                   (size_t)C4, py_step, nz);
+        }
+        } else {
         const int ncol = nr * pool;
-        // (rl, px) advance incrementally by G columns: no integer division in the column loop
         int rl = g / pool, px = g - rl * pool;
         const int d_rl = G / pool, d_px = G - d_rl * pool;
         int it = 0;
         for (int base = 0; base < ncol; base += G, rl += d_rl, px += d_px, ++it) {
-            // lockstep: the warps of the CTA (and, in a cluster, the CTAs of neighbouring channel slices of the same
-            // panel) are kept within `sync_every` column rounds of each other, so that what the SM writes at any
-            // moment stays within a few RoIs - see the launcher for the measured effect
             if (p.sync_every > 0 && it % p.sync_every == 0) {
                 if (p.cluster > 1) cluster_sync_relaxed();
                 else __syncthreads();
@@ -353,6 +431,7 @@ __global__ void __launch_bounds__(kSliceThreads, 1) roi_pool_slice_kernel(RoiPoo
             float4 *dst = reinterpret_cast<float4 *>(p.out) +
                           (((size_t)b * p.R + r0 + rl) * PP + px) * C4 + (size_t)s * LANES + q;
             pool_column<POOL>(mapb, s_ytab + rl * pool, 0, pool, xo0, xo1, lx, row_step, dst, py_step, nz);
+        }
         }
     }
     }   // work items

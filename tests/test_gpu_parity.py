@@ -197,11 +197,13 @@ def test_calc_region_props_matches_reference_golden(pkg, manifest, golden_a3):
     assert pkg.calc_rpn is pkg.calc_region_props
 
 
-@pytest.mark.parametrize("fill_bulk", [0, 1, 4096])
-def test_rpn_targets_batched_presample_vs_oracle(pkg, lib_option, fill_bulk):
-    """fill_bulk > 0: the regression zeros are streamed by TMA bulk copies that every CTA of the launch shares out."""
+@pytest.mark.parametrize("fill_bulk,two_launches", [(0, 0), (1, 0), (4096, 0), (0, 1), (1, 1)])
+def test_rpn_targets_batched_presample_vs_oracle(pkg, lib_option, fill_bulk, two_launches):
+    """fill_bulk > 0: the regression zeros are streamed by TMA bulk copies that every CTA of the launch shares out;
+    two_launches: the fill and the panels as two launches (no co-residency assumed)."""
     from rock_art_radnet_b200.utils import rpn_targets_device
     lib_option("targets_fill_bulk", fill_bulk)
+    lib_option("targets_two_launches", two_launches)
     C = S.HotPathConfig((64, 128, 256, 512))          # 12 anchors
     sizes = [(600, 600, 20), (800, 600, 9), (600, 750, 33), (600, 600, 0)]
     B, Gmax = len(sizes), 33

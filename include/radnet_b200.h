@@ -71,7 +71,8 @@ int radnet_device_info(int *h_out3);
  * 0 none | 2 | 4 | 8 CTAs per cluster) with roipool_sync_every (barrier every n column rounds), roipool_ctas (0 = one
  * CTA per work item, else that many persistent CTAs), targets_hit_cap (0 = default),
  * targets_compute_ctas (0 = 43 % of the SMs), targets_two_launches (0 | 1: fill and panels as two
- * launches, no co-residency assumed), sampler_force_exact (0 | 1). */
+ * launches, no co-residency assumed), targets_fill_bulk (0 plain stores | 1 regression zeros by TMA bulk copies
+ * shared out over all CTAs | n = size of the zero buffer), sampler_force_exact (0 | 1). */
 int radnet_set_option(const char *h_name, long long value);
 int radnet_get_option(const char *h_name, long long *h_value);
 

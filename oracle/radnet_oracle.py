@@ -21,7 +21,9 @@ Parity pinning
   published TF-1 legacy `ResizeBilinear` CPU kernel (align_corners=False, no
   half-pixel centres; tensorflow/core/kernels/resize_bilinear_op.cc and
   image_resizer_state.h, TF ~1.13-1.15, version unpinned by the reference) and is
-  cross-checked against an independent float64 bilinear evaluation
+  cross-checked against an independent float64 bilinear evaluation and against
+  OpenCV-DNN's import of a hand-encoded TF `ResizeBilinear` GraphDef - an
+  independent implementation of the TF op - to 2e-6 relative
   (`tests/test_oracle_roipool.py`).
 
 Score ties: the reference orders candidates with `np.argsort` (default,

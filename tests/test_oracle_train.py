@@ -90,3 +90,38 @@ def test_loss_restatements_against_float64_formulas():
     want = (-(Y1[0] * np.log(o)).sum(-1)).mean()
     got = T.class_loss_cls(Y1, q_cls)
     assert abs(got - want) <= 1e-5 * abs(want)
+
+
+def test_loss_restatements_against_torch_library_functions():
+    """The Keras/TF backend calls `losses.py` composes have library counterparts in torch with the same published
+    definitions: tf.nn.sigmoid_cross_entropy_with_logits = F.binary_cross_entropy_with_logits (max(x,0) - x*z +
+    log(1+exp(-|x|))), the reference's hand-written smooth-L1 = F.smooth_l1_loss(beta=1), categorical cross-entropy =
+    NLL of the log of the re-normalised, clipped probabilities.  Not Keras itself (not installable: the losses stay
+    'parity unpinned'), but an independent implementation of every building block."""
+    import torch
+    import torch.nn.functional as F
+    y_cls, y_regr, p_cls, p_regr, Y1, Y2, q_cls, q_regr = loss_inputs(3)
+    A, n_cls = 9, 7
+    t64 = lambda a: torch.from_numpy(np.asarray(a)).double()
+    # rpn_loss_cls (losses.py:63-65): K.binary_crossentropy(y_pred, label) -> logits from the CLIPPED LABEL
+    lab = torch.from_numpy(np.clip(y_cls[..., A:], 1e-7, 1 - 1e-7).astype(np.float32)).double()
+    logits = torch.log(lab / (1 - lab))
+    bce = F.binary_cross_entropy_with_logits(logits, t64(p_cls), reduction="none")
+    valid = t64(y_cls[..., :A])
+    want = float((valid * bce).sum() / (1e-4 + valid).sum())
+    got = float(T.rpn_loss_cls(A)(y_cls, p_cls))
+    assert abs(got - want) <= 2e-5 * abs(want)
+    # smooth-L1 (losses.py:31-42, 79-86)
+    for y_true, pred, n4 in ((y_regr, p_regr, 4 * A), (Y2, q_regr, 4 * (n_cls - 1))):
+        mask, tgt = t64(y_true[..., :n4]), t64(y_true[..., n4:].astype(np.float32))
+        sl1 = F.smooth_l1_loss(t64(pred), tgt, beta=1.0, reduction="none")
+        want = float((mask * sl1).sum() / (1e-4 + mask).sum())
+        fn = T.rpn_loss_regr(A) if n4 == 4 * A else T.class_loss_regr(n_cls - 1)
+        got = float(fn(y_true, pred))
+        assert abs(got - want) <= 1e-5 * abs(want)
+    # class_loss_cls (losses.py:93-95)
+    o = t64(q_cls[0])
+    o = torch.clamp(o / o.sum(-1, keepdim=True), 1e-7, 1 - 1e-7)
+    want = float(F.nll_loss(torch.log(o), torch.from_numpy(Y1[0].argmax(-1)), reduction="mean"))
+    got = float(T.class_loss_cls(Y1, q_cls))
+    assert abs(got - want) <= 1e-5 * abs(want)

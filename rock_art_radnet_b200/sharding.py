@@ -130,8 +130,12 @@ class OwnerRoutedTiles:
     The schedule (who sends which slots to whom, in which order they arrive) is a pure function of
     (n_panels, T, world) and is built once on the host.  world == 1 needs no process group."""
 
-    def __init__(self, n_panels, tiles_per_panel, rank=None, world=None, group=None, device=None):
+    def __init__(self, n_panels, tiles_per_panel, rank=None, world=None, group=None, device=None, final_stride=None):
         self.group = group
+        # width in bytes of one merged (final) panel record.  Every rank must gather rows of the SAME width, also a
+        # rank that owns no panel (fewer panels than ranks) and therefore has no merged record to take it from: give
+        # it here and a mismatch is an error instead of a hung collective
+        self.final_stride = None if final_stride is None else int(final_stride)
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
             rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -185,8 +189,18 @@ class OwnerRoutedTiles:
         return recv.index_select(0, self._to_panel_order)
 
     def gather_final(self, final_records):
-        """final_records: (len(owned), stride) uint8, one merged record per owned panel, ascending panel id.
-        Returns (n_panels, stride) in global panel order on every rank (one all-gather of max_owned records)."""
+        """final_records: (len(owned), stride) uint8, one merged record per owned panel, ascending panel id (None on a
+        rank that owns no panel, when `final_stride` was given).  Returns (n_panels, stride) in global panel order on
+        every rank (one all-gather of max_owned records)."""
+        if final_records is None:
+            if self.final_stride is None:
+                raise ValueError("gather_final(None) needs OwnerRoutedTiles(final_stride=...)")
+            final_records = torch.zeros((0, self.final_stride), dtype=torch.uint8, device=self._final_order.device)
+        if self.final_stride is not None and int(final_records.shape[1]) != self.final_stride:
+            raise ValueError("gather_final: records of %d bytes, every rank gathers %d" % (int(final_records.shape[1]),
+                                                                                          self.final_stride))
+        if int(final_records.shape[0]) != len(self.owned):
+            raise ValueError("gather_final: %d records for %d owned panels" % (int(final_records.shape[0]), len(self.owned)))
         if self.world == 1:
             return final_records
         pad = self.max_owned - int(final_records.shape[0])

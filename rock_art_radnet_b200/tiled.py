@@ -27,7 +27,10 @@ class TiledPanelRunner:
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         dev = self.device
         self.C, self.tiles, self.T = C, list(tiles), len(tiles)
-        self.router = sharding.OwnerRoutedTiles(n_panels, self.T, rank=rank, world=world, group=group, device=dev)
+        # width of a merged panel record: final_nms / class_nms keep room for every box of the panel's T tiles
+        self.final_stride = DT.record_bytes(self.T * int(max_boxes))
+        self.router = sharding.OwnerRoutedTiles(n_panels, self.T, rank=rank, world=world, group=group, device=dev,
+                                                final_stride=self.final_stride)
         self.rank, self.world, self.n_panels = self.router.rank, self.router.world, int(n_panels)
         self.local_ids = self.router.local_ids
         self.n_local = len(self.local_ids)
@@ -47,8 +50,6 @@ class TiledPanelRunner:
         self.ratio = torch.ones((max(self.n_local, 1),), dtype=torch.float64, device=dev)
         self.launches = 0
         self.has_pooled = alloc_pooled
-        # width of a merged panel record: final_nms / class_nms keep room for every box of the panel's T tiles
-        self.final_stride = DT.record_bytes(self.T * self.max_boxes)
 
     def chunks(self):
         """(first local slot, size, pipeline) of every chunk."""
@@ -86,11 +87,10 @@ class TiledPanelRunner:
             final = DT.class_nms(merged, n_owned, 1, self.n_cls, 0.4, max_boxes=300)
             self.launches += 2
             final_raw = final.raw
-            assert int(final_raw.shape[1]) == self.final_stride
         else:
             # a rank that owns no panel (fewer panels than ranks) still takes part in the gather, with rows of the
             # SAME width as everybody else's final records - not the (narrower) tile records
-            final_raw = torch.zeros((0, self.final_stride), dtype=torch.uint8, device=self.device)
+            final_raw = None
         return self.router.gather_final(final_raw)
 
 

@@ -107,8 +107,8 @@ def _owner_worker(rank, world, port, n_panels, T, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from rock_art_radnet_b200 import sharding
-    router = sharding.OwnerRoutedTiles(n_panels, T)
-    stride = 32
+    stride, final_stride = 32, 80            # merged panel records are wider than tile records, as in the real path
+    router = sharding.OwnerRoutedTiles(n_panels, T, final_stride=final_stride)
     raw = torch.zeros((len(router.local_ids), stride), dtype=torch.uint8)
     for slot, g in enumerate(router.local_ids):
         raw[slot, 0] = int(g) // T            # panel
@@ -119,12 +119,18 @@ def _owner_worker(rank, world, port, n_panels, T, out_dir):
     want = [(int(p), t) for p in router.owned for t in range(T)]
     ok &= [(int(r[0]), int(r[1])) for r in got] == want                     # (owned panel, tile) order
     ok &= all(int(r[2]) == (int(r[0]) * T + int(r[1])) % world for r in got)   # each came from the rank that held it
-    final = torch.zeros((len(router.owned), stride), dtype=torch.uint8)
+    final = torch.zeros((len(router.owned), final_stride), dtype=torch.uint8)
     for i, p in enumerate(router.owned):
         final[i, 0] = int(p)
         final[i, 1] = 100 + rank
-    glob = router.gather_final(final)
-    ok &= tuple(glob.shape) == (n_panels, stride) and glob[:, 0].tolist() == list(range(n_panels))
+    try:                                      # rows of the tile-record width (the bug class that hangs a real gather)
+        router.gather_final(torch.zeros((len(router.owned), stride), dtype=torch.uint8))
+        ok = False
+    except ValueError:
+        pass
+    # a rank that owns no panel has no merged record to take the width from: it passes None
+    glob = router.gather_final(final if len(router.owned) else None)
+    ok &= tuple(glob.shape) == (n_panels, final_stride) and glob[:, 0].tolist() == list(range(n_panels))
     ok &= glob[:, 1].tolist() == [100 + p % world for p in range(n_panels)]
     np.save(os.path.join(out_dir, "owner_ok_%d.npy" % rank), np.array([int(ok)]))
     dist.barrier()

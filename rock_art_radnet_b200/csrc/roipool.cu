@@ -141,7 +141,7 @@ __device__ __forceinline__ float lerp1(float a, float b, float t) {
 // with an addend of -0.0 (d*t + (-0.0) rounds exactly like d*t, signed zeros included; the -0.0 comes from a
 // kernel parameter so that ptxas cannot fold it away), and an FMA result feeding an add cannot be fused again:
 // FADD2 (b-a), FFMA2 (d*t - 0), FADD2 (a + m).  tests/test_build_sass.py checks that the kernels contain no
-// scalar FFMA and no FMUL2; the parity tests check the bits.
+// FMUL2 and exactly two FADD2 per FFMA2 (a contraction would trade an FADD2 for an FFMA2); the parity tests check the bits.
 __device__ __forceinline__ void lerp2(float a0, float a1, float b0, float b1, unsigned long long tt,
                                       unsigned long long nz, float &r0, float &r1) {
     unsigned long long a, b, d, m, r;

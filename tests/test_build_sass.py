@@ -29,14 +29,14 @@ def test_sm100a_and_no_contracted_multiply_add_in_roi_pool():
     assert len(pool) >= 5
     for name, lines in pool.items():
         # TF computes a + (b-a)*t with separate multiply and add.  ptxas 12.9 contracts a packed multiply feeding a
-        # packed add into FFMA2, so the kernels issue the PRODUCT as a packed FMA whose addend is -0.0 held in a
-        # uniform register (d*t + (-0.0) == d*t exactly) and add with a separate FADD2 (see roipool.cu): there must
-        # be no packed multiply left that could be contracted, and every FFMA2 must be of that form
-        for ln in lines:
-            assert "FMUL2" not in ln, (name, ln)
-            if "FFMA2" in ln:
-                ops = ln.split("FFMA2")[1].split(";")[0].split(",")
-                assert ops[-1].strip().startswith("UR"), (name, ln)
+        # packed add into FFMA2, so the kernels issue the PRODUCT as a packed FMA whose addend is an opaque -0.0
+        # (d*t + (-0.0) == d*t exactly) and add with a separate FADD2 (see roipool.cu).  Every lerp of two lanes is
+        # then FADD2 (b-a), FFMA2 (d*t - 0), FADD2 (a + m): no packed multiply may be left that could be contracted,
+        # and a contraction would turn one of the FADD2 into an extra FFMA2 - so the counts must be exactly 2 : 1
+        text = "\n".join(lines)
+        assert "FMUL2" not in text, name
+        n_add, n_fma = text.count("FADD2"), text.count("FFMA2")
+        assert n_add == 2 * n_fma, (name, n_add, n_fma)
     slice8 = "\n".join(next(v for k, v in pool.items() if "slice_kernelILi8ELi14" in k))
     assert "FFMA2" in slice8 and "FADD2" in slice8          # packed f32x2 math is in use
     assert "UTMALDG.4D" in slice8                           # TMA tensor copy of the map slice (cp.async.bulk.tensor.4d)
